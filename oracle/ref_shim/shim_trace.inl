@@ -1,0 +1,186 @@
+// oracle/ref_shim/shim_trace.inl — TEST INFRASTRUCTURE (see optix.h in this directory).
+//
+// Included AFTER the reference's forward.cu / backward.cu in the same translation unit, so that
+// `params` (forward.cu:21-23 / backward.cu:22-24), `__raygen__ot` and `__anyhit__ot` are visible.
+// Provides: the OptiX stand-in's optixTrace (all triangle hits in (tmin, tmax) -> __anyhit__ot),
+// a median-split BVH over the proxy triangles so large scenes stay tractable on a CPU, and
+// shim_launch (the optixLaunch(H, W, 1) stand-in, trace_surfels.cpp:256,378).
+
+#include <vector>
+#include <numeric>
+#include <omp.h>
+
+thread_local ShimThreadState shim_ts;
+
+namespace shim {
+
+struct Box { float lo[3], hi[3]; };
+struct Node { Box b; int left, right, first, count; };   // leaf iff count > 0
+
+static std::vector<Node> g_nodes;
+static std::vector<int> g_tri;          // triangle ids in leaf order
+static const float3* g_verts = nullptr;
+static int g_ntri = 0;
+static bool g_brute = false;
+
+// triangle t of build2DRectangle: even -> (4g, 4g+1, 4g+2); odd -> (4g+2, 4g+3, 4g+1)
+// (primitive_utils.py:212-221)
+static inline void tri_verts(int t, const float3*& a, const float3*& b, const float3*& c)
+{
+    const int g = t >> 1;
+    if ((t & 1) == 0) { a = g_verts + 4 * g; b = g_verts + 4 * g + 1; c = g_verts + 4 * g + 2; }
+    else              { a = g_verts + 4 * g + 2; b = g_verts + 4 * g + 3; c = g_verts + 4 * g + 1; }
+}
+
+static inline Box tri_box(int t)
+{
+    const float3 *a, *b, *c; tri_verts(t, a, b, c);
+    Box bx;
+    const float xs[3] = {a->x, b->x, c->x}, ys[3] = {a->y, b->y, c->y}, zs[3] = {a->z, b->z, c->z};
+    bx.lo[0] = std::min({xs[0], xs[1], xs[2]}); bx.hi[0] = std::max({xs[0], xs[1], xs[2]});
+    bx.lo[1] = std::min({ys[0], ys[1], ys[2]}); bx.hi[1] = std::max({ys[0], ys[1], ys[2]});
+    bx.lo[2] = std::min({zs[0], zs[1], zs[2]}); bx.hi[2] = std::max({zs[0], zs[1], zs[2]});
+    return bx;
+}
+
+static inline bool box_valid(const Box& b)
+{
+    for (int k = 0; k < 3; k++) if (!(b.lo[k] <= b.hi[k])) return false;   // NaN verts (opacity<1/255)
+    return true;
+}
+
+static int build_rec(int first, int count, const std::vector<Box>& tb, const std::vector<float3>& cen)
+{
+    Node n; n.left = n.right = -1; n.first = first; n.count = 0;
+    for (int k = 0; k < 3; k++) { n.b.lo[k] = 1e30f; n.b.hi[k] = -1e30f; }
+    float clo[3] = {1e30f, 1e30f, 1e30f}, chi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = first; i < first + count; i++) {
+        const Box& b = tb[g_tri[i]];
+        const float c[3] = {cen[g_tri[i]].x, cen[g_tri[i]].y, cen[g_tri[i]].z};
+        for (int k = 0; k < 3; k++) {
+            n.b.lo[k] = std::min(n.b.lo[k], b.lo[k]); n.b.hi[k] = std::max(n.b.hi[k], b.hi[k]);
+            clo[k] = std::min(clo[k], c[k]); chi[k] = std::max(chi[k], c[k]);
+        }
+    }
+    const int id = (int)g_nodes.size();
+    g_nodes.push_back(n);
+    int axis = 0;
+    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+    if (count <= 8 || !(chi[axis] > clo[axis])) { g_nodes[id].count = count; return id; }
+    const int mid = first + count / 2;
+    std::nth_element(g_tri.begin() + first, g_tri.begin() + mid, g_tri.begin() + first + count,
+                     [&](int a, int b) {
+                         const float ca = axis == 0 ? cen[a].x : axis == 1 ? cen[a].y : cen[a].z;
+                         const float cb = axis == 0 ? cen[b].x : axis == 1 ? cen[b].y : cen[b].z;
+                         return ca < cb;
+                     });
+    const int l = build_rec(first, mid - first, tb, cen);
+    const int r = build_rec(mid, first + count - mid, tb, cen);
+    g_nodes[id].left = l; g_nodes[id].right = r;
+    return id;
+}
+
+static void build(const float3* verts, int ntri)
+{
+    g_verts = verts; g_ntri = ntri;
+    g_nodes.clear(); g_tri.clear();
+    const char* e = getenv("ORC_REF_BRUTE");
+    g_brute = (e && e[0] == '1') || ntri <= 64;
+    if (g_brute) return;
+    std::vector<Box> tb(ntri);
+    std::vector<float3> cen(ntri);
+    for (int t = 0; t < ntri; t++) {
+        tb[t] = tri_box(t);
+        if (!box_valid(tb[t])) continue;      // never hit by anything
+        cen[t] = make_float3(0.5f * (tb[t].lo[0] + tb[t].hi[0]), 0.5f * (tb[t].lo[1] + tb[t].hi[1]),
+                             0.5f * (tb[t].lo[2] + tb[t].hi[2]));
+        g_tri.push_back(t);
+    }
+    if (g_tri.empty()) { g_brute = true; return; }
+    g_nodes.reserve(g_tri.size() / 2 + 16);
+    build_rec(0, (int)g_tri.size(), tb, cen);
+}
+
+// Double-precision Moeller-Trumbore, no back-face culling (OptiX default for this pipeline:
+// OPTIX_RAY_FLAG_NONE, forward.cu:58). Returns t or a negative number.
+static inline double tri_hit(const float3& o, const float3& d, const float3& A, const float3& B, const float3& C)
+{
+    const double e1[3] = {(double)B.x - A.x, (double)B.y - A.y, (double)B.z - A.z};
+    const double e2[3] = {(double)C.x - A.x, (double)C.y - A.y, (double)C.z - A.z};
+    const double dd[3] = {d.x, d.y, d.z};
+    const double p[3] = {dd[1] * e2[2] - dd[2] * e2[1], dd[2] * e2[0] - dd[0] * e2[2], dd[0] * e2[1] - dd[1] * e2[0]};
+    const double det = e1[0] * p[0] + e1[1] * p[1] + e1[2] * p[2];
+    if (!(det != 0.0)) return -1.0;
+    const double inv = 1.0 / det;
+    const double s[3] = {(double)o.x - A.x, (double)o.y - A.y, (double)o.z - A.z};
+    const double u = (s[0] * p[0] + s[1] * p[1] + s[2] * p[2]) * inv;
+    if (!(u >= 0.0 && u <= 1.0)) return -1.0;
+    const double q[3] = {s[1] * e1[2] - s[2] * e1[1], s[2] * e1[0] - s[0] * e1[2], s[0] * e1[1] - s[1] * e1[0]};
+    const double v = (dd[0] * q[0] + dd[1] * q[1] + dd[2] * q[2]) * inv;
+    if (!(v >= 0.0 && u + v <= 1.0)) return -1.0;
+    return (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]) * inv;
+}
+
+static inline void report(int t, const float3& o, const float3& d, float tmin, float tmax)
+{
+    const float3 *a, *b, *c; tri_verts(t, a, b, c);
+    const double th = tri_hit(o, d, *a, *b, *c);
+    const float tf = (float)th;
+    if (th > 0.0 && tf > tmin && tf < tmax) {
+        shim_ts.cur_tmax = tf;
+        shim_ts.cur_prim = (unsigned)t;
+        __anyhit__ot();
+    }
+}
+
+static inline bool ray_box(const Box& b, const float3& o, const float inv[3], float tmax)
+{
+    const float oo[3] = {o.x, o.y, o.z};
+    float t0 = 0.0f, t1 = tmax;
+    for (int k = 0; k < 3; k++) {
+        // widen a little: the BVH is only a candidate filter, the triangle test decides
+        const float pad = 1e-4f + 1e-5f * std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+        float a = (b.lo[k] - pad - oo[k]) * inv[k], c = (b.hi[k] + pad - oo[k]) * inv[k];
+        if (a > c) std::swap(a, c);
+        if (a != a || c != c) continue;           // 0 * inf: ray origin on the slab plane
+        t0 = std::max(t0, a); t1 = std::min(t1, c);
+    }
+    return t0 <= t1 * 1.00001f + 1e-6f;
+}
+
+} // namespace shim
+
+void optixTrace(OptixTraversableHandle, float3 ray_o, float3 ray_d, float tmin, float tmax,
+                float, OptixVisibilityMask, unsigned int, unsigned int, unsigned int, unsigned int,
+                unsigned int& p0, unsigned int& p1)
+{
+    shim_ts.payload0 = p0; shim_ts.payload1 = p1;
+    if (shim::g_brute) {
+        for (int t = 0; t < shim::g_ntri; t++) shim::report(t, ray_o, ray_d, tmin, tmax);
+        return;
+    }
+    const float inv[3] = {1.0f / ray_d.x, 1.0f / ray_d.y, 1.0f / ray_d.z};
+    int stack[128]; int sp = 0; stack[sp++] = 0;
+    while (sp) {
+        const shim::Node& n = shim::g_nodes[stack[--sp]];
+        if (!shim::ray_box(n.b, ray_o, inv, tmax)) continue;
+        if (n.count > 0) {
+            for (int i = n.first; i < n.first + n.count; i++) shim::report(shim::g_tri[i], ray_o, ray_d, tmin, tmax);
+        } else {
+            stack[sp++] = n.left; stack[sp++] = n.right;
+        }
+    }
+}
+
+// optixLaunch(pipeline, stream, d_params, sizeof(Params), &sbt, H, W, 1) stand-in.
+static void shim_launch(int H, int W)
+{
+    shim::build(params.vertices, 2 * params.P);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < H * W; i++) {
+        shim_ts.launch_index = make_uint3(i / W, i % W, 0);
+        shim_ts.launch_dims = make_uint3(H, W, 1);
+        __raygen__ot();
+    }
+}
