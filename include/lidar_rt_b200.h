@@ -1,0 +1,115 @@
+/*
+ * lidar_rt_b200.h — C ABI of the B200-native differentiable LiDAR Gaussian ray tracer.
+ *
+ * This is the drop-in boundary for the ONE hot path of zju3dv/LiDAR-RT: everything that sits
+ * behind the reference's pybind11 module `diff_lidar_tracer._C`
+ * (submodules/diff-lidar-tracer/ext.cpp:17-22, trace_surfels.h:21-77). Plain pointers, sizes and
+ * a cudaStream_t (as void*); no torch types. All pointers are DEVICE pointers on the context's
+ * device unless stated otherwise; all floats are fp32; tensors are dense row-major.
+ *
+ * Error model: every function returns 0 on success or a negative lrt_status; the message is
+ * available from lrt_last_error(). (The reference only prints CUDA/OptiX failures —
+ * optix_tracer/common.h:38-50 — here they are returned.)
+ *
+ * Threading: a context is thread-compatible (one call at a time per context). Calls enqueue work
+ * on `stream` and do not synchronise the device (the reference ends every call with
+ * cudaStreamSynchronize, trace_surfels.cpp:260,382). Workspace growth may call cudaMalloc.
+ */
+#ifndef LIDAR_RT_B200_H
+#define LIDAR_RT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRT_VERSION 100
+#define LRT_NUM_CHANNELS 9        /* optix_tracer/config.h:19-24: rgb(3) depth accum normal(3) finalT */
+#define LRT_CHUNK 16              /* optix_tracer/config.h:16 CHUNK_SIZE */
+
+typedef struct lrt_ctx lrt_ctx;
+
+enum lrt_status {
+    LRT_OK = 0,
+    LRT_ERR_INVALID = -1,         /* bad argument (the reference raises via AT_ERROR, trace_surfels.cpp:53-58) */
+    LRT_ERR_CUDA = -2,            /* a CUDA runtime call failed */
+    LRT_ERR_STATE = -3            /* no acceleration structure / size mismatch with the built one */
+};
+
+enum lrt_flags {
+    LRT_FLAG_FIX_BG_GRAD = 1      /* drop the duplicated background term of backward.cu:595-598 */
+};
+
+/* Replaces _C.OptiXStateWrapper(pkg_dir) (optix_wrapper.cpp:177-233): creates the per-device
+ * context that owns the acceleration structure and workspace. */
+int lrt_ctx_create(int device, lrt_ctx** out_ctx);
+int lrt_ctx_destroy(lrt_ctx* ctx);
+/* Message of the last failing call on this context (ctx == NULL: last lrt_ctx_create failure). */
+const char* lrt_last_error(const lrt_ctx* ctx);
+int lrt_version(void);
+
+/* Replaces build2DRectangle (lib/utils/primitive_utils.py:182-224) + _C.build_acceleration_structure
+ * with rebuild=1 (trace_surfels.cpp:46-148): derives the proxy quad of every Gaussian straight from
+ * its parameters and builds the LBVH (Morton sort + 8-wide implicit hierarchy) over the quad AABBs.
+ *   means (P,3)  scales (P,2) >0  rots (P,4) w-first, need not be unit  opac (P) in (0,1)
+ * The arrays are only read during the call. */
+int lrt_build(lrt_ctx* ctx, int P, const float* means, const float* scales, const float* rots,
+              const float* opac, float scale_modifier, void* stream);
+
+/* The rebuild=0 / OPTIX_BUILD_OPERATION_UPDATE path (trace_surfels.cpp:70-73): keeps the Morton
+ * order of the last lrt_build and recomputes records and boxes bottom-up. Same P required. */
+int lrt_refit(lrt_ctx* ctx, int P, const float* means, const float* scales, const float* rots,
+              const float* opac, float scale_modifier, void* stream);
+
+/* Replaces _C.trace_surfels (trace_surfels.cpp:151-265; device program forward.cu:146-356).
+ *   R rays; ray_o_stride = 3 (origins (R,3)) or 0 (one shared origin — the expanded stride-0 view
+ *   LiDARSensor.get_range_rays returns, lidar_sensor.py:400); ray_d (R,3); bg (3) device.
+ *   Gaussian arrays as given to lrt_build/lrt_refit (same values); shs (P,M,3); D = active degree.
+ * Outputs (written entirely by the call):
+ *   out (R,9)           channel map of config.h:19-24
+ *   accum_w (P)         sum of blending weights per Gaussian (forward.cu:272)
+ *   hit_gidx, hit_t     optional, (cap,R) each: contributing Gaussian ids (caller's indexing) and
+ *                       depths in compositing order, slot k of ray r at [k*R + r]
+ *   hit_cnt (R)         optional: number of contributing hits (may exceed cap; list is truncated)
+ *   slot_cnt (R)        optional: k-buffer slots consumed (evaluated proxy hits)
+ */
+int lrt_forward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
+                const float* bg, int P, const float* means, const float* scales, const float* rots,
+                const float* opac, const float* shs, int D, int M, float scale_modifier,
+                float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, int32_t* hit_cnt,
+                int cap, int32_t* slot_cnt, void* stream);
+
+/* Replaces _C.trace_surfels_backward (trace_surfels.cpp:268-386; backward.cu:434-691).
+ * fwd_out / dL_dout (R,9). If hit lists from the forward are given, rays with hit_cnt <= cap are
+ * replayed from the list (no traversal); the others — or all rays when the lists are NULL — are
+ * re-traced through the current acceleration structure like the reference does.
+ * Gradients (written entirely by the call, accumulated with float atomics):
+ *   dL_dmeans (P,3)  dL_dshs (P,M,3)  dL_dopac (P)  dL_dscales (P,2)  dL_drots (P,4) */
+int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
+                 const float* bg, int P, const float* means, const float* scales, const float* rots,
+                 const float* opac, const float* shs, int D, int M, float scale_modifier,
+                 const float* fwd_out, const float* dL_dout,
+                 const int32_t* hit_gidx, const float* hit_t, const int32_t* hit_cnt, int cap,
+                 float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
+                 float* dL_drots, int flags, void* stream);
+
+/* Introspection for tests / benchmarks (host pointers). */
+typedef struct lrt_info {
+    int32_t P;                    /* Gaussians in the built structure */
+    int32_t levels;               /* hierarchy levels (8-wide) */
+    int64_t nodes;                /* total nodes */
+    int64_t bytes_records;        /* HBM bytes of the sorted surfel records */
+    int64_t bytes_nodes;          /* HBM bytes of the hierarchy */
+    int64_t bytes_workspace;      /* total device bytes owned by the context */
+    int64_t builds, refits;       /* counters */
+    int32_t kernel_launches;      /* kernels launched by this library since context creation */
+} lrt_info;
+int lrt_get_info(const lrt_ctx* ctx, lrt_info* out);
+/* sorted position -> caller's Gaussian index, (P) int32 device copy */
+int lrt_get_permutation(const lrt_ctx* ctx, int32_t* perm_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDAR_RT_B200_H */

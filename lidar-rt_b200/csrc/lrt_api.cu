@@ -1,0 +1,104 @@
+// lrt_api.cu — the extern "C" surface declared in include/lidar_rt_b200.h.
+#include <new>
+#include "lrt_ctx.cuh"
+
+static std::string g_create_error;
+
+extern "C" {
+
+int lrt_version(void) { return LRT_VERSION; }
+
+int lrt_ctx_create(int device, lrt_ctx** out_ctx)
+{
+    if (!out_ctx) { g_create_error = "lrt_ctx_create: out_ctx is null"; return LRT_ERR_INVALID; }
+    *out_ctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_error = std::string("lrt_ctx_create: no CUDA device (") + cudaGetErrorString(e) + ")";
+        return LRT_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "lrt_ctx_create: device index out of range"; return LRT_ERR_INVALID; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice failed: ") + cudaGetErrorString(e); return LRT_ERR_CUDA; }
+    lrt_ctx* c = new (std::nothrow) lrt_ctx();
+    if (!c) { g_create_error = "lrt_ctx_create: out of host memory"; return LRT_ERR_INVALID; }
+    c->device = device;
+    *out_ctx = c;
+    return LRT_OK;
+}
+
+int lrt_ctx_destroy(lrt_ctx* ctx)
+{
+    if (!ctx) return LRT_OK;
+    cudaSetDevice(ctx->device);
+    DevBuf* bufs[] = {&ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->sort_tmp, &ctx->bounds};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    delete ctx;
+    return LRT_OK;
+}
+
+const char* lrt_last_error(const lrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int lrt_build(lrt_ctx* ctx, int P, const float* means, const float* scales, const float* rots,
+              const float* opac, float scale_modifier, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_build_impl(ctx, P, means, scales, rots, opac, scale_modifier, false, (cudaStream_t)stream);
+}
+
+int lrt_refit(lrt_ctx* ctx, int P, const float* means, const float* scales, const float* rots,
+              const float* opac, float scale_modifier, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_build_impl(ctx, P, means, scales, rots, opac, scale_modifier, true, (cudaStream_t)stream);
+}
+
+int lrt_forward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
+                const float* bg, int P, const float* means, const float* scales, const float* rots,
+                const float* opac, const float* shs, int D, int M, float scale_modifier,
+                float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, int32_t* hit_cnt,
+                int cap, int32_t* slot_cnt, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_forward_impl(ctx, R, ray_o, ray_o_stride, ray_d, bg, P, means, scales, rots, opac, shs, D, M,
+                            scale_modifier, out, accum_w, hit_gidx, hit_t, hit_cnt, cap, slot_cnt, (cudaStream_t)stream);
+}
+
+int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
+                 const float* bg, int P, const float* means, const float* scales, const float* rots,
+                 const float* opac, const float* shs, int D, int M, float scale_modifier,
+                 const float* fwd_out, const float* dL_dout,
+                 const int32_t* hit_gidx, const float* hit_t, const int32_t* hit_cnt, int cap,
+                 float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
+                 float* dL_drots, int flags, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_backward_impl(ctx, R, ray_o, ray_o_stride, ray_d, bg, P, means, scales, rots, opac, shs, D, M,
+                             scale_modifier, fwd_out, dL_dout, hit_gidx, hit_t, hit_cnt, cap,
+                             dL_dmeans, dL_dshs, dL_dopac, dL_dscales, dL_drots, flags, (cudaStream_t)stream);
+}
+
+int lrt_get_info(const lrt_ctx* ctx, lrt_info* out)
+{
+    if (!ctx || !out) return LRT_ERR_INVALID;
+    out->P = ctx->built ? ctx->P : 0;
+    out->levels = ctx->levels;
+    out->nodes = ctx->n_nodes;
+    out->bytes_records = (int64_t)sizeof(SurfelRec) * ctx->P_pad;
+    out->bytes_nodes = (int64_t)sizeof(Node8) * ctx->n_nodes;
+    out->bytes_workspace = (int64_t)ctx->total_bytes();
+    out->builds = ctx->builds; out->refits = ctx->refits;
+    out->kernel_launches = ctx->launches;
+    return LRT_OK;
+}
+
+int lrt_get_permutation(const lrt_ctx* ctx, int32_t* perm_out, void* stream)
+{
+    if (!ctx || !perm_out || !ctx->built) return LRT_ERR_STATE;
+    cudaError_t e = cudaMemcpyAsync(perm_out, ctx->perm_a.p, sizeof(int32_t) * (size_t)ctx->P, cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream);
+    return e == cudaSuccess ? LRT_OK : LRT_ERR_CUDA;
+}
+
+} // extern "C"

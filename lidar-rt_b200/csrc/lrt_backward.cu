@@ -1,0 +1,320 @@
+// lrt_backward.cu — backward device program: gradients onto xyz / scale / rotation / opacity / SH.
+//
+// Replaces __raygen__ot of the reference's backward pipeline
+// (submodules/diff-lidar-tracer/optix_tracer/backward.cu:434-691) and TraceSurfelsBackwardCUDA
+// (trace_surfels.cpp:268-386). The per-hit math follows backward.cu:577-675,
+// compute_transmat_uv_backward (:339-431), computeColorFromSHBackward (:123-247) and
+// quat_to_rotmat_vjp (auxiliary.h:389-433) term for term.
+//
+// Two ways to enumerate a ray's contributing hits, in the same front-to-back order:
+//   k_backward_list  : replay the (id, depth) list the forward pass recorded — no traversal at all;
+//   k_backward_trace : re-trace through the LBVH exactly like the reference does (used for rays
+//                      whose list overflowed `cap`, or when the caller passes no lists).
+#include "lrt_ctx.cuh"
+#include "lrt_trace.cuh"
+
+namespace {
+
+struct RayState {
+    float g_rgb[3], g_d, g_n[3];          // upstream gradients (dL_daccum / dL_dT are ignored, backward.cu:476)
+    float F_c[3], F_d, F_n[3], F_T;       // saved forward outputs
+    float C[3], N[3], Dp, T;              // running prefix (includes the current hit)
+};
+
+struct GradOut {
+    float* d_means; float* d_shs; float* d_opac; float* d_scales; float* d_rots;
+};
+
+__device__ __forceinline__ void cross3(const float* a, const float* b, float* o)
+{
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+__device__ __forceinline__ void load_sh_bw(const float* __restrict__ shs, int g, int M, int nb, float* sh)
+{
+    const float* p = shs + (size_t)g * M * 3;
+    if ((M & 3) == 0 && ((reinterpret_cast<uintptr_t>(shs) & 15) == 0)) {
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+        const int n4 = (nb * 3 + 3) >> 2;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            if (i < n4) { const float4 v = ld_f4(p4 + i); sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w; }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 48; i++) if (i < nb * 3) sh[i] = ld_f(p + i);
+    }
+}
+
+// One proxy hit of ray (o, d) at depth dpt on Gaussian g.
+// FILTER = true replays the forward's skip / termination rules (re-trace path);
+// returns 0 = not contributing, 1 = composited (gradients scattered), 2 = ray terminated.
+template <bool FILTER>
+__device__ __forceinline__ int hit_backward(int g, float dpt, const float* o, const float* d, const float* dirn,
+                                            const float* __restrict__ means, const float* __restrict__ scales,
+                                            const float* __restrict__ rots, const float* __restrict__ opac,
+                                            const float* __restrict__ shs, int D, int M, float mod,
+                                            const float* __restrict__ bg, int flags, RayState& st, const GradOut& go)
+{
+    if (FILTER && dpt < LRT_MIN_T) return 0;                                          // backward.cu:528
+    const float mu_[3] = {ld_f(means + 3 * (size_t)g), ld_f(means + 3 * (size_t)g + 1), ld_f(means + 3 * (size_t)g + 2)};
+    const float2 sc2 = __ldg(reinterpret_cast<const float2*>(scales + 2 * (size_t)g));
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(rots + 4 * (size_t)g));
+    const float sc_[2] = {sc2.x, sc2.y};
+    const float q_[4] = {q4.x, q4.y, q4.z, q4.w};
+    Derived s;
+    derive_surfel(mu_, sc_, q_, ld_f(opac + g), mod, s);
+
+    const float xyz[3] = {o[0] + dpt * d[0], o[1] + dpt * d[1], o[2] + dpt * d[2]};
+    const float rr[3] = {xyz[0] - s.mu[0], xyz[1] - s.mu[1], xyz[2] - s.mu[2]};
+    const float u = s.Lu[0] * rr[0] + s.Lu[1] * rr[1] + s.Lu[2] * rr[2];
+    const float v = s.Lv[0] * rr[0] + s.Lv[1] * rr[1] + s.Lv[2] * rr[2];
+    const float cosv = -((s.mu[0] - o[0]) * s.n[0] + (s.mu[1] - o[1]) * s.n[1] + (s.mu[2] - o[2]) * s.n[2]);
+    const float rho = u * u + v * v;
+    const float power = -0.5f * rho;
+    if (FILTER && power > 0.0f) return 0;
+    const float G = expf(power);
+    const float alpha = fminf(LRT_ALPHA_MAX, s.op * G);
+    if (FILTER && alpha < 1.0f / 255.0f) return 0;
+    const float testT = st.T * (1.0f - alpha);
+    if (FILTER && testT < LRT_T_MIN) return 2;
+    const float T = st.T;
+    const float w = alpha * T;
+
+    const int nb = (D + 1) * (D + 1);
+    float sh[48], c[3], basis[16]; bool clamped0;
+    load_sh_bw(shs, g, M, nb, sh);
+    sh_colour<true>(D, dirn, sh, c, clamped0, basis);
+
+#pragma unroll
+    for (int k = 0; k < 3; k++) { st.C[k] += w * c[k]; st.N[k] += w * s.n[k]; }       // :577-578
+    st.Dp += w * dpt;
+
+    const float inv1a = 1.0f / (1.0f - alpha);
+    float dalpha = 0.0f, dcol[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        dcol[ch] = st.g_rgb[ch] * w;
+        dalpha += st.g_rgb[ch] * (T * c[ch] - (st.F_c[ch] - st.C[ch]) * inv1a);      // :590
+    }
+    if (!(flags & LRT_FLAG_FIX_BG_GRAD)) {
+        float dbg = 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) dbg += st.g_rgb[ch] * bg[ch];
+        dalpha += dbg * (-st.F_T * inv1a);                                            // :595-598 (duplicate term)
+    }
+    const float dD_gs = st.g_d * w;
+    dalpha += st.g_d * (T * dpt - (st.F_d - st.Dp) * inv1a);                          // :601
+    float dN_gs[3];
+    {
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { dN_gs[k] = st.g_n[k] * w; acc += st.g_n[k] * (T * s.n[k] - (st.F_n[k] - st.N[k]) * inv1a); }
+        dalpha += acc;                                                                // :604
+    }
+    if (s.op * G > LRT_ALPHA_MAX) dalpha = 0.0f;                                      // :607-608
+    const float dG = s.op * dalpha;
+    atomicAdd(go.d_opac + g, G * dalpha);                                             // :615
+    const float nsign = cosv > 0.0f ? 1.0f : -1.0f;                                   // :649-650
+
+    // compute_transmat_uv_backward (:339-431)
+    const float du = dG * -G * u, dv = dG * -G * v;
+    float dtu[3], dtv[3], dn[3], dmu[3], dsc[2], dxyz[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { dtu[k] = du * rr[k] / s.sx; dtv[k] = dv * rr[k] / s.sy; dn[k] = dN_gs[k] * nsign; }
+    dsc[0] = dG * (G * u * u / s.sx); dsc[1] = dG * (G * v * v / s.sy);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { dmu[k] = dG * (G * (s.Lu[k] * u + s.Lv[k] * v)); dxyz[k] = du * s.Lu[k] + dv * s.Lv[k]; }
+    const float dd = (dxyz[0] * d[0] + dxyz[1] * d[1] + dxyz[2] * d[2]) + dD_gs;      // :390
+    // gradient through the hit depth: plane of the proxy triangle that contains the hit
+    // (:628-647: even -> corners 0,1,2 ; odd -> corners 1,2,3 ; corners = build2DRectangle order)
+    const bool odd = !(v >= u);
+    const float ax = s.sx * s.f, ay = s.sy * s.f;
+    const float lx[4] = {-1.f, -1.f, 1.f, 1.f}, ly[4] = {1.f, -1.f, 1.f, -1.f};
+    const int i1 = odd ? 1 : 0, i2 = odd ? 2 : 1, i3 = odd ? 3 : 2;
+    float v1[3], v2[3], v3[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float a = s.tu[k] * ax, b = s.tv[k] * ay;
+        v1[k] = (lx[i1] * a + ly[i1] * b) + s.mu[k];
+        v2[k] = (lx[i2] * a + ly[i2] * b) + s.mu[k];
+        v3[k] = (lx[i3] * a + ly[i3] * b) + s.mu[k];
+    }
+    const float cutoff = (float)(sqrt(2.0 * log((double)s.op * 255.)) + 0.01);       // :625 (double there too)
+    const float h1x = lx[i1] * cutoff, h1y = ly[i1] * cutoff, h2x = lx[i2] * cutoff, h2y = ly[i2] * cutoff,
+                h3x = lx[i3] * cutoff, h3y = ly[i3] * cutoff;
+    float e21[3], e31[3], e23[3], e12[3], nT[3], cT[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        e21[k] = v2[k] - v1[k]; e31[k] = v3[k] - v1[k]; e23[k] = v2[k] - v3[k]; e12[k] = v1[k] - v2[k];
+        cT[k] = v1[k] - o[k];
+    }
+    cross3(e21, e31, nT);
+    const float pp = nT[0] * cT[0] + nT[1] * cT[1] + nT[2] * cT[2];
+    const float qq = nT[0] * d[0] + nT[1] * d[1] + nT[2] * d[2];
+    float a_[3], x1[3], x2[3], x3[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) a_[k] = (cT[k] - pp / qq * d[k]) / qq;                // :399
+    cross3(e23, a_, x1); cross3(e31, a_, x2); cross3(e12, a_, x3);
+    float Sx[3], Sy[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float dv1 = x1[k] * dd + nT[k] / qq * dd, dv2 = x2[k] * dd, dv3 = x3[k] * dd;   // :400-402
+        Sx[k] = h1x * dv1 + h2x * dv2 + h3x * dv3;
+        Sy[k] = h1y * dv1 + h2y * dv2 + h3y * dv3;
+        dtu[k] += s.sx * Sx[k]; dtv[k] += s.sy * Sy[k];                               // :405-410
+        dmu[k] += dv1 + dv2 + dv3;                                                    // :430
+    }
+    dsc[0] += (s.sx * s.Lu[0]) * Sx[0] + (s.sx * s.Lu[1]) * Sx[1] + (s.sx * s.Lu[2]) * Sx[2];   // :426-427
+    dsc[1] += (s.sy * s.Lv[0]) * Sy[0] + (s.sy * s.Lv[1]) * Sy[1] + (s.sy * s.Lv[2]) * Sy[2];
+
+    // quat_to_rotmat_vjp (auxiliary.h:389-433); Gm[r][c] = dL/dR(r,c), columns (tu, tv, n)
+    {
+        const float qw = s.qn[0], qx = s.qn[1], qy = s.qn[2], qz = s.qn[3];
+#define GM(r, c) ((c) == 0 ? dtu[r] : (c) == 1 ? dtv[r] : dn[r])
+        const float dq0 = 2.0f * (qx * (GM(2, 1) - GM(1, 2)) + qy * (GM(0, 2) - GM(2, 0)) + qz * (GM(1, 0) - GM(0, 1)));
+        const float dq1 = 2.0f * (-2.0f * qx * (GM(1, 1) + GM(2, 2)) + qy * (GM(1, 0) + GM(0, 1)) + qz * (GM(2, 0) + GM(0, 2)) + qw * (GM(2, 1) - GM(1, 2)));
+        const float dq2 = 2.0f * (qx * (GM(1, 0) + GM(0, 1)) - 2.0f * qy * (GM(0, 0) + GM(2, 2)) + qz * (GM(2, 1) + GM(1, 2)) + qw * (GM(0, 2) - GM(2, 0)));
+        const float dq3 = 2.0f * (qx * (GM(2, 0) + GM(0, 2)) + qy * (GM(2, 1) + GM(1, 2)) - 2.0f * qz * (GM(0, 0) + GM(1, 1)) + qw * (GM(1, 0) - GM(0, 1)));
+#undef GM
+        atomicAdd(go.d_scales + 2 * (size_t)g, dsc[0]); atomicAdd(go.d_scales + 2 * (size_t)g + 1, dsc[1]);      // :659-669
+        atomicAdd(go.d_rots + 4 * (size_t)g, dq0); atomicAdd(go.d_rots + 4 * (size_t)g + 1, dq1);
+        atomicAdd(go.d_rots + 4 * (size_t)g + 2, dq2); atomicAdd(go.d_rots + 4 * (size_t)g + 3, dq3);
+        atomicAdd(go.d_means + 3 * (size_t)g, dmu[0]); atomicAdd(go.d_means + 3 * (size_t)g + 1, dmu[1]);
+        atomicAdd(go.d_means + 3 * (size_t)g + 2, dmu[2]);
+    }
+    // computeColorFromSHBackward (:123-247): dL_dsh[j] = basis_j * dL_dcolour, channel 0 zero if clamped
+    if (clamped0) dcol[0] = 0.0f;
+    float* dsh = go.d_shs + (size_t)g * M * 3;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (j < nb) {
+            atomicAdd(dsh + 3 * j, basis[j] * dcol[0]);
+            atomicAdd(dsh + 3 * j + 1, basis[j] * dcol[1]);
+            atomicAdd(dsh + 3 * j + 2, basis[j] * dcol[2]);
+        }
+    }
+    st.T = testT;
+    return 1;
+}
+
+__device__ __forceinline__ void ray_state_init(RayState& st, int r, const float* __restrict__ fwd_out,
+                                               const float* __restrict__ dL)
+{
+    const float* g = dL + (size_t)LRT_NCH * r;
+    const float* f = fwd_out + (size_t)LRT_NCH * r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { st.g_rgb[k] = g[k]; st.g_n[k] = g[5 + k]; st.F_c[k] = f[k]; st.F_n[k] = f[5 + k]; st.C[k] = 0.f; st.N[k] = 0.f; }
+    st.g_d = g[3]; st.F_d = f[3]; st.F_T = f[8]; st.Dp = 0.f; st.T = 1.f;
+}
+
+struct BwArgs {
+    int R; const float* ray_o; int ray_o_stride; const float* ray_d; const float* bg;
+    const float* means; const float* scales; const float* rots; const float* opac; const float* shs;
+    int D, M; float mod; const float* fwd_out; const float* dL; int flags;
+    const int32_t* hit_gidx; const float* hit_t; const int32_t* hit_cnt; int cap;
+    GradOut go;
+};
+
+__global__ void __launch_bounds__(128) k_backward_list(BwArgs a)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const int cnt = a.hit_cnt[r];
+    if (cnt <= 0 || cnt > a.cap) return;                 // overflowed rays are handled by k_backward_trace
+    const float o[3] = {a.ray_o[(size_t)r * a.ray_o_stride], a.ray_o[(size_t)r * a.ray_o_stride + 1], a.ray_o[(size_t)r * a.ray_o_stride + 2]};
+    const float d[3] = {a.ray_d[3 * (size_t)r], a.ray_d[3 * (size_t)r + 1], a.ray_d[3 * (size_t)r + 2]};
+    const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const float dirn[3] = {d[0] / dl, d[1] / dl, d[2] / dl};
+    const float bg[3] = {a.bg[0], a.bg[1], a.bg[2]};
+    RayState st;
+    ray_state_init(st, r, a.fwd_out, a.dL);
+    for (int k = 0; k < cnt; k++) {
+        const int g = a.hit_gidx[(size_t)k * a.R + r];
+        const float dpt = a.hit_t[(size_t)k * a.R + r];
+        hit_backward<false>(g, dpt, o, d, dirn, a.means, a.scales, a.rots, a.opac, a.shs, a.D, a.M, a.mod, bg, a.flags, st, a.go);
+    }
+}
+
+// only_overflow: process just the rays whose forward list overflowed
+__global__ void __launch_bounds__(128) k_backward_trace(BvhView bvh, BwArgs a, int only_overflow)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    if (only_overflow && a.hit_cnt[r] <= a.cap) return;
+    const float o[3] = {a.ray_o[(size_t)r * a.ray_o_stride], a.ray_o[(size_t)r * a.ray_o_stride + 1], a.ray_o[(size_t)r * a.ray_o_stride + 2]};
+    const float d[3] = {a.ray_d[3 * (size_t)r], a.ray_d[3 * (size_t)r + 1], a.ray_d[3 * (size_t)r + 2]};
+    const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const float dirn[3] = {d[0] / dl, d[1] / dl, d[2] / dl};
+    const float bg[3] = {a.bg[0], a.bg[1], a.bg[2]};
+    RayState st;
+    ray_state_init(st, r, a.fwd_out, a.dL);
+    float base = 0.f, dpt = 0.f;
+    for (;;) {
+        RaySetup rs;
+        ray_setup(rs, o, d, base);
+        unsigned long long kb[LRT_KBUF];
+        const int n = trace_round(bvh, rs, kb);
+        unsigned long long hits[LRT_KBUF];
+#pragma unroll
+        for (int i = 0; i < LRT_KBUF; i++) hits[i] = kb[i];
+        bool terminated = false;
+        for (int i = 0; i < n; i++) {
+            const unsigned long long key = hits[i];
+            const int prim = (int)(unsigned)(key & 0xffffffffull);
+            dpt = __uint_as_float((unsigned)(key >> 32)) + base;
+            const int g = __float_as_int(ld_f4(&bvh.rec[prim].r2).w);
+            const int res = hit_backward<true>(g, dpt, o, d, dirn, a.means, a.scales, a.rots, a.opac, a.shs, a.D, a.M, a.mod,
+                                               bg, a.flags, st, a.go);
+            if (res == 2) { terminated = true; break; }
+        }
+        if (terminated || n < LRT_KBUF) break;
+        base = (float)((double)dpt + LRT_STEP_EPS);
+    }
+}
+
+} // namespace
+
+int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
+                      const float* bg, int P, const float* means, const float* scales, const float* rots,
+                      const float* opac, const float* shs, int D, int M, float mod,
+                      const float* fwd_out, const float* dL_dout,
+                      const int32_t* hit_gidx, const float* hit_t, const int32_t* hit_cnt, int cap,
+                      float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
+                      float* dL_drots, int flags, cudaStream_t s)
+{
+    if (R < 0 || P <= 0 || !ray_o || !ray_d || !bg || !means || !scales || !rots || !opac || !shs || !fwd_out || !dL_dout ||
+        !dL_dmeans || !dL_dshs || !dL_dopac || !dL_dscales || !dL_drots) { ctx->set_error("lrt_backward: null argument"); return LRT_ERR_INVALID; }
+    if (ray_o_stride != 0 && ray_o_stride != 3) { ctx->set_error("lrt_backward: ray_o_stride must be 0 or 3"); return LRT_ERR_INVALID; }
+    if (D < 0 || D > 3 || M < (D + 1) * (D + 1)) { ctx->set_error("lrt_backward: need 0 <= D <= 3 and M >= (D+1)^2"); return LRT_ERR_INVALID; }
+    const bool have_lists = hit_gidx && hit_t && hit_cnt && cap > 0;
+    if (!have_lists && (hit_gidx || hit_t)) { ctx->set_error("lrt_backward: hit_gidx, hit_t, hit_cnt and cap go together"); return LRT_ERR_INVALID; }
+    LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dmeans, 0, sizeof(float) * (size_t)P * 3, s));
+    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dshs, 0, sizeof(float) * (size_t)P * M * 3, s));
+    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dopac, 0, sizeof(float) * (size_t)P, s));
+    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dscales, 0, sizeof(float) * (size_t)P * 2, s));
+    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_drots, 0, sizeof(float) * (size_t)P * 4, s));
+    if (R == 0) return LRT_OK;
+    BwArgs a;
+    a.R = R; a.ray_o = ray_o; a.ray_o_stride = ray_o_stride; a.ray_d = ray_d; a.bg = bg;
+    a.means = means; a.scales = scales; a.rots = rots; a.opac = opac; a.shs = shs;
+    a.D = D; a.M = M; a.mod = mod; a.fwd_out = fwd_out; a.dL = dL_dout; a.flags = flags;
+    a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_cnt = hit_cnt; a.cap = cap;
+    a.go.d_means = dL_dmeans; a.go.d_shs = dL_dshs; a.go.d_opac = dL_dopac; a.go.d_scales = dL_dscales; a.go.d_rots = dL_drots;
+    const int TB = 128, GB = (R + TB - 1) / TB;
+    const bool can_trace = ctx->built && ctx->P == P && ctx->scale_modifier == mod;
+    if (have_lists) {
+        k_backward_list<<<GB, TB, 0, s>>>(a);
+        ctx->launches += 1;
+        // Rays whose list overflowed need the structure that produced them. The caller (host
+        // wrapper) guarantees it is current; without one they cannot be differentiated.
+        if (can_trace) { k_backward_trace<<<GB, TB, 0, s>>>(ctx->view(), a, 1); ctx->launches += 1; }
+    } else {
+        if (!can_trace) { ctx->set_error("lrt_backward: no hit lists given and no matching acceleration structure built"); return LRT_ERR_STATE; }
+        k_backward_trace<<<GB, TB, 0, s>>>(ctx->view(), a, 0);
+        ctx->launches += 1;
+    }
+    LRT_CUDA_TRY(ctx, cudaGetLastError());
+    return LRT_OK;
+}

@@ -1,0 +1,216 @@
+// lrt_build.cu — LBVH build / refit over the per-Gaussian proxy quads.
+//
+// Replaces build2DRectangle (lib/utils/primitive_utils.py:182-224: 4 verts + 2 triangles per
+// Gaussian, 72 B written and re-read) and optixAccelBuild/optixAccelCompact
+// (submodules/diff-lidar-tracer/trace_surfels.cpp:46-148) of the reference.
+//
+// Pipeline (all on the caller's stream, no host sync):
+//   k_bounds   : min/max of the means                          read 12 B/Gaussian
+//   k_morton   : 30-bit Morton key of each mean + identity     read 12 B, write 8 B
+//   cub radix  : sort (key, index) pairs, 4 passes of 8 bits
+//   k_records  : gather raw parameters through the permutation, derive the surfel frame,
+//                write the 64 B record in Morton order and the padded quad AABB into its
+//                level-0 node slot                              read 40 B, write 64 + 24 B
+//   k_fit      : one launch per upper level: child box = union of the child's 8 boxes
+// The hierarchy is IMPLICIT: level l node j has children 8j..8j+7 of level l-1 (level 0: surfels),
+// so there are no child pointers, a refit is k_records + k_fit with the stored permutation, and
+// the traversal needs no stack (see lrt_trace.cuh).
+#include <cub/device/device_radix_sort.cuh>
+#include <cfloat>
+#include "lrt_ctx.cuh"
+
+namespace {
+
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void k_bounds_init(int* b)
+{
+    if (threadIdx.x < 3) b[threadIdx.x] = 0x7fffffff;          // min
+    else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000; // max
+}
+
+__global__ void __launch_bounds__(256) k_bounds(int P, const float* __restrict__ means, int* __restrict__ b)
+{
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float v = means[3 * i + k];
+            if (v == v && fabsf(v) < 1e30f) { lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { atomicMin(&b[k], f2ord(lo[k])); atomicMax(&b[3 + k], f2ord(hi[k])); }
+    }
+}
+
+__device__ __forceinline__ unsigned expand10(unsigned v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton(int P, const float* __restrict__ means, const int* __restrict__ b,
+                                                unsigned* __restrict__ keys, unsigned* __restrict__ idx)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    unsigned q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float lo = ord2f(b[k]), hi = ord2f(b[3 + k]);
+        const float ext = fmaxf(hi - lo, 1e-20f);
+        float t = (means[3 * i + k] - lo) / ext * 1024.0f;
+        t = fminf(fmaxf(t, 0.0f), 1023.0f);
+        q[k] = (t == t) ? (unsigned)t : 0u;
+    }
+    keys[i] = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    idx[i] = (unsigned)i;
+}
+
+__global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigned* __restrict__ perm,
+                                                 const float* __restrict__ means, const float* __restrict__ scales,
+                                                 const float* __restrict__ rots, const float* __restrict__ opac,
+                                                 float mod, SurfelRec* __restrict__ rec, Node8* __restrict__ leaf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P_pad) return;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (i < P) {
+        const int g = (int)perm[i];
+        const float mu[3] = {means[3 * g], means[3 * g + 1], means[3 * g + 2]};
+        const float2 sc2 = *reinterpret_cast<const float2*>(scales + 2 * g);
+        const float4 q4 = *reinterpret_cast<const float4*>(rots + 4 * g);
+        const float sc[2] = {sc2.x, sc2.y};
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float op = opac[g];
+        Derived d;
+        derive_surfel(mu, sc, q, op, mod, d);
+        SurfelRec r;
+        r.r0 = make_float4(d.mu[0], d.mu[1], d.mu[2], d.f);
+        r.r1 = make_float4(d.Lu[0], d.Lu[1], d.Lu[2], d.op);
+        r.r2 = make_float4(d.Lv[0], d.Lv[1], d.Lv[2], __int_as_float(g));
+        r.r3 = make_float4(d.n[0], d.n[1], d.n[2], 0.0f);
+        rec[i] = r;
+        const bool valid = (d.f == d.f) && d.f >= 0.0f && d.f < 1e30f;
+        if (valid) {
+            const float ax = mod * d.sx * d.f, ay = mod * d.sy * d.f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float e = fabsf(d.tu[k]) * ax + fabsf(d.tv[k]) * ay;
+                const float pad = 1e-4f + 1e-5f * (fabsf(mu[k]) + e);       // slab tests are a filter, the quad test decides
+                lo[k] = mu[k] - e - pad; hi[k] = mu[k] + e + pad;
+                if (!(lo[k] <= hi[k])) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+            }
+            if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+            }
+        }
+    } else {
+        SurfelRec r;
+        r.r0 = make_float4(0.f, 0.f, 0.f, -1.0f); r.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.r2 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); r.r3 = make_float4(0.f, 0.f, 1.f, 0.f);
+        rec[i] = r;
+    }
+    Node8& n = leaf[i >> 3];
+    const int c = i & 7;
+    n.lox[c] = lo[0]; n.loy[c] = lo[1]; n.loz[c] = lo[2];
+    n.hix[c] = hi[0]; n.hiy[c] = hi[1]; n.hiz[c] = hi[2];
+}
+
+// level l >= 1: child c of node j is the union of the 8 boxes of node 8j+c one level below
+__global__ void __launch_bounds__(256) k_fit(int n_parent, int n_child, const Node8* __restrict__ child,
+                                             Node8* __restrict__ parent)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_parent * 8) return;
+    const int j = t >> 3, c = t & 7, cj = 8 * j + c;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (cj < n_child) {
+        const Node8& ch = child[cj];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            lo[0] = fminf(lo[0], ch.lox[k]); lo[1] = fminf(lo[1], ch.loy[k]); lo[2] = fminf(lo[2], ch.loz[k]);
+            hi[0] = fmaxf(hi[0], ch.hix[k]); hi[1] = fmaxf(hi[1], ch.hiy[k]); hi[2] = fmaxf(hi[2], ch.hiz[k]);
+        }
+    }
+    Node8& n = parent[j];
+    n.lox[c] = lo[0]; n.loy[c] = lo[1]; n.loz[c] = lo[2];
+    n.hix[c] = hi[0]; n.hiy[c] = hi[1]; n.hiz[c] = hi[2];
+}
+
+} // namespace
+
+int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales, const float* rots,
+                   const float* opac, float mod, bool refit, cudaStream_t s)
+{
+    if (P <= 0 || !means || !scales || !rots || !opac) { ctx->set_error("lrt_build: P must be > 0 and arrays non-null"); return LRT_ERR_INVALID; }
+    if (!(mod > 0.0f)) { ctx->set_error("lrt_build: scale_modifier must be > 0"); return LRT_ERR_INVALID; }
+    if (refit && (!ctx->built || ctx->P != P)) { ctx->set_error("lrt_refit: no structure built for this P (call lrt_build)"); return LRT_ERR_STATE; }
+    LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+
+    // level layout
+    const int P_pad = (P + 7) & ~7;
+    int cnt[LRT_MAX_LEVELS], off[LRT_MAX_LEVELS], L = 0;
+    long long total = 0;
+    int n = P_pad / 8;
+    for (;;) {
+        if (L >= LRT_MAX_LEVELS) { ctx->set_error("lrt_build: too many levels"); return LRT_ERR_INVALID; }
+        cnt[L] = n; off[L] = (int)total; total += n; L++;
+        if (n == 1) break;
+        n = (n + 7) / 8;
+    }
+    LRT_CUDA_TRY(ctx, ctx->reserve(ctx->rec, sizeof(SurfelRec) * (size_t)P_pad));
+    LRT_CUDA_TRY(ctx, ctx->reserve(ctx->nodes, sizeof(Node8) * (size_t)total));
+    LRT_CUDA_TRY(ctx, ctx->reserve(ctx->perm_a, sizeof(unsigned) * (size_t)P));
+    const int TB = 256;
+    if (!refit) {
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->perm_b, sizeof(unsigned) * (size_t)P));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_a, sizeof(unsigned) * (size_t)P));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_b, sizeof(unsigned) * (size_t)P));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bounds, sizeof(int) * 8));
+        size_t tmp_bytes = 0;
+        cub::DoubleBuffer<unsigned> dk((unsigned*)ctx->keys_a.p, (unsigned*)ctx->keys_b.p);
+        cub::DoubleBuffer<unsigned> dv((unsigned*)ctx->perm_b.p, (unsigned*)ctx->perm_a.p);
+        LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, P, 0, 30, s));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sort_tmp, tmp_bytes));
+        k_bounds_init<<<1, 32, 0, s>>>((int*)ctx->bounds.p);
+        const int gb = min((P + TB - 1) / TB, 148 * 8);
+        k_bounds<<<gb, TB, 0, s>>>(P, means, (int*)ctx->bounds.p);
+        k_morton<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
+                                                   (unsigned*)ctx->perm_b.p);
+        LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk, dv, P, 0, 30, s));
+        ctx->launches += 3 + 8;     // + radix sort passes (histogram/scan/onesweep)
+        if (dv.Current() != (unsigned*)ctx->perm_a.p) {          // keep the permutation in perm_a
+            LRT_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->perm_a.p, dv.Current(), sizeof(unsigned) * (size_t)P,
+                                              cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    Node8* nodes = (Node8*)ctx->nodes.p;
+    k_records<<<(P_pad + TB - 1) / TB, TB, 0, s>>>(P, P_pad, (const unsigned*)ctx->perm_a.p, means, scales, rots, opac,
+                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0]);
+    for (int l = 1; l < L; l++)
+        k_fit<<<(cnt[l] * 8 + TB - 1) / TB, TB, 0, s>>>(cnt[l], cnt[l - 1], nodes + off[l - 1], nodes + off[l]);
+    ctx->launches += L;
+    LRT_CUDA_TRY(ctx, cudaGetLastError());
+
+    ctx->P = P; ctx->P_pad = P_pad; ctx->levels = L; ctx->n_nodes = total; ctx->scale_modifier = mod;
+    for (int i = 0; i < LRT_MAX_LEVELS; i++) { ctx->level_off[i] = i < L ? off[i] : 0; ctx->level_cnt[i] = i < L ? cnt[i] : 0; }
+    ctx->built = true;
+    if (refit) ctx->refits++; else ctx->builds++;
+    return LRT_OK;
+}

@@ -1,0 +1,132 @@
+// lrt_common.cuh — shared device/host definitions of the B200-native LiDAR surfel tracer.
+//
+// Arithmetic contract: this library is compiled with -fmad=false, so every expression below is
+// evaluated exactly as written (IEEE fp32, no implicit FMA contraction). The expressions that
+// decide WHICH surfels a ray hits and in WHAT order (derive_surfel, quad test, depth) are written
+// in the same operation order as the parity oracle, so hit lists are reproducible bit for bit.
+// Explicit fmaf() is used only where results are not part of that contract (box slabs).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define LRT_NCH 9                 // reference: optix_tracer/config.h:24 NUM_CHANNELS_F
+#define LRT_KBUF 16               // reference: optix_tracer/config.h:16 CHUNK_SIZE
+#define LRT_STEP_EPS 0.00001      // reference: optix_tracer/config.h:17 STEP_EPSILON (double literal)
+#define LRT_TMAX 1e16f            // reference: forward.cu:55
+#define LRT_MIN_T 0.2f            // reference: forward.cu:214
+#define LRT_ALPHA_MAX 0.99f       // reference: forward.cu:249
+#define LRT_T_MIN 0.0001f         // reference: forward.cu:254
+#define LRT_MAX_LEVELS 8          // 8^8 = 16.7 M surfels; one trail byte per level fits 64 bits
+#define LRT_WIDTH 8               // children per node
+
+// SH constants, reference: optix_tracer/auxiliary.h:23-40
+#define LRT_SH_C0 0.28209479177387814f
+#define LRT_SH_C1 0.4886025119029199f
+#define LRT_SH_C2_0 1.0925484305920792f
+#define LRT_SH_C2_1 -1.0925484305920792f
+#define LRT_SH_C2_2 0.31539156525252005f
+#define LRT_SH_C2_3 -1.0925484305920792f
+#define LRT_SH_C2_4 0.5462742152960396f
+#define LRT_SH_C3_0 -0.5900435899266435f
+#define LRT_SH_C3_1 2.890611442640554f
+#define LRT_SH_C3_2 -0.4570457994644658f
+#define LRT_SH_C3_3 0.3731763325901154f
+#define LRT_SH_C3_4 -0.4570457994644658f
+#define LRT_SH_C3_5 1.445305721320277f
+#define LRT_SH_C3_6 -0.5900435899266435f
+
+// One surfel in Morton order: 64 B = 4 x 128-bit loads.
+//   r0 = (mu.x, mu.y, mu.z, f)        f = proxy cutoff sqrt(2 ln(255 o)) + 0.01
+//   r1 = (Lu.x, Lu.y, Lu.z, opacity)  Lu = tu / sx  (row 0 of S^-1 R^T, forward.cu:130-132)
+//   r2 = (Lv.x, Lv.y, Lv.z, gidx)     Lv = tv / sy ; gidx = caller's index (int bits)
+//   r3 = (n.x,  n.y,  n.z,  unused)   n = R[:,2]
+struct __align__(16) SurfelRec { float4 r0, r1, r2, r3; };
+
+// 8-wide node: child boxes as SoA, 192 B = 12 x 128-bit loads.
+struct __align__(16) Node8 { float lox[8], loy[8], loz[8], hix[8], hiy[8], hiz[8]; };
+
+struct BvhView {
+    const SurfelRec* rec;         // (P_pad)
+    const Node8* nodes;           // all levels, level 0 (children = surfels) first
+    int level_off[LRT_MAX_LEVELS];
+    int levels;
+    int P;
+};
+
+struct Derived {
+    float mu[3], tu[3], tv[3], n[3], Lu[3], Lv[3];
+    float sx, sy, op, f;
+    float qn[4];
+};
+
+// Proxy + surfel frame of one Gaussian. Same operation order as oracle derive().
+// reference: general_utils.py:176-197 (build_rotation), auxiliary.h:306-328, :445-452,
+//            primitive_utils.py:182-224 (cutoff), forward.cu:116-141 (L = S^-1 R^T)
+__device__ __forceinline__ void derive_surfel(const float* mu, const float* sc, const float* q, float op,
+                                              float mod, Derived& o)
+{
+    const float nrm = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const float inv = 1.0f / sqrtf(nrm);          // the reference's rsqrtf is approximate; IEEE here
+    const float w = q[0] * inv, x = q[1] * inv, y = q[2] * inv, z = q[3] * inv;
+    o.qn[0] = w; o.qn[1] = x; o.qn[2] = y; o.qn[3] = z;
+    o.tu[0] = 1.0f - 2.0f * (y * y + z * z); o.tv[0] = 2.0f * (x * y - w * z); o.n[0] = 2.0f * (x * z + w * y);
+    o.tu[1] = 2.0f * (x * y + w * z); o.tv[1] = 1.0f - 2.0f * (x * x + z * z); o.n[1] = 2.0f * (y * z - w * x);
+    o.tu[2] = 2.0f * (x * z - w * y); o.tv[2] = 2.0f * (y * z + w * x); o.n[2] = 1.0f - 2.0f * (x * x + y * y);
+    o.sx = sc[0]; o.sy = sc[1]; o.op = op;
+    const float isx = 1.0f / (mod * sc[0]), isy = 1.0f / (mod * sc[1]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { o.mu[k] = mu[k]; o.Lu[k] = o.tu[k] * isx; o.Lv[k] = o.tv[k] * isy; }
+    o.f = sqrtf(2.0f * logf(op * 255.0f)) + 0.01f;
+}
+
+// SH colour of the (normalised) ray direction + the basis values (for the VJP).
+// reference: forward.cu:67-111 / backward.cu:68-118. sh = (M,3) coefficients of one Gaussian.
+template <bool WITH_BASIS>
+__device__ __forceinline__ void sh_colour(int deg, const float* dirn, const float* __restrict__ sh,
+                                          float* c, bool& clamped0, float* basis)
+{
+    const float x = dirn[0], y = dirn[1], z = dirn[2];
+    float b[16];
+    int nb = 1;
+    b[0] = LRT_SH_C0;
+    if (deg > 0) {
+        b[1] = -LRT_SH_C1 * y; b[2] = LRT_SH_C1 * z; b[3] = -LRT_SH_C1 * x; nb = 4;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            b[4] = LRT_SH_C2_0 * xy; b[5] = LRT_SH_C2_1 * yz; b[6] = LRT_SH_C2_2 * (2.0f * zz - xx - yy);
+            b[7] = LRT_SH_C2_3 * xz; b[8] = LRT_SH_C2_4 * (xx - yy); nb = 9;
+            if (deg > 2) {
+                b[9] = LRT_SH_C3_0 * y * (3.0f * xx - yy);
+                b[10] = LRT_SH_C3_1 * xy * z;
+                b[11] = LRT_SH_C3_2 * y * (4.0f * zz - xx - yy);
+                b[12] = LRT_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                b[13] = LRT_SH_C3_4 * x * (4.0f * zz - xx - yy);
+                b[14] = LRT_SH_C3_5 * z * (xx - yy);
+                b[15] = LRT_SH_C3_6 * x * (xx - 3.0f * yy);
+                nb = 16;
+            }
+        }
+    }
+    float r0 = b[0] * sh[0], r1 = b[0] * sh[1], r2 = b[0] * sh[2];
+#pragma unroll
+    for (int j = 1; j < 16; j++) {
+        if (j < nb) { r0 = r0 + b[j] * sh[3 * j]; r1 = r1 + b[j] * sh[3 * j + 1]; r2 = r2 + b[j] * sh[3 * j + 2]; }
+    }
+    c[0] = r0 + 0.5f; c[1] = r1 + 0.5f; c[2] = r2 + 0.5f;
+    clamped0 = c[0] < 0.0f;
+    if (clamped0) c[0] = 0.0f;
+    if (WITH_BASIS) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) basis[j] = j < nb ? b[j] : 0.0f;
+    }
+}
+
+__device__ __forceinline__ float ld_f(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float4 ld_f4(const float4* p) { return __ldg(p); }
+
+#define LRT_CUDA_TRY(ctx, call)                                                                     \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) { (ctx)->set_error(#call, e__); return LRT_ERR_CUDA; }              \
+    } while (0)

@@ -1,0 +1,77 @@
+// lrt_ctx.cuh — the per-device context behind the C ABI (include/lidar_rt_b200.h).
+// Replaces the reference's OptiXState (optix_tracer/optix_wrapper.h:34-49): owns the acceleration
+// structure (sorted surfel records + 8-wide implicit hierarchy) and the build workspace.
+#pragma once
+
+#include <string>
+#include <cstdio>
+#include "../../include/lidar_rt_b200.h"
+#include "lrt_common.cuh"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct lrt_ctx {
+    int device = 0;
+    std::string err;
+    // acceleration structure
+    int P = 0, P_pad = 0, levels = 0;
+    int level_off[LRT_MAX_LEVELS] = {0};
+    int level_cnt[LRT_MAX_LEVELS] = {0};
+    long long n_nodes = 0;
+    bool built = false;
+    float scale_modifier = 1.0f;
+    DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, sort_tmp, bounds;
+    long long builds = 0, refits = 0;
+    int launches = 0;
+
+    void set_error(const char* what, cudaError_t e)
+    {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s failed: %s", what, cudaGetErrorString(e));
+        err = buf;
+    }
+    void set_error(const char* msg) { err = msg; }
+
+    cudaError_t reserve(DevBuf& b, size_t bytes)
+    {
+        if (bytes <= b.cap) return cudaSuccess;
+        if (b.p) { cudaError_t e = cudaFree(b.p); b.p = nullptr; b.cap = 0; if (e != cudaSuccess) return e; }
+        const size_t want = bytes + bytes / 4 + 256;      // headroom: densification grows P every 100 iterations
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e == cudaSuccess) b.cap = want;
+        return e;
+    }
+    size_t total_bytes() const
+    {
+        return rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + sort_tmp.cap + bounds.cap;
+    }
+    BvhView view() const
+    {
+        BvhView v;
+        v.rec = (const SurfelRec*)rec.p;
+        v.nodes = (const Node8*)nodes.p;
+        for (int i = 0; i < LRT_MAX_LEVELS; i++) v.level_off[i] = level_off[i];
+        v.levels = levels;
+        v.P = P;
+        return v;
+    }
+};
+
+// implemented in lrt_build.cu / lrt_forward.cu / lrt_backward.cu
+int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales, const float* rots,
+                   const float* opac, float mod, bool refit, cudaStream_t s);
+int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
+                     const float* bg, int P, const float* means, const float* scales, const float* rots,
+                     const float* opac, const float* shs, int D, int M, float mod,
+                     float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, int32_t* hit_cnt,
+                     int cap, int32_t* slot_cnt, cudaStream_t s);
+int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
+                      const float* bg, int P, const float* means, const float* scales, const float* rots,
+                      const float* opac, const float* shs, int D, int M, float mod,
+                      const float* fwd_out, const float* dL_dout,
+                      const int32_t* hit_gidx, const float* hit_t, const int32_t* hit_cnt, int cap,
+                      float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
+                      float* dL_drots, int flags, cudaStream_t s);

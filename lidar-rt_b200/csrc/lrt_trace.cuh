@@ -1,0 +1,133 @@
+// lrt_trace.cuh — one k-buffer round of a ray through the implicit 8-wide LBVH.
+//
+// Replaces optixTrace + __anyhit__ot of the reference (forward.cu:48-63, :312-356): find the
+// (at most) 16 nearest proxy hits of the re-based ray (o', d) with t' in (0, 1e16), ascending.
+// Differences in HOW (results are identical):
+//   * the reference's any-hit program must see every triangle on the whole ray in every round
+//     (optixIgnoreIntersection never shortens the ray); here subtrees whose entry distance exceeds
+//     the current 16th-nearest hit are culled;
+//   * the proxy is one analytic quad |u|,|v| <= f per Gaussian instead of two triangles;
+//   * traversal is stackless: the hierarchy is implicit (children of node j at level l are nodes
+//     8j..8j+7 at level l-1), so the only state is (level, node) plus one pending-children byte per
+//     level packed into a 64-bit trail.
+#pragma once
+
+#include "lrt_common.cuh"
+
+#define LRT_KEY_EMPTY 0x5A0E1BCAFFFFFFFFull     // (bits(1e16f) << 32) | 0xffffffff : nothing at t' >= 1e16
+
+struct RaySetup {
+    float ox, oy, oz;     // re-based origin o' = o + base d (forward.cu:291)
+    float dx, dy, dz;
+    float ix, iy, iz;     // 1 / d (clamped away from 0) for the slab tests
+    float px, py, pz;     // o' * (1/d)
+};
+
+__device__ __forceinline__ float safe_inv(float d)
+{
+    const float a = fabsf(d) < 1e-18f ? copysignf(1e-18f, d) : d;
+    return 1.0f / a;
+}
+
+__device__ __forceinline__ void ray_setup(RaySetup& r, const float* o, const float* d, float base)
+{
+    r.ox = o[0] + base * d[0]; r.oy = o[1] + base * d[1]; r.oz = o[2] + base * d[2];
+    r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+    r.ix = safe_inv(d[0]); r.iy = safe_inv(d[1]); r.iz = safe_inv(d[2]);
+    r.px = r.ox * r.ix; r.py = r.oy * r.iy; r.pz = r.oz * r.iz;
+}
+
+// Analytic proxy test, same operation order as the oracle's quad_hit().
+__device__ __forceinline__ bool quad_hit(const SurfelRec* __restrict__ rec, int prim, const RaySetup& r, float& t_out)
+{
+    const float4 a0 = ld_f4(&rec[prim].r0), a3 = ld_f4(&rec[prim].r3);
+    const float c0 = a0.x - r.ox, c1 = a0.y - r.oy, c2 = a0.z - r.oz;
+    const float den = a3.x * r.dx + a3.y * r.dy + a3.z * r.dz;
+    const float num = a3.x * c0 + a3.y * c1 + a3.z * c2;
+    const float t = num / den;
+    if (!(t > 0.0f)) return false;
+    const float4 a1 = ld_f4(&rec[prim].r1), a2 = ld_f4(&rec[prim].r2);
+    const float r0 = (r.ox + t * r.dx) - a0.x, r1 = (r.oy + t * r.dy) - a0.y, r2 = (r.oz + t * r.dz) - a0.z;
+    const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
+    const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+    if (!(fabsf(u) <= a0.w && fabsf(v) <= a0.w)) return false;
+    t_out = t;
+    return t < LRT_TMAX;
+}
+
+// Sorted insertion into the register-resident k-buffer (ascending 64-bit keys = (t bits, surfel)).
+__device__ __forceinline__ void kbuf_insert(unsigned long long (&kb)[LRT_KBUF], unsigned long long key)
+{
+    if (key >= kb[LRT_KBUF - 1]) return;
+#pragma unroll
+    for (int i = 0; i < LRT_KBUF; i++) {
+        const unsigned long long cur = kb[i];
+        const bool sw = key < cur;
+        kb[i] = sw ? key : cur;
+        key = sw ? cur : key;
+    }
+}
+
+// 8 slab tests of one node against [0, tmax]; returns the mask of children to visit.
+__device__ __forceinline__ unsigned node_mask(const Node8* __restrict__ node, const RaySetup& r, float tmax)
+{
+    const float4* p = reinterpret_cast<const float4*>(node);
+    unsigned m = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const float4 lx = ld_f4(p + h), ly = ld_f4(p + 2 + h), lz = ld_f4(p + 4 + h);
+        const float4 hx = ld_f4(p + 6 + h), hy = ld_f4(p + 8 + h), hz = ld_f4(p + 10 + h);
+        const float lxs[4] = {lx.x, lx.y, lx.z, lx.w}, lys[4] = {ly.x, ly.y, ly.z, ly.w}, lzs[4] = {lz.x, lz.y, lz.z, lz.w};
+        const float hxs[4] = {hx.x, hx.y, hx.z, hx.w}, hys[4] = {hy.x, hy.y, hy.z, hy.w}, hzs[4] = {hz.x, hz.y, hz.z, hz.w};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float x0 = fmaf(lxs[c], r.ix, -r.px), x1 = fmaf(hxs[c], r.ix, -r.px);
+            const float y0 = fmaf(lys[c], r.iy, -r.py), y1 = fmaf(hys[c], r.iy, -r.py);
+            const float z0 = fmaf(lzs[c], r.iz, -r.pz), z1 = fmaf(hzs[c], r.iz, -r.pz);
+            const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+            const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+            if (tn <= tf) m |= 1u << (4 * h + c);
+        }
+    }
+    return m;
+}
+
+// One round. On return `kb` holds the nearest hits ascending; returns how many are valid (<= 16).
+// 16 valid entries <=> the reference's `payload.cnt >= CHUNK_SIZE` (forward.cu:282).
+__device__ __forceinline__ int trace_round(const BvhView& bvh, const RaySetup& r, unsigned long long (&kb)[LRT_KBUF])
+{
+#pragma unroll
+    for (int i = 0; i < LRT_KBUF; i++) kb[i] = LRT_KEY_EMPTY;
+    const int L = bvh.levels;
+    int level = L - 1;
+    unsigned node = 0;
+    unsigned long long trail = 0;
+    for (;;) {
+        const float tmax = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32));
+        unsigned m = node_mask(bvh.nodes + bvh.level_off[level] + node, r, tmax);
+        if (level == 0) {
+            while (m) {
+                const int c = __ffs(m) - 1; m &= m - 1;
+                const int prim = (int)(node * 8u + c);
+                float t;
+                if (quad_hit(bvh.rec, prim, r, t))
+                    kbuf_insert(kb, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)prim);
+            }
+        }
+        if (m == 0) {                                   // nothing (left) below this node: climb
+            do {
+                level++; node >>= 3;
+                if (level >= L) goto done;
+                m = (unsigned)(trail >> (8 * level)) & 0xffu;
+            } while (m == 0);
+        }
+        const int c = __ffs(m) - 1; m &= m - 1;          // next pending child
+        trail = (trail & ~(0xffull << (8 * level))) | ((unsigned long long)m << (8 * level));
+        node = node * 8u + c; level--;
+    }
+done:
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < LRT_KBUF; i++) n += kb[i] != LRT_KEY_EMPTY;
+    return n;
+}

@@ -1,0 +1,215 @@
+"""ctypes binding of the C-ABI library (include/lidar_rt_b200.h -> csrc/liblidar_rt_b200.so).
+
+This is the thin host layer the reference implements as a pybind11 torch extension
+(/root/reference/submodules/diff-lidar-tracer/ext.cpp:17-22). PyTorch is used only for device
+memory and streams; tensors are handed to the library as raw device pointers.
+
+There is NO fallback: if the library is missing or fails, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "liblidar_rt_b200.so")
+
+LRT_FLAG_FIX_BG_GRAD = 1
+NUM_CHANNELS = 9
+DEFAULT_HIT_CAP = 64
+
+
+class LrtError(RuntimeError):
+    pass
+
+
+class LrtInfo(ctypes.Structure):
+    _fields_ = [("P", c_int32), ("levels", c_int32), ("nodes", c_int64), ("bytes_records", c_int64),
+                ("bytes_nodes", c_int64), ("bytes_workspace", c_int64), ("builds", c_int64), ("refits", c_int64),
+                ("kernel_launches", c_int32)]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load liblidar_rt_b200.so; raises if it has not been built (csrc/build.sh)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LrtError(f"{LIB_PATH} not found: build it with lidar-rt_b200/csrc/build.sh "
+                       "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    fp, ip = c_void_p, c_void_p
+    lib.lrt_version.restype = c_int
+    lib.lrt_ctx_create.argtypes = [c_int, POINTER(c_void_p)]
+    lib.lrt_ctx_destroy.argtypes = [c_void_p]
+    lib.lrt_last_error.argtypes = [c_void_p]; lib.lrt_last_error.restype = c_char_p
+    build_args = [c_void_p, c_int, fp, fp, fp, fp, c_float, c_void_p]
+    lib.lrt_build.argtypes = build_args
+    lib.lrt_refit.argtypes = build_args
+    lib.lrt_forward.argtypes = [c_void_p, c_int, fp, c_int, fp, fp, c_int, fp, fp, fp, fp, fp, c_int, c_int, c_float,
+                                fp, fp, ip, fp, ip, c_int, ip, c_void_p]
+    lib.lrt_backward.argtypes = [c_void_p, c_int, fp, c_int, fp, fp, c_int, fp, fp, fp, fp, fp, c_int, c_int, c_float,
+                                 fp, fp, ip, fp, ip, c_int, fp, fp, fp, fp, fp, c_int, c_void_p]
+    lib.lrt_get_info.argtypes = [c_void_p, POINTER(LrtInfo)]
+    lib.lrt_get_permutation.argtypes = [c_void_p, c_void_p, c_void_p]
+    for f in (lib.lrt_ctx_create, lib.lrt_ctx_destroy, lib.lrt_build, lib.lrt_refit, lib.lrt_forward, lib.lrt_backward,
+              lib.lrt_get_info, lib.lrt_get_permutation):
+        f.restype = c_int
+    _lib = lib
+    return lib
+
+
+def _f32(t: torch.Tensor, name: str, shape_tail=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise LrtError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise LrtError(f"{name} must be float32, got {t.dtype}")
+    if shape_tail is not None and tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+        raise LrtError(f"{name} must have trailing shape {shape_tail}, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream(device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Context:
+    """Owns one lrt_ctx (acceleration structure + workspace) on one device."""
+
+    def __init__(self, device=None):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise LrtError("lidar_rt_b200 needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+        h = c_void_p()
+        rc = self.lib.lrt_ctx_create(self.device.index, byref(h))
+        if rc != 0:
+            raise LrtError(self.lib.lrt_last_error(None).decode())
+        self._h = h
+        self.generation = 0          # bumps on every build / refit
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.lrt_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LrtError(self.lib.lrt_last_error(self._h).decode())
+
+    # ---- acceleration structure
+    def _gauss(self, means, scales, rots, opac):
+        means = _f32(means, "means3D", (3,))
+        P = means.shape[0]
+        if means.dim() != 2:
+            raise LrtError("means3D must have dimensions (num_points, 3)")      # trace_surfels.cpp:178-180
+        scales = _f32(scales, "scales", (2,)); rots = _f32(rots, "rotations", (4,))
+        opac = _f32(opac, "opacities").reshape(-1)
+        if scales.shape[0] != P or rots.shape[0] != P or opac.shape[0] != P:
+            raise LrtError("means3D / scales / rotations / opacities disagree on the number of Gaussians")
+        return P, means, scales, rots, opac
+
+    def build(self, means, scales, rots, opac, scale_modifier: float = 1.0, refit: bool = False):
+        P, means, scales, rots, opac = self._gauss(means, scales, rots, opac)
+        with torch.cuda.device(self.device):
+            fn = self.lib.lrt_refit if refit else self.lib.lrt_build
+            self._check(fn(self._h, P, _ptr(means), _ptr(scales), _ptr(rots), _ptr(opac), c_float(scale_modifier),
+                           _stream(self.device)))
+        self.generation += 1
+        return self.generation
+
+    def info(self) -> LrtInfo:
+        i = LrtInfo()
+        self._check(self.lib.lrt_get_info(self._h, byref(i)))
+        return i
+
+    def permutation(self) -> torch.Tensor:
+        P = self.info().P
+        out = torch.empty(P, dtype=torch.int32, device=self.device)
+        self._check(self.lib.lrt_get_permutation(self._h, _ptr(out), _stream(self.device)))
+        return out
+
+    # ---- forward / backward
+    @staticmethod
+    def _rays(ray_o, ray_d):
+        ray_d = _f32(ray_d, "ray_d", (3,))
+        lead = tuple(ray_d.shape[:-1])
+        R = ray_d.numel() // 3
+        if not isinstance(ray_o, torch.Tensor) or ray_o.dtype != torch.float32 or not ray_o.is_cuda:
+            raise LrtError("ray_o must be a float32 CUDA tensor")
+        # LiDARSensor.get_range_rays returns one centre .expand()-ed to (H,W,3): a stride-0 view.
+        # The reference calls .contiguous() on a temporary (trace_surfels.cpp:227); we pass stride 0.
+        if ray_o.numel() == 3 or (ray_o.shape[-1] == 3 and all(s == 0 for s in ray_o.stride()[:-1]) and ray_o.stride(-1) == 1):
+            o = ray_o.reshape(-1)[:3] if ray_o.numel() == 3 else ray_o[(0,) * (ray_o.dim() - 1)]
+            return R, lead, o.contiguous(), 0, ray_d
+        if tuple(ray_o.shape) != tuple(ray_d.shape):
+            raise LrtError("ray_o and ray_d must have the same shape")
+        return R, lead, ray_o.contiguous(), 3, ray_d
+
+    def forward(self, ray_o, ray_d, bg, means, scales, rots, opac, shs, sh_degree: int, scale_modifier: float = 1.0,
+                record_hits: bool = True, cap: int = DEFAULT_HIT_CAP, want_slots: bool = False):
+        P, means, scales, rots, opac = self._gauss(means, scales, rots, opac)
+        R, lead, o, stride, d = self._rays(ray_o, ray_d)
+        shs = _f32(shs, "shs", (3,))
+        if shs.dim() != 3 or shs.shape[0] != P:
+            raise LrtError("shs must have dimensions (num_points, M, 3)")
+        M = shs.shape[1]
+        bg = _f32(bg, "bg").reshape(-1)
+        dev = self.device
+        with torch.cuda.device(dev):
+            out = torch.empty(lead + (NUM_CHANNELS,), dtype=torch.float32, device=dev)
+            accum = torch.empty(P, dtype=torch.float32, device=dev)
+            hit_g = hit_t = hit_c = slots = None
+            if record_hits:
+                hit_g = torch.empty((cap, R), dtype=torch.int32, device=dev)
+                hit_t = torch.empty((cap, R), dtype=torch.float32, device=dev)
+                hit_c = torch.empty(R, dtype=torch.int32, device=dev)
+            if want_slots:
+                slots = torch.empty(R, dtype=torch.int32, device=dev)
+            self._check(self.lib.lrt_forward(self._h, R, _ptr(o), stride, _ptr(d), _ptr(bg), P, _ptr(means), _ptr(scales),
+                                             _ptr(rots), _ptr(opac), _ptr(shs), int(sh_degree), M, c_float(scale_modifier),
+                                             _ptr(out), _ptr(accum), _ptr(hit_g), _ptr(hit_t), _ptr(hit_c), cap, _ptr(slots),
+                                             _stream(dev)))
+        return dict(out=out, accum_w=accum, hit_gidx=hit_g, hit_t=hit_t, hit_cnt=hit_c, slot_cnt=slots, cap=cap)
+
+    def backward(self, ray_o, ray_d, bg, means, scales, rots, opac, shs, sh_degree: int, fwd_out, dL_dout,
+                 hits: dict | None = None, scale_modifier: float = 1.0, flags: int = 0):
+        P, means, scales, rots, opac = self._gauss(means, scales, rots, opac)
+        R, lead, o, stride, d = self._rays(ray_o, ray_d)
+        shs = _f32(shs, "shs", (3,)); M = shs.shape[1]
+        bg = _f32(bg, "bg").reshape(-1)
+        fwd_out = _f32(fwd_out, "out_attr_float32", (NUM_CHANNELS,)); dL = _f32(dL_dout, "dL_dout", (NUM_CHANNELS,))
+        if fwd_out.numel() != R * NUM_CHANNELS or dL.numel() != R * NUM_CHANNELS:
+            raise LrtError("out / dL_dout must be (..., 9) matching the rays")
+        dev = self.device
+        with torch.cuda.device(dev):
+            g_means = torch.empty((P, 3), dtype=torch.float32, device=dev)
+            g_shs = torch.empty((P, M, 3), dtype=torch.float32, device=dev)
+            g_opac = torch.empty((P, 1), dtype=torch.float32, device=dev)
+            g_scales = torch.empty((P, 2), dtype=torch.float32, device=dev)
+            g_rots = torch.empty((P, 4), dtype=torch.float32, device=dev)
+            hg = ht = hc = None; cap = 0
+            if hits is not None and hits.get("hit_gidx") is not None:
+                hg, ht, hc, cap = hits["hit_gidx"], hits["hit_t"], hits["hit_cnt"], int(hits["cap"])
+            self._check(self.lib.lrt_backward(self._h, R, _ptr(o), stride, _ptr(d), _ptr(bg), P, _ptr(means), _ptr(scales),
+                                              _ptr(rots), _ptr(opac), _ptr(shs), int(sh_degree), M, c_float(scale_modifier),
+                                              _ptr(fwd_out), _ptr(dL), _ptr(hg), _ptr(ht), _ptr(hc), cap,
+                                              _ptr(g_means), _ptr(g_shs), _ptr(g_opac), _ptr(g_scales), _ptr(g_rots),
+                                              int(flags), _stream(dev)))
+        return dict(means=g_means, shs=g_shs, opac=g_opac, scales=g_scales, rots=g_rots)
