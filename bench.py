@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — LiDAR Mrays/s forward+backward on synthetic Waymo-shaped frames (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle/_ref)
+
+One "step" = one LiDAR frame through the hot path exactly as the reference's raytracing() runs it:
+acceleration-structure (re)build from the Gaussian parameters + forward + backward.
+Workload (N = 1): P = 2 M Gaussians (street-like surfel cloud), 64 x 2650 = 169 600
+rays (Waymo top LiDAR), SH degree 3; every step is a different frame pose. N > 1: frames shard across
+ranks (weak scaling, no data-path collective); the rendered buffers are gathered once per sweep.
+
+Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "lidar-rt_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "lidar_mrays_per_s_fwd_bwd"
+UNIT = "Mrays/s"
+H, W = 64, 2650
+BG = np.array([0.0, 0.0, 1.0], np.float32)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gaussians", type=int, default=2_000_000)
+    ap.add_argument("--sh-degree", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(args, n_frames, rank, world):
+    from lidar_rt_b200 import synthetic as syn
+    sc = syn.make_street_scene(args.gaussians, seed=args.seed)
+    inc = syn.waymo_inclinations()
+    frames = []
+    rng = np.random.default_rng(1000 + rank)
+    for i in range(n_frames):
+        f = rank + i * world
+        o, d = syn.lidar_rays(H, W, inc, syn.sensor_pose(f))
+        dL = np.zeros((H, W, 9), np.float32)
+        dL[..., :4] = rng.standard_normal((H, W, 4)).astype(np.float32)       # N(0,1) on channels 0-3
+        frames.append((f, o, d, dL))
+    return sc, frames
+
+
+# --------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle/_ref = its forward.cu/backward.cu
+    compiled as host code; the C restatement if _ref was never built), on a bounded ray sample."""
+    if rank != 0:
+        return
+    from oracle.oracle import ORC_BVH, Oracle, Ref, ref_available
+    sc, frames = make_inputs(args, args.steps + args.warmup, 0, 1)
+    kind = "reference" if ref_available() else "port"
+    impl = Ref() if kind == "reference" else Oracle(False)
+    cores = Oracle(False).threads
+    R = H * W
+    stride_h, stride_w = 4, 10                     # 16 x 265 = 4240 rays spread over the whole range image
+    times = []
+    t_build = None
+
+    def fwd_bwd(o, ds, dLs):
+        a = (o, ds, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, args.sh_degree)
+        kw = {} if kind == "reference" else {"flags": ORC_BVH}
+        t0 = time.perf_counter()
+        out = impl.forward(*a, **kw); impl.backward(*a, out["out"], dLs, **kw)
+        return time.perf_counter() - t0
+
+    for i, (f, o, d, dL) in enumerate(frames):
+        ds = np.ascontiguousarray(d[::stride_h, ::stride_w]); dLs = np.ascontiguousarray(dL[::stride_h, ::stride_w]).reshape(-1, 9)
+        n = ds.shape[0] * ds.shape[1]
+        if t_build is None:
+            # accel-build share of a pass, measured once: the same calls on a single ray. The per-ray cost is
+            # then scaled to the full 169 600-ray frame while the per-frame build is counted once per pass.
+            t_build = fwd_bwd(o, np.ascontiguousarray(ds[:1, :1]), dLs[:1])
+        t_all = fwd_bwd(o, ds, dLs)
+        t_frame = t_build + max(t_all - t_build, 1e-9) * (R / n)
+        if i >= args.warmup:
+            times.append(t_frame)
+    ms = 1e3 * float(np.mean(times))
+    val = R / (ms * 1e-3) / 1e6
+    sample = (f"{H // stride_h}x{W // stride_w}={n} of {R} rays per frame (every {stride_h}th beam, every {stride_w}th azimuth), "
+              f"P={args.gaussians}; frame time = accel build + traced-sample time x {R / n:.0f}")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"waymo_static_{args.gaussians // 1000}k_gaussians_64x2650_rays_fwd_bwd_sh{args.sh_degree}",
+                       "gaussians": args.gaussians, "rays_per_frame": R, "sh_degree": args.sh_degree},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------- CPU baseline leg
+def cpu_baseline(args, sc, frame):
+    from oracle.oracle import ORC_BVH, Oracle, Ref, ref_available
+    kind = "reference" if ref_available() else "port"
+    impl = Ref() if kind == "reference" else Oracle(False)
+    cores = Oracle(False).threads
+    f, o, d, dL = frame
+    R = H * W
+    n_target = args.cpu_sample_rays or max(1060, min(R, 330 * cores))
+    sw = max(1, int(round((R / n_target) / 4)))
+    ds = np.ascontiguousarray(d[::4, ::sw]); dLs = np.ascontiguousarray(dL[::4, ::sw]).reshape(-1, 9)
+    n = ds.shape[0] * ds.shape[1]
+    kw = {} if kind == "reference" else {"flags": ORC_BVH}
+    a = (o, ds, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, args.sh_degree)
+    t0 = time.perf_counter(); out = impl.forward(*a, **kw); impl.backward(*a, out["out"], dLs, **kw); t_all = time.perf_counter() - t0
+    one = np.ascontiguousarray(ds[:1, :1]); a1 = (o, one, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, args.sh_degree)
+    t0 = time.perf_counter(); o1 = impl.forward(*a1, **kw); impl.backward(*a1, o1["out"], dLs[:1], **kw); t_build = time.perf_counter() - t0
+    t_frame = t_build + max(t_all - t_build, 1e-9) * (R / n)
+    return {"value": R / t_frame / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n} of {R} rays of one frame (P={args.gaussians}), fwd+bwd; frame time = accel build ({t_build:.2f} s) + "
+                      f"traced-sample time ({t_all - t_build:.2f} s) x {R / n:.0f}"}
+
+
+# --------------------------------------------------------------------------------- B200 arm
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from lidar_rt_b200 import native
+    from lidar_rt_b200.scene import GaussianAsset
+    from lidar_rt_b200.sweep import gather_frames
+    import lib.gaussian_renderer as gr
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+    n_frames = K + Wm
+    sc, frames = make_inputs(args, n_frames, rank, world)
+    R = H * W
+    D = args.sh_degree
+    cu = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)
+    means, scales, rots, opac, shs = map(cu, (sc.means, sc.scales, sc.rots, sc.opac, sc.shs))
+    bg = cu(BG)
+    ctx = native.Context(dev)
+    # device-resident per-frame inputs for the kernel-only number
+    d_dev = [cu(d) for (_, _, d, _) in frames]
+    o_dev = [cu(o) for (_, o, _, _) in frames]
+    dL_dev = [cu(dL) for (_, _, _, dL) in frames]
+    # pinned host copies for the end-to-end number
+    d_pin = [torch.from_numpy(d).pin_memory() for (_, _, d, _) in frames]
+    o_pin = [torch.from_numpy(o).pin_memory() for (_, o, _, _) in frames]
+    dL_pin = [torch.from_numpy(dL).pin_memory() for (_, _, _, dL) in frames]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_kernels(i, keep=None):
+        ctx.build(means, scales, rots, opac)                                   # rebuild every frame, like raytracing():145
+        f = ctx.forward(o_dev[i], d_dev[i], bg, means, scales, rots, opac, shs, D)
+        ctx.backward(o_dev[i], d_dev[i], bg, means, scales, rots, opac, shs, D, f["out"], dL_dev[i], hits=f)
+        if keep is not None:
+            keep.append(f["out"])
+        return f
+
+    # ---- 1. kernel-only throughput (inputs resident in HBM)
+    for i in range(Wm):
+        step_kernels(i)
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = ctx.info().kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    outs = []
+    ev0.record()
+    for i in range(Wm, Wm + K):
+        step_kernels(i, outs)
+    if world > 1:                                                              # the sweep's only collective
+        gather_frames(torch.stack(outs, 0), K * world, rank, world)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ctx.info().kernel_launches - launches0
+    del outs
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * K * R / (ms_total * 1e-3) / 1e6
+
+    # ---- 2. per-phase device times + hit statistics (separate instrumented pass)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    Ksum = Kcsum = 0.0
+    for j, i in enumerate(range(Wm, Wm + K)):
+        evs[j][0].record(); ctx.build(means, scales, rots, opac)
+        evs[j][1].record(); f = ctx.forward(o_dev[i], d_dev[i], bg, means, scales, rots, opac, shs, D)
+        evs[j][2].record(); ctx.backward(o_dev[i], d_dev[i], bg, means, scales, rots, opac, shs, D, f["out"], dL_dev[i], hits=f)
+        evs[j][3].record()
+    torch.cuda.synchronize()
+    t_build = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    t_fwd = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    t_bwd = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+    f = ctx.forward(o_dev[Wm], d_dev[Wm], bg, means, scales, rots, opac, shs, D, want_slots=True)
+    Ksum = float(f["slot_cnt"].sum().item()); Kcsum = float(f["hit_cnt"].sum().item())
+    overflow = float((f["hit_cnt"] > f["cap"]).float().mean().item())
+    nsh = 12 * (D + 1) ** 2
+    P = args.gaussians
+    # algorithmic bytes per launch, SURVEY.md §8d (shared ray origin); see DESIGN.md §Roofline
+    B_fwd = R * (12 + 36) + Ksum * 40 + Kcsum * (nsh + 8)
+    B_bwd = R * (12 + 36 + 36) + Kcsum * (8 + 40 + nsh + 2 * (40 + nsh))
+    B_build = P * (40 + 64 + 24) + 2 * P * 8 * 4 + (P / 7.0) * 192
+    peak, peak_src = measured_peak()
+    phases = {"build": (t_build, B_build), "forward": (t_fwd, B_fwd), "backward": (t_bwd, B_bwd)}
+    dom = max(phases, key=lambda k: phases[k][0])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": phases[dom][1] / (phases[dom][0] * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": phases[dom][1] / (phases[dom][0] * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes": phases[dom][1], "ms": phases[dom][0],
+                "phases": {k: {"ms": v[0], "algorithmic_bytes": v[1], "gbs": v[1] / (v[0] * 1e-3) / 1e9} for k, v in phases.items()},
+                "step_frac_of_peak": (B_fwd + B_bwd + B_build) / (ms_step * 1e-3) / 1e9 / peak,
+                "hits_per_ray_evaluated": Ksum / R, "hits_per_ray_contributing": Kcsum / R, "hit_list_overflow_frac": overflow}
+
+    # ---- 3. end to end through the public API (raytracing() + autograd), host buffers in pinned memory
+    asset = GaussianAsset(sc, device=dev)
+    h2d = d_pin[0].numel() * 4 + o_pin[0].numel() * 4 + dL_pin[0].numel() * 4
+    out_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()      # intensity, raydrop, depth
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    d2h = out_host.numel() * 4 + 4
+    bg_cpu = torch.tensor(BG)
+
+    def step_e2e(i):
+        rd = d_pin[i].to(dev, non_blocking=True)
+        centre = o_pin[i].to(dev, non_blocking=True).reshape(3)
+        dL = dL_pin[i].to(dev, non_blocking=True)
+        ro = centre[None, None].expand(H, W, 3)
+        for p in asset.parameters():
+            p.grad = None
+        pkg = gr.raytracing(frames[i][0], [asset], (ro, rd, centre), bg_cpu, None)
+        rendered = torch.cat([pkg["intensity"], pkg["raydrop"], pkg["depth"]], -1)
+        loss = (pkg["intensity"] * dL[..., 0:1]).sum() + (pkg["depth"] * dL[..., 3:4]).sum() + (pkg["raydrop"] * dL[..., 2:3]).sum()
+        loss.backward()
+        out_host.copy_(rendered.detach(), non_blocking=True)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+
+    for i in range(Wm):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Wm, Wm + K):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    t = torch.tensor([t_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_e2e = float(t.item())
+    e2e = {"value": world * K * R / t_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": 1e3 * t_e2e / K, "api": "lib.gaussian_renderer.raytracing() + loss.backward()"}
+
+    # ---- 4. CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(args, sc, frames[Wm])
+        except Exception as ex:      # the checker must never take the bench line down
+            cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"waymo_static_{P // 1000}k_gaussians_64x2650_rays_fwd_bwd_sh{D}", "gaussians": P,
+                           "rays_per_frame": R, "sh_degree": D, "step": "lbvh rebuild + forward + backward per frame",
+                           "l2": "inputs larger than L2 (Gaussian parameters 464 MB + SH gradients 384 MB per step vs 126 MB L2)",
+                           "frames_per_rank": K, "sharding": "frame-parallel, replicated Gaussians, one gather of rendered buffers per sweep"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

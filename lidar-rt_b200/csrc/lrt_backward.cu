@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(128) k_backward_trace(BvhView bvh, BwArgs a, i
     RayState st;
     ray_state_init(st, r, a.fwd_out, a.dL);
     float base = 0.f, dpt = 0.f;
+    int last = -1;
     for (;;) {
         RaySetup rs;
         ray_setup(rs, o, d, base);
@@ -263,7 +264,10 @@ __global__ void __launch_bounds__(128) k_backward_trace(BvhView bvh, BwArgs a, i
             const unsigned long long key = hits[i];
             const int prim = (int)(unsigned)(key & 0xffffffffull);
             dpt = __uint_as_float((unsigned)(key >> 32)) + base;
+            if (dpt < LRT_MIN_T) continue;                                            // backward.cu:528
             const int g = __float_as_int(ld_f4(&bvh.rec[prim].r2).w);
+            if (g == last) continue;                                                  // :534-536
+            last = g;
             const int res = hit_backward<true>(g, dpt, o, d, dirn, a.means, a.scales, a.rots, a.opac, a.shs, a.D, a.M, a.mod,
                                                bg, a.flags, st, a.go);
             if (res == 2) { terminated = true; break; }

@@ -88,7 +88,9 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P_pad) return;
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    // empty slot marker: lo = hi = +FLT_MAX on every axis. A slab test maps it to an interval beyond
+    // any tmax (or before 0), so it is never entered; k_fit skips it in unions.
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
     if (i < P) {
         const int g = (int)perm[i];
         const float mu[3] = {means[3 * g], means[3 * g + 1], means[3 * g + 2]};
@@ -113,11 +115,11 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
                 const float e = fabsf(d.tu[k]) * ax + fabsf(d.tv[k]) * ay;
                 const float pad = 1e-4f + 1e-5f * (fabsf(mu[k]) + e);       // slab tests are a filter, the quad test decides
                 lo[k] = mu[k] - e - pad; hi[k] = mu[k] + e + pad;
-                if (!(lo[k] <= hi[k])) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
             }
-            if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) {
+            if (!(lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]) || fabsf(lo[0]) > 1e30f || fabsf(hi[0]) > 1e30f ||
+                fabsf(lo[1]) > 1e30f || fabsf(hi[1]) > 1e30f || fabsf(lo[2]) > 1e30f || fabsf(hi[2]) > 1e30f) {
 #pragma unroll
-                for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+                for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = FLT_MAX; }
             }
         }
     } else {
@@ -140,14 +142,19 @@ __global__ void __launch_bounds__(256) k_fit(int n_parent, int n_child, const No
     if (t >= n_parent * 8) return;
     const int j = t >> 3, c = t & 7, cj = 8 * j + c;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool any = false;
     if (cj < n_child) {
         const Node8& ch = child[cj];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            lo[0] = fminf(lo[0], ch.lox[k]); lo[1] = fminf(lo[1], ch.loy[k]); lo[2] = fminf(lo[2], ch.loz[k]);
-            hi[0] = fmaxf(hi[0], ch.hix[k]); hi[1] = fmaxf(hi[1], ch.hiy[k]); hi[2] = fmaxf(hi[2], ch.hiz[k]);
+            if (ch.lox[k] != FLT_MAX) {                         // skip empty slots
+                any = true;
+                lo[0] = fminf(lo[0], ch.lox[k]); lo[1] = fminf(lo[1], ch.loy[k]); lo[2] = fminf(lo[2], ch.loz[k]);
+                hi[0] = fmaxf(hi[0], ch.hix[k]); hi[1] = fmaxf(hi[1], ch.hiy[k]); hi[2] = fmaxf(hi[2], ch.hiz[k]);
+            }
         }
     }
+    if (!any) { lo[0] = lo[1] = lo[2] = FLT_MAX; hi[0] = hi[1] = hi[2] = FLT_MAX; }
     Node8& n = parent[j];
     n.lox[c] = lo[0]; n.loy[c] = lo[1]; n.loz[c] = lo[2];
     n.hix[c] = hi[0]; n.hiy[c] = hi[1]; n.hiz[c] = hi[2];

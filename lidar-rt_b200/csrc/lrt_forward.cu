@@ -45,7 +45,7 @@ k_forward(BvhView bvh, int R, const float* __restrict__ ray_o, int ray_o_stride,
     const int nb = (D + 1) * (D + 1);
 
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, W = 0.f, T = 1.f, testT = 1.f, base = 0.f, dpt = 0.f;
-    int ncontrib = 0, nslots = 0;
+    int ncontrib = 0, nslots = 0, last = -1;
     for (;;) {
         RaySetup rs;
         ray_setup(rs, o, d, base);
@@ -64,6 +64,11 @@ k_forward(BvhView bvh, int R, const float* __restrict__ ray_o, int ray_o_stride,
             const float x0 = o[0] + dpt * d[0], x1 = o[1] + dpt * d[1], x2 = o[2] + dpt * d[2];
             const float4 a0 = ld_f4(&bvh.rec[prim].r0), a1 = ld_f4(&bvh.rec[prim].r1);
             const float4 a2 = ld_f4(&bvh.rec[prim].r2), a3 = ld_f4(&bvh.rec[prim].r3);
+            const int g = __float_as_int(a2.w);
+            // :220-224 — a re-based round can find the previous round's last surfel again at t' ~ +0
+            // (the 1e-5 step is below one ulp of the depth beyond 128 m): it must not composite twice
+            if (g == last) continue;
+            last = g;
             const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
             const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;                        // :139
             const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
@@ -78,7 +83,6 @@ k_forward(BvhView bvh, int R, const float* __restrict__ ray_o, int ray_o_stride,
             testT = T * (1.0f - alpha);
             if (testT < LRT_T_MIN) { terminated = true; break; }                      // :253-257
             const float w = alpha * T;
-            const int g = __float_as_int(a2.w);
             float sh[48], c[3]; bool cl;
             load_sh(shs, g, M, nb, sh);
             sh_colour<false>(D, dirn, sh, c, cl, nullptr);

@@ -91,7 +91,7 @@ typedef struct {
 typedef struct {
     int P;
     gauss_t* g;
-    /* median BVH over Gaussians (candidate filter; validated against brute force in tests) */
+    /* Morton-ordered BVH over Gaussians (candidate filter; validated against brute force in tests) */
     int n_nodes;
     real* nlo; real* nhi;        /* 3 per node */
     int* nleft; int* nright; int* nfirst; int* ncount;
@@ -134,51 +134,74 @@ static void derive(const real* mu, const real* sc, const real* q, real op, real 
     }
 }
 
-/* ---------------- candidate filter: median-split BVH over Gaussian AABBs ---------------- */
+/* ---------------- candidate filter: Morton-ordered binary BVH over Gaussian AABBs ---------------- */
 
-typedef struct { const gauss_t* g; int axis; } sortctx_t;
-static sortctx_t g_sortctx;   /* build is single-threaded */
-static int cmp_center(const void* a, const void* b)
+/* Morton order once (qsort), then split every range at its middle index; boxes bottom-up. */
+typedef struct { uint64_t key; int id; } mkey_t;
+static int cmp_mkey(const void* a, const void* b)
 {
-    const gauss_t* ga = &g_sortctx.g[*(const int*)a]; const gauss_t* gb = &g_sortctx.g[*(const int*)b];
-    const real ca = ga->mu[g_sortctx.axis], cb = gb->mu[g_sortctx.axis];
-    return (ca > cb) - (ca < cb);
+    const mkey_t* x = (const mkey_t*)a; const mkey_t* y = (const mkey_t*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return (x->id > y->id) - (x->id < y->id);
+}
+static uint64_t spread21(uint64_t v)
+{
+    v &= 0x1fffffULL;
+    v = (v | v << 32) & 0x1f00000000ffffULL;
+    v = (v | v << 16) & 0x1f0000ff0000ffULL;
+    v = (v | v << 8) & 0x100f00f00f00f00fULL;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+    v = (v | v << 2) & 0x1249249249249249ULL;
+    return v;
 }
 
 static int bvh_rec(scene_t* s, int first, int count)
 {
     const int id = s->n_nodes++;
-    real lo[3] = {(real)1e30, (real)1e30, (real)1e30}, hi[3] = {(real)-1e30, (real)-1e30, (real)-1e30};
-    real clo[3] = {(real)1e30, (real)1e30, (real)1e30}, chi[3] = {(real)-1e30, (real)-1e30, (real)-1e30};
-    for (int i = first; i < first + count; i++) {
-        const gauss_t* g = &s->g[s->order[i]];
-        for (int k = 0; k < 3; k++) {
-            if (g->lo[k] < lo[k]) lo[k] = g->lo[k];
-            if (g->hi[k] > hi[k]) hi[k] = g->hi[k];
-            if (g->mu[k] < clo[k]) clo[k] = g->mu[k];
-            if (g->mu[k] > chi[k]) chi[k] = g->mu[k];
-        }
-    }
-    for (int k = 0; k < 3; k++) { s->nlo[3 * id + k] = lo[k]; s->nhi[3 * id + k] = hi[k]; }
     s->nfirst[id] = first; s->ncount[id] = 0; s->nleft[id] = s->nright[id] = -1;
-    int axis = 0;
-    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
-    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
-    if (count <= 8 || !(chi[axis] > clo[axis])) { s->ncount[id] = count; return id; }
-    g_sortctx.g = s->g; g_sortctx.axis = axis;
-    qsort(s->order + first, (size_t)count, sizeof(int), cmp_center);
+    real* lo = s->nlo + 3 * id; real* hi = s->nhi + 3 * id;
+    if (count <= 8) {
+        for (int k = 0; k < 3; k++) { lo[k] = (real)1e30; hi[k] = (real)-1e30; }
+        for (int i = first; i < first + count; i++) {
+            const gauss_t* g = &s->g[s->order[i]];
+            for (int k = 0; k < 3; k++) { if (g->lo[k] < lo[k]) lo[k] = g->lo[k]; if (g->hi[k] > hi[k]) hi[k] = g->hi[k]; }
+        }
+        s->ncount[id] = count;
+        return id;
+    }
     const int half = count / 2;
     const int l = bvh_rec(s, first, half);
     const int r = bvh_rec(s, first + half, count - half);
     s->nleft[id] = l; s->nright[id] = r;
+    lo = s->nlo + 3 * id; hi = s->nhi + 3 * id;
+    for (int k = 0; k < 3; k++) {
+        lo[k] = s->nlo[3 * l + k] < s->nlo[3 * r + k] ? s->nlo[3 * l + k] : s->nlo[3 * r + k];
+        hi[k] = s->nhi[3 * l + k] > s->nhi[3 * r + k] ? s->nhi[3 * l + k] : s->nhi[3 * r + k];
+    }
     return id;
 }
 
 static void bvh_build(scene_t* s)
 {
     int nv = 0;
-    s->order = (int*)malloc(sizeof(int) * (size_t)(s->P > 0 ? s->P : 1));
-    for (int i = 0; i < s->P; i++) if (s->g[i].valid) s->order[nv++] = i;
+    real clo[3] = {(real)1e30, (real)1e30, (real)1e30}, chi[3] = {(real)-1e30, (real)-1e30, (real)-1e30};
+    mkey_t* mk = (mkey_t*)malloc(sizeof(mkey_t) * (size_t)(s->P > 0 ? s->P : 1));
+    for (int i = 0; i < s->P; i++) if (s->g[i].valid)
+        for (int k = 0; k < 3; k++) { if (s->g[i].mu[k] < clo[k]) clo[k] = s->g[i].mu[k]; if (s->g[i].mu[k] > chi[k]) chi[k] = s->g[i].mu[k]; }
+    for (int i = 0; i < s->P; i++) if (s->g[i].valid) {
+        uint64_t key = 0;
+        for (int k = 0; k < 3; k++) {
+            const double ext = (double)chi[k] - (double)clo[k];
+            double t = ext > 0 ? ((double)s->g[i].mu[k] - (double)clo[k]) / ext * 2097151.0 : 0.0;
+            if (t < 0) t = 0; if (t > 2097151.0) t = 2097151.0;
+            key |= spread21((uint64_t)t) << (2 - k);
+        }
+        mk[nv].key = key; mk[nv].id = i; nv++;
+    }
+    qsort(mk, (size_t)nv, sizeof(mkey_t), cmp_mkey);
+    s->order = (int*)malloc(sizeof(int) * (size_t)(nv > 0 ? nv : 1));
+    for (int i = 0; i < nv; i++) s->order[i] = mk[i].id;
+    free(mk);
     const int cap = 2 * (nv > 0 ? nv : 1);
     s->nlo = (real*)malloc(sizeof(real) * 3 * (size_t)cap); s->nhi = (real*)malloc(sizeof(real) * 3 * (size_t)cap);
     s->nleft = (int*)malloc(sizeof(int) * (size_t)cap); s->nright = (int*)malloc(sizeof(int) * (size_t)cap);
