@@ -6,7 +6,7 @@ set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 HOSTCXX="/usr/bin/g++"; [ -x "$HOSTCXX" ] || HOSTCXX="g++"
-OUT="$HERE/liblidar_rt_b200.so"
+OUT="${LRT_OUT:-$HERE/liblidar_rt_b200.so}"
 "$NVCC" -ccbin "$HOSTCXX" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
     -Xcompiler -fPIC -shared ${LRT_NVCC_EXTRA:-} \
     "$HERE/lrt_api.cu" "$HERE/lrt_build.cu" "$HERE/lrt_forward.cu" "$HERE/lrt_backward.cu" \

@@ -32,7 +32,7 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
 {
     if (!ctx) return LRT_OK;
     cudaSetDevice(ctx->device);
-    DevBuf* bufs[] = {&ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->sort_tmp, &ctx->bounds};
+    DevBuf* bufs[] = {&ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     delete ctx;
     return LRT_OK;

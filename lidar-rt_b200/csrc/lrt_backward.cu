@@ -255,17 +255,21 @@ __global__ void __launch_bounds__(128) k_backward_trace(BvhView bvh, BwArgs a, i
         RaySetup rs;
         ray_setup(rs, o, d, base);
         unsigned long long kb[LRT_KBUF];
+#ifdef LRT_STATS
+        int nv_ = 0;
+        const int n = trace_round(bvh, rs, kb, nv_);
+#else
         const int n = trace_round(bvh, rs, kb);
+#endif
         unsigned long long hits[LRT_KBUF];
 #pragma unroll
         for (int i = 0; i < LRT_KBUF; i++) hits[i] = kb[i];
         bool terminated = false;
         for (int i = 0; i < n; i++) {
             const unsigned long long key = hits[i];
-            const int prim = (int)(unsigned)(key & 0xffffffffull);
+            const int g = (int)(unsigned)(key & 0xffffffffull);
             dpt = __uint_as_float((unsigned)(key >> 32)) + base;
             if (dpt < LRT_MIN_T) continue;                                            // backward.cu:528
-            const int g = __float_as_int(ld_f4(&bvh.rec[prim].r2).w);
             if (g == last) continue;                                                  // :534-536
             last = g;
             const int res = hit_backward<true>(g, dpt, o, d, dirn, a.means, a.scales, a.rots, a.opac, a.shs, a.D, a.M, a.mod,

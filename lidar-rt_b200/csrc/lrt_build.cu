@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(256) k_morton(int P, const float* __restrict__
 __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigned* __restrict__ perm,
                                                  const float* __restrict__ means, const float* __restrict__ scales,
                                                  const float* __restrict__ rots, const float* __restrict__ opac,
-                                                 float mod, SurfelRec* __restrict__ rec, Node8* __restrict__ leaf)
+                                                 float mod, SurfelRec* __restrict__ rec, Node8* __restrict__ leaf,
+                                                 int* __restrict__ iperm)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P_pad) return;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
         r.r2 = make_float4(d.Lv[0], d.Lv[1], d.Lv[2], __int_as_float(g));
         r.r3 = make_float4(d.n[0], d.n[1], d.n[2], 0.0f);
         rec[i] = r;
+        iperm[g] = i;
         const bool valid = (d.f == d.f) && d.f >= 0.0f && d.f < 1e30f;
         if (valid) {
             const float ax = mod * d.sx * d.f, ay = mod * d.sy * d.f;
@@ -184,6 +186,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->rec, sizeof(SurfelRec) * (size_t)P_pad));
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->nodes, sizeof(Node8) * (size_t)total));
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->perm_a, sizeof(unsigned) * (size_t)P));
+    LRT_CUDA_TRY(ctx, ctx->reserve(ctx->iperm, sizeof(int) * (size_t)P));
     const int TB = 256;
     if (!refit) {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->perm_b, sizeof(unsigned) * (size_t)P));
@@ -209,7 +212,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
     }
     Node8* nodes = (Node8*)ctx->nodes.p;
     k_records<<<(P_pad + TB - 1) / TB, TB, 0, s>>>(P, P_pad, (const unsigned*)ctx->perm_a.p, means, scales, rots, opac,
-                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0]);
+                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0], (int*)ctx->iperm.p);
     for (int l = 1; l < L; l++)
         k_fit<<<(cnt[l] * 8 + TB - 1) / TB, TB, 0, s>>>(cnt[l], cnt[l - 1], nodes + off[l - 1], nodes + off[l]);
     ctx->launches += L;

@@ -49,6 +49,7 @@ struct __align__(16) Node8 { float lox[8], loy[8], loz[8], hix[8], hiy[8], hiz[8
 struct BvhView {
     const SurfelRec* rec;         // (P_pad)
     const Node8* nodes;           // all levels, level 0 (children = surfels) first
+    const int* iperm;             // (P) caller's Gaussian index -> position in Morton order
     int level_off[LRT_MAX_LEVELS];
     int levels;
     int P;

@@ -23,7 +23,7 @@ struct lrt_ctx {
     long long n_nodes = 0;
     bool built = false;
     float scale_modifier = 1.0f;
-    DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, sort_tmp, bounds;
+    DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, iperm, sort_tmp, bounds;
     long long builds = 0, refits = 0;
     int launches = 0;
 
@@ -46,13 +46,14 @@ struct lrt_ctx {
     }
     size_t total_bytes() const
     {
-        return rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + sort_tmp.cap + bounds.cap;
+        return rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + iperm.cap + sort_tmp.cap + bounds.cap;
     }
     BvhView view() const
     {
         BvhView v;
         v.rec = (const SurfelRec*)rec.p;
         v.nodes = (const Node8*)nodes.p;
+        v.iperm = (const int*)iperm.p;
         for (int i = 0; i < LRT_MAX_LEVELS; i++) v.level_off[i] = level_off[i];
         v.levels = levels;
         v.P = P;

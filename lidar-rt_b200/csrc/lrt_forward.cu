@@ -46,29 +46,36 @@ k_forward(BvhView bvh, int R, const float* __restrict__ ray_o, int ray_o_stride,
 
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, W = 0.f, T = 1.f, testT = 1.f, base = 0.f, dpt = 0.f;
     int ncontrib = 0, nslots = 0, last = -1;
+#ifdef LRT_STATS
+    int node_visits = 0;
+#endif
     for (;;) {
         RaySetup rs;
         ray_setup(rs, o, d, base);
         unsigned long long kb[LRT_KBUF];
+#ifdef LRT_STATS
+        const int n = trace_round(bvh, rs, kb, node_visits);
+#else
         const int n = trace_round(bvh, rs, kb);
+#endif
         unsigned long long hits[LRT_KBUF];
 #pragma unroll
         for (int i = 0; i < LRT_KBUF; i++) hits[i] = kb[i];
         bool terminated = false;
         for (int i = 0; i < n; i++) {
             const unsigned long long key = hits[i];
-            const int prim = (int)(unsigned)(key & 0xffffffffull);
+            const int g = (int)(unsigned)(key & 0xffffffffull);
             nslots++;
             dpt = __uint_as_float((unsigned)(key >> 32)) + base;                      // forward.cu:212
             if (dpt < LRT_MIN_T) continue;                                            // :214
             const float x0 = o[0] + dpt * d[0], x1 = o[1] + dpt * d[1], x2 = o[2] + dpt * d[2];
-            const float4 a0 = ld_f4(&bvh.rec[prim].r0), a1 = ld_f4(&bvh.rec[prim].r1);
-            const float4 a2 = ld_f4(&bvh.rec[prim].r2), a3 = ld_f4(&bvh.rec[prim].r3);
-            const int g = __float_as_int(a2.w);
             // :220-224 — a re-based round can find the previous round's last surfel again at t' ~ +0
             // (the 1e-5 step is below one ulp of the depth beyond 128 m): it must not composite twice
             if (g == last) continue;
             last = g;
+            const int prim = __ldg(bvh.iperm + g);
+            const float4 a0 = ld_f4(&bvh.rec[prim].r0), a1 = ld_f4(&bvh.rec[prim].r1);
+            const float4 a2 = ld_f4(&bvh.rec[prim].r2), a3 = ld_f4(&bvh.rec[prim].r3);
             const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
             const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;                        // :139
             const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
@@ -103,7 +110,11 @@ k_forward(BvhView bvh, int R, const float* __restrict__ ray_o, int ray_o_stride,
     op[0] = C0 + T * bg[0]; op[1] = C1 + T * bg[1]; op[2] = C2 + T * bg[2];          // :296-305
     op[3] = Dp; op[4] = W; op[5] = 0.f; op[6] = 0.f; op[7] = 0.f; op[8] = T;
     if (hit_cnt) hit_cnt[r] = ncontrib;
+#ifdef LRT_STATS
+    if (slot_cnt) slot_cnt[r] = (nslots & 0xffff) | (min(node_visits, 32767) << 16);   // development statistics build
+#else
     if (slot_cnt) slot_cnt[r] = nslots;
+#endif
 }
 
 } // namespace

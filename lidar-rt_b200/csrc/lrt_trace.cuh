@@ -38,7 +38,7 @@ __device__ __forceinline__ void ray_setup(RaySetup& r, const float* o, const flo
 }
 
 // Analytic proxy test, same operation order as the oracle's quad_hit().
-__device__ __forceinline__ bool quad_hit(const SurfelRec* __restrict__ rec, int prim, const RaySetup& r, float& t_out)
+__device__ __forceinline__ bool quad_hit(const SurfelRec* __restrict__ rec, int prim, const RaySetup& r, float& t_out, int& g_out)
 {
     const float4 a0 = ld_f4(&rec[prim].r0), a3 = ld_f4(&rec[prim].r3);
     const float c0 = a0.x - r.ox, c1 = a0.y - r.oy, c2 = a0.z - r.oz;
@@ -52,10 +52,11 @@ __device__ __forceinline__ bool quad_hit(const SurfelRec* __restrict__ rec, int 
     const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
     if (!(fabsf(u) <= a0.w && fabsf(v) <= a0.w)) return false;
     t_out = t;
+    g_out = __float_as_int(a2.w);
     return t < LRT_TMAX;
 }
 
-// Sorted insertion into the register-resident k-buffer (ascending 64-bit keys = (t bits, surfel)).
+// Sorted insertion into the register-resident k-buffer (ascending 64-bit keys = (t' bits, Gaussian id)).
 __device__ __forceinline__ void kbuf_insert(unsigned long long (&kb)[LRT_KBUF], unsigned long long key)
 {
     if (key >= kb[LRT_KBUF - 1]) return;
@@ -94,7 +95,11 @@ __device__ __forceinline__ unsigned node_mask(const Node8* __restrict__ node, co
 
 // One round. On return `kb` holds the nearest hits ascending; returns how many are valid (<= 16).
 // 16 valid entries <=> the reference's `payload.cnt >= CHUNK_SIZE` (forward.cu:282).
-__device__ __forceinline__ int trace_round(const BvhView& bvh, const RaySetup& r, unsigned long long (&kb)[LRT_KBUF])
+__device__ __forceinline__ int trace_round(const BvhView& bvh, const RaySetup& r, unsigned long long (&kb)[LRT_KBUF]
+#ifdef LRT_STATS
+                                           , int& node_visits
+#endif
+                                           )
 {
 #pragma unroll
     for (int i = 0; i < LRT_KBUF; i++) kb[i] = LRT_KEY_EMPTY;
@@ -105,13 +110,16 @@ __device__ __forceinline__ int trace_round(const BvhView& bvh, const RaySetup& r
     for (;;) {
         const float tmax = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32));
         unsigned m = node_mask(bvh.nodes + bvh.level_off[level] + node, r, tmax);
+#ifdef LRT_STATS
+        node_visits++;
+#endif
         if (level == 0) {
             while (m) {
                 const int c = __ffs(m) - 1; m &= m - 1;
                 const int prim = (int)(node * 8u + c);
-                float t;
-                if (quad_hit(bvh.rec, prim, r, t))
-                    kbuf_insert(kb, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)prim);
+                float t; int g;
+                if (quad_hit(bvh.rec, prim, r, t, g))     // ties in t' resolve by the caller's Gaussian index
+                    kbuf_insert(kb, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g);
             }
         }
         if (m == 0) {                                   // nothing (left) below this node: climb

@@ -15,7 +15,7 @@ from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "liblidar_rt_b200.so")
+LIB_PATH = os.environ.get("LIDAR_RT_B200_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "liblidar_rt_b200.so")
 
 LRT_FLAG_FIX_BG_GRAD = 1
 NUM_CHANNELS = 9
