@@ -94,6 +94,15 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
                  float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
                  float* dL_drots, int flags, void* stream);
 
+/* Tuning knobs; none of them changes results.
+ *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill (default)
+ *   LRT_OPT_RAY_GRID_WIDTH  W > 0: the R rays of the next calls are a row-major (R / W, W) range image
+ *                           (the (H, W, 3) tensors of the reference API); lets a warp take a 4 x 8 tile of
+ *                           neighbouring rays. 0 = no structure known (default).
+ *   LRT_OPT_VECTOR_ATOMICS  backward: 128-bit vector reductions where alignment allows (default 1) */
+enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3 };
+int lrt_set_option(lrt_ctx* ctx, int option, int value);
+
 /* Introspection for tests / benchmarks (host pointers). */
 typedef struct lrt_info {
     int32_t P;                    /* Gaussians in the built structure */

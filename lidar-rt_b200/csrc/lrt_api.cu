@@ -32,7 +32,7 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
 {
     if (!ctx) return LRT_OK;
     cudaSetDevice(ctx->device);
-    DevBuf* bufs[] = {&ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds};
+    DevBuf* bufs[] = {&ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds, &ctx->counter};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     delete ctx;
     return LRT_OK;
@@ -77,6 +77,19 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
     return lrt_backward_impl(ctx, R, ray_o, ray_o_stride, ray_d, bg, P, means, scales, rots, opac, shs, D, M,
                              scale_modifier, fwd_out, dL_dout, hit_gidx, hit_t, hit_cnt, cap,
                              dL_dmeans, dL_dshs, dL_dopac, dL_dscales, dL_drots, flags, (cudaStream_t)stream);
+}
+
+int lrt_set_option(lrt_ctx* ctx, int option, int value)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    switch (option) {
+    case LRT_OPT_FORWARD_KERNEL: if (value != 0 && value != 1) break; ctx->opt_forward_kernel = value; return LRT_OK;
+    case LRT_OPT_RAY_GRID_WIDTH: if (value < 0) break; ctx->opt_ray_grid_w = value; return LRT_OK;
+    case LRT_OPT_VECTOR_ATOMICS: if (value != 0 && value != 1) break; ctx->opt_vector_atomics = value; return LRT_OK;
+    default: break;
+    }
+    ctx->set_error("lrt_set_option: unknown option or value out of range");
+    return LRT_ERR_INVALID;
 }
 
 int lrt_get_info(const lrt_ctx* ctx, lrt_info* out)

@@ -23,7 +23,18 @@ struct RayState {
 
 struct GradOut {
     float* d_means; float* d_shs; float* d_opac; float* d_scales; float* d_rots;
+    int vec;                              // 128-bit / 64-bit vector reductions usable (alignment checked on the host)
 };
+
+// sm_90+ vector float reductions: one L2 operation for 4 (2) adjacent floats instead of 4 (2).
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b)
+{
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 
 __device__ __forceinline__ void cross3(const float* a, const float* b, float* o)
 {
@@ -177,21 +188,42 @@ __device__ __forceinline__ int hit_backward(int g, float dpt, const float* o, co
         const float dq2 = 2.0f * (qx * (GM(1, 0) + GM(0, 1)) - 2.0f * qy * (GM(0, 0) + GM(2, 2)) + qz * (GM(2, 1) + GM(1, 2)) + qw * (GM(0, 2) - GM(2, 0)));
         const float dq3 = 2.0f * (qx * (GM(2, 0) + GM(0, 2)) + qy * (GM(2, 1) + GM(1, 2)) - 2.0f * qz * (GM(0, 0) + GM(1, 1)) + qw * (GM(1, 0) - GM(0, 1)));
 #undef GM
-        atomicAdd(go.d_scales + 2 * (size_t)g, dsc[0]); atomicAdd(go.d_scales + 2 * (size_t)g + 1, dsc[1]);      // :659-669
-        atomicAdd(go.d_rots + 4 * (size_t)g, dq0); atomicAdd(go.d_rots + 4 * (size_t)g + 1, dq1);
-        atomicAdd(go.d_rots + 4 * (size_t)g + 2, dq2); atomicAdd(go.d_rots + 4 * (size_t)g + 3, dq3);
+        if (go.vec) {                                                                                             // :659-669
+            red_add_v2(go.d_scales + 2 * (size_t)g, dsc[0], dsc[1]);
+            red_add_v4(go.d_rots + 4 * (size_t)g, dq0, dq1, dq2, dq3);
+        } else {
+            atomicAdd(go.d_scales + 2 * (size_t)g, dsc[0]); atomicAdd(go.d_scales + 2 * (size_t)g + 1, dsc[1]);
+            atomicAdd(go.d_rots + 4 * (size_t)g, dq0); atomicAdd(go.d_rots + 4 * (size_t)g + 1, dq1);
+            atomicAdd(go.d_rots + 4 * (size_t)g + 2, dq2); atomicAdd(go.d_rots + 4 * (size_t)g + 3, dq3);
+        }
         atomicAdd(go.d_means + 3 * (size_t)g, dmu[0]); atomicAdd(go.d_means + 3 * (size_t)g + 1, dmu[1]);
         atomicAdd(go.d_means + 3 * (size_t)g + 2, dmu[2]);
     }
     // computeColorFromSHBackward (:123-247): dL_dsh[j] = basis_j * dL_dcolour, channel 0 zero if clamped
     if (clamped0) dcol[0] = 0.0f;
     float* dsh = go.d_shs + (size_t)g * M * 3;
+    if (go.vec && (M & 3) == 0) {
+        // (j, ch) pairs are contiguous: 3 nb floats = groups of 4 (nb = 1 -> 3 floats: scalar tail)
+        float vals[48];
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        if (j < nb) {
-            atomicAdd(dsh + 3 * j, basis[j] * dcol[0]);
-            atomicAdd(dsh + 3 * j + 1, basis[j] * dcol[1]);
-            atomicAdd(dsh + 3 * j + 2, basis[j] * dcol[2]);
+        for (int j = 0; j < 16; j++) { vals[3 * j] = basis[j] * dcol[0]; vals[3 * j + 1] = basis[j] * dcol[1]; vals[3 * j + 2] = basis[j] * dcol[2]; }
+        const int nf = 3 * nb;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            if (4 * i + 3 < nf) red_add_v4(dsh + 4 * i, vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+            else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) if (4 * i + e < nf) atomicAdd(dsh + 4 * i + e, vals[4 * i + e]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (j < nb) {
+                atomicAdd(dsh + 3 * j, basis[j] * dcol[0]);
+                atomicAdd(dsh + 3 * j + 1, basis[j] * dcol[1]);
+                atomicAdd(dsh + 3 * j + 2, basis[j] * dcol[2]);
+            }
         }
     }
     st.T = testT;
@@ -310,6 +342,8 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
     a.D = D; a.M = M; a.mod = mod; a.fwd_out = fwd_out; a.dL = dL_dout; a.flags = flags;
     a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_cnt = hit_cnt; a.cap = cap;
     a.go.d_means = dL_dmeans; a.go.d_shs = dL_dshs; a.go.d_opac = dL_dopac; a.go.d_scales = dL_dscales; a.go.d_rots = dL_drots;
+    a.go.vec = ctx->opt_vector_atomics && (reinterpret_cast<uintptr_t>(dL_dshs) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(dL_drots) & 15) == 0 && (reinterpret_cast<uintptr_t>(dL_dscales) & 7) == 0;
     const int TB = 128, GB = (R + TB - 1) / TB;
     const bool can_trace = ctx->built && ctx->P == P && ctx->scale_modifier == mod;
     if (have_lists) {

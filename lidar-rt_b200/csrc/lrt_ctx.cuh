@@ -23,7 +23,12 @@ struct lrt_ctx {
     long long n_nodes = 0;
     bool built = false;
     float scale_modifier = 1.0f;
-    DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, iperm, sort_tmp, bounds;
+    DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, iperm, sort_tmp, bounds, counter;
+    // options (lrt_set_option)
+    int opt_forward_kernel = 1;   // 0: one thread per ray, 1: persistent threads with per-lane refill
+    int opt_ray_grid_w = 0;       // > 0: rays are a row-major range image of this width (enables 4 x 8 warp tiles)
+    int opt_vector_atomics = 1;   // backward: red.global.add.v4.f32 where alignment allows
+    int fwd_blocks_per_sm = 0, num_sms = 0;
     long long builds = 0, refits = 0;
     int launches = 0;
 
@@ -46,7 +51,7 @@ struct lrt_ctx {
     }
     size_t total_bytes() const
     {
-        return rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + iperm.cap + sort_tmp.cap + bounds.cap;
+        return rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + iperm.cap + sort_tmp.cap + bounds.cap + counter.cap;
     }
     BvhView view() const
     {

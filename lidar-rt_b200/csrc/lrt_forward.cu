@@ -30,28 +30,126 @@ __device__ __forceinline__ void load_sh(const float* __restrict__ shs, int g, in
     }
 }
 
-__global__ void __launch_bounds__(128)
-k_forward(BvhView bvh, int R, const float* __restrict__ ray_o, int ray_o_stride, const float* __restrict__ ray_d,
-          const float* __restrict__ bg, const float* __restrict__ shs, int D, int M,
-          float* __restrict__ out, float* __restrict__ accum_w, int32_t* __restrict__ hit_gidx,
-          float* __restrict__ hit_t, int32_t* __restrict__ hit_cnt, int cap, int32_t* __restrict__ slot_cnt)
-{
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const float o[3] = {ray_o[(size_t)r * ray_o_stride], ray_o[(size_t)r * ray_o_stride + 1], ray_o[(size_t)r * ray_o_stride + 2]};
-    const float d[3] = {ray_d[3 * (size_t)r], ray_d[3 * (size_t)r + 1], ray_d[3 * (size_t)r + 2]};
-    const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    const float dirn[3] = {d[0] / dl, d[1] / dl, d[2] / dl};
-    const int nb = (D + 1) * (D + 1);
+struct FwdArgs {
+    int R; const float* ray_o; int ray_o_stride; const float* ray_d; const float* bg; const float* shs; int D, M;
+    float* out; float* accum_w; int32_t* hit_gidx; float* hit_t; int32_t* hit_cnt; int cap; int32_t* slot_cnt;
+    int grid_w;                  // > 0: rays form a row-major (R / grid_w, grid_w) range image -> 4 x 8 warp tiles
+    int* work_counter;           // persistent kernel: next work slot
+};
 
-    float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f, W = 0.f, T = 1.f, testT = 1.f, base = 0.f, dpt = 0.f;
-    int ncontrib = 0, nslots = 0, last = -1;
+// Per-ray compositing state (forward.cu:174-193).
+struct FwdRay {
+    float o[3], d[3], dirn[3];
+    float C0, C1, C2, Dp, W, T, testT, base, dpt;
+    int ncontrib, nslots, last, r;
+};
+
+__device__ __forceinline__ void fwd_ray_init(FwdRay& q, int r, const FwdArgs& a)
+{
+    q.r = r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { q.o[k] = a.ray_o[(size_t)r * a.ray_o_stride + k]; q.d[k] = a.ray_d[3 * (size_t)r + k]; }
+    const float dl = sqrtf(q.d[0] * q.d[0] + q.d[1] * q.d[1] + q.d[2] * q.d[2]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) q.dirn[k] = q.d[k] / dl;
+    q.C0 = q.C1 = q.C2 = q.Dp = q.W = 0.f; q.T = 1.f; q.testT = 1.f; q.base = 0.f; q.dpt = 0.f;
+    q.ncontrib = 0; q.nslots = 0; q.last = -1;
+}
+
+// Composite one round's sorted hits (forward.cu:201-292). Returns true if the ray needs another round.
+__device__ __forceinline__ bool fwd_shade_round(FwdRay& q, const unsigned long long* hits, int n, const BvhView& bvh, const FwdArgs& a)
+{
+    const int nb = (a.D + 1) * (a.D + 1);
+    bool terminated = false;
+    for (int i = 0; i < n; i++) {
+        const unsigned long long key = hits[i];
+        const int g = (int)(unsigned)(key & 0xffffffffull);
+        q.nslots++;
+        q.dpt = __uint_as_float((unsigned)(key >> 32)) + q.base;                  // forward.cu:212
+        if (q.dpt < LRT_MIN_T) continue;                                          // :214
+        const float x0 = q.o[0] + q.dpt * q.d[0], x1 = q.o[1] + q.dpt * q.d[1], x2 = q.o[2] + q.dpt * q.d[2];
+        // :220-224 — a re-based round can find the previous round's last surfel again at t' ~ +0
+        // (the 1e-5 step is below one ulp of the depth beyond 128 m): it must not composite twice
+        if (g == q.last) continue;
+        q.last = g;
+        const int prim = __ldg(bvh.iperm + g);
+        const float4 a0 = ld_f4(&bvh.rec[prim].r0), a1 = ld_f4(&bvh.rec[prim].r1);
+        const float4 a2 = ld_f4(&bvh.rec[prim].r2), a3 = ld_f4(&bvh.rec[prim].r3);
+        const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
+        const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;                        // :139
+        const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+        const float cosv = -((a0.x - q.o[0]) * a3.x + (a0.y - q.o[1]) * a3.y + (a0.z - q.o[2]) * a3.z);
+        if (cosv == 0.0f) continue;                                               // :233-237
+        const float rho = u * u + v * v;
+        const float power = -0.5f * rho;
+        if (power > 0.0f) continue;
+        const float G = expf(power);
+        const float alpha = fminf(LRT_ALPHA_MAX, a1.w * G);                       // :249
+        if (alpha < 1.0f / 255.0f) continue;
+        q.testT = q.T * (1.0f - alpha);
+        if (q.testT < LRT_T_MIN) { terminated = true; break; }                    // :253-257
+        const float w = alpha * q.T;
+        float sh[48], c[3]; bool cl;
+        load_sh(a.shs, g, a.M, nb, sh);
+        sh_colour<false>(a.D, q.dirn, sh, c, cl, nullptr);
+        q.C0 += w * c[0]; q.C1 += w * c[1]; q.C2 += w * c[2];
+        q.Dp += w * q.dpt; q.W += w;
+        atomicAdd(a.accum_w + g, w);                                              // :272
+        if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
+            a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g;
+            a.hit_t[(size_t)q.ncontrib * a.R + q.r] = q.dpt;
+        }
+        q.ncontrib++;
+        q.T = q.testT;
+    }
+    if (terminated || q.testT < LRT_T_MIN || n < LRT_KBUF) return false;          // :282-285
+    q.base = (float)((double)q.dpt + LRT_STEP_EPS);                               // :288
+    return true;
+}
+
+__device__ __forceinline__ void fwd_write(const FwdRay& q, const FwdArgs& a, int node_visits)
+{
+    float* op = a.out + (size_t)LRT_NCH * q.r;
+    op[0] = q.C0 + q.T * a.bg[0]; op[1] = q.C1 + q.T * a.bg[1]; op[2] = q.C2 + q.T * a.bg[2];      // :296-305
+    op[3] = q.Dp; op[4] = q.W; op[5] = 0.f; op[6] = 0.f; op[7] = 0.f; op[8] = q.T;
+    if (a.hit_cnt) a.hit_cnt[q.r] = q.ncontrib;
 #ifdef LRT_STATS
-    int node_visits = 0;
+    if (a.slot_cnt) a.slot_cnt[q.r] = (q.nslots & 0xffff) | (min(node_visits, 32767) << 16);   // development statistics build
+#else
+    (void)node_visits;
+    if (a.slot_cnt) a.slot_cnt[q.r] = q.nslots;
 #endif
+}
+
+// Work slot -> ray index. With a known range-image width, consecutive slots walk 4 x 8 tiles so that
+// the 32 rays of a warp are spatial neighbours (shared nodes, similar traversal length); -1 = padding.
+__device__ __forceinline__ int slot_to_ray(int s, int R, int grid_w)
+{
+    if (grid_w <= 0) return s < R ? s : -1;
+    const int H = R / grid_w, tiles_x = (grid_w + 7) >> 3;
+    const int tile = s >> 5, l = s & 31;
+    const int h = (tile / tiles_x) * 4 + (l >> 3), w = (tile % tiles_x) * 8 + (l & 7);
+    return (h < H && w < grid_w) ? h * grid_w + w : -1;
+}
+
+__host__ __device__ __forceinline__ int num_slots(int R, int grid_w)
+{
+    if (grid_w <= 0) return R;
+    const int H = R / grid_w;
+    return ((H + 3) >> 2) * ((grid_w + 7) >> 3) * 32;
+}
+
+// ---- kernel A: one thread per ray, whole ray in one go (simple; kept as the comparison baseline)
+__global__ void __launch_bounds__(128) k_forward(BvhView bvh, FwdArgs a)
+{
+    const int r = slot_to_ray(blockIdx.x * blockDim.x + threadIdx.x, a.R, a.grid_w);
+    if (r < 0) return;
+    FwdRay q;
+    fwd_ray_init(q, r, a);
+    int node_visits = 0;
     for (;;) {
         RaySetup rs;
-        ray_setup(rs, o, d, base);
+        ray_setup(rs, q.o, q.d, q.base);
         unsigned long long kb[LRT_KBUF];
 #ifdef LRT_STATS
         const int n = trace_round(bvh, rs, kb, node_visits);
@@ -61,60 +159,82 @@ k_forward(BvhView bvh, int R, const float* __restrict__ ray_o, int ray_o_stride,
         unsigned long long hits[LRT_KBUF];
 #pragma unroll
         for (int i = 0; i < LRT_KBUF; i++) hits[i] = kb[i];
-        bool terminated = false;
-        for (int i = 0; i < n; i++) {
-            const unsigned long long key = hits[i];
-            const int g = (int)(unsigned)(key & 0xffffffffull);
-            nslots++;
-            dpt = __uint_as_float((unsigned)(key >> 32)) + base;                      // forward.cu:212
-            if (dpt < LRT_MIN_T) continue;                                            // :214
-            const float x0 = o[0] + dpt * d[0], x1 = o[1] + dpt * d[1], x2 = o[2] + dpt * d[2];
-            // :220-224 — a re-based round can find the previous round's last surfel again at t' ~ +0
-            // (the 1e-5 step is below one ulp of the depth beyond 128 m): it must not composite twice
-            if (g == last) continue;
-            last = g;
-            const int prim = __ldg(bvh.iperm + g);
-            const float4 a0 = ld_f4(&bvh.rec[prim].r0), a1 = ld_f4(&bvh.rec[prim].r1);
-            const float4 a2 = ld_f4(&bvh.rec[prim].r2), a3 = ld_f4(&bvh.rec[prim].r3);
-            const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
-            const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;                        // :139
-            const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
-            const float cosv = -((a0.x - o[0]) * a3.x + (a0.y - o[1]) * a3.y + (a0.z - o[2]) * a3.z);
-            if (cosv == 0.0f) continue;                                               // :233-237
-            const float rho = u * u + v * v;
-            const float power = -0.5f * rho;
-            if (power > 0.0f) continue;
-            const float G = expf(power);
-            const float alpha = fminf(LRT_ALPHA_MAX, a1.w * G);                       // :249
-            if (alpha < 1.0f / 255.0f) continue;
-            testT = T * (1.0f - alpha);
-            if (testT < LRT_T_MIN) { terminated = true; break; }                      // :253-257
-            const float w = alpha * T;
-            float sh[48], c[3]; bool cl;
-            load_sh(shs, g, M, nb, sh);
-            sh_colour<false>(D, dirn, sh, c, cl, nullptr);
-            C0 += w * c[0]; C1 += w * c[1]; C2 += w * c[2];
-            Dp += w * dpt; W += w;
-            atomicAdd(accum_w + g, w);                                                // :272
-            if (hit_gidx != nullptr && ncontrib < cap) {
-                hit_gidx[(size_t)ncontrib * R + r] = g;
-                hit_t[(size_t)ncontrib * R + r] = dpt;
-            }
-            ncontrib++;
-            T = testT;
-        }
-        if (terminated || testT < LRT_T_MIN || n < LRT_KBUF) break;                   // :282-285
-        base = (float)((double)dpt + LRT_STEP_EPS);                                   // :288
+        if (!fwd_shade_round(q, hits, n, bvh, a)) break;
     }
-    float* op = out + (size_t)LRT_NCH * r;
-    op[0] = C0 + T * bg[0]; op[1] = C1 + T * bg[1]; op[2] = C2 + T * bg[2];          // :296-305
-    op[3] = Dp; op[4] = W; op[5] = 0.f; op[6] = 0.f; op[7] = 0.f; op[8] = T;
-    if (hit_cnt) hit_cnt[r] = ncontrib;
-#ifdef LRT_STATS
-    if (slot_cnt) slot_cnt[r] = (nslots & 0xffff) | (min(node_visits, 32767) << 16);   // development statistics build
-#else
-    if (slot_cnt) slot_cnt[r] = nslots;
-#endif
+    fwd_write(q, a, node_visits);
+}
+
+// ---- kernel B: persistent threads. Rays differ 20x in traversal length (sky vs. long grazing rays), so
+// with one ray per thread a warp idles at ~30 % lane utilisation waiting for its longest ray. Here every
+// lane runs a small state machine and pulls a new ray the moment its own finishes:
+//   FETCH -> (TRAV: one node evaluation per loop trip)* -> SHADE (16 sorted hits) -> TRAV | FETCH
+// All lanes in TRAV execute the same node-evaluation code each trip; shading is batched (it runs when
+// >= LRT_SHADE_BATCH lanes wait for it or nobody can traverse) so that its divergent code is amortised.
+#define LRT_ST_FETCH 0
+#define LRT_ST_TRAV 1
+#define LRT_ST_SHADE 2
+#define LRT_ST_DONE 3
+#define LRT_SHADE_BATCH 8
+
+__global__ void __launch_bounds__(128) k_forward_persistent(BvhView bvh, FwdArgs a)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int S = num_slots(a.R, a.grid_w);
+    int st = LRT_ST_FETCH;
+    FwdRay q;
+    RaySetup rs;
+    Trav tv;
+    unsigned long long kb[LRT_KBUF];
+    int node_visits = 0;
+    q.r = -1;
+    for (;;) {
+        // 1. refill idle lanes (one atomic per warp)
+        const unsigned need = __ballot_sync(FULL, st == LRT_ST_FETCH);
+        if (need) {
+            int base_slot = 0;
+            const int leader = __ffs(need) - 1;
+            if (lane == leader) base_slot = atomicAdd(a.work_counter, __popc(need));
+            base_slot = __shfl_sync(FULL, base_slot, leader);
+            if (st == LRT_ST_FETCH) {
+                const int s = base_slot + __popc(need & ((1u << lane) - 1u));
+                if (s >= S) st = LRT_ST_DONE;
+                else {
+                    const int r = slot_to_ray(s, a.R, a.grid_w);
+                    if (r >= 0) {
+                        fwd_ray_init(q, r, a);
+                        ray_setup(rs, q.o, q.d, q.base);
+                        trav_init(bvh, tv, kb);
+                        node_visits = 0;
+                        st = LRT_ST_TRAV;
+                    }                                   // padding slot: fetch again next trip
+                }
+            }
+        }
+        if (__all_sync(FULL, st == LRT_ST_DONE)) break;
+        // 2. one node evaluation for every traversing lane
+        if (st == LRT_ST_TRAV) {
+            node_visits++;
+            if (trav_step(bvh, rs, kb, tv)) st = LRT_ST_SHADE;
+        }
+        // 3. batched shading
+        const unsigned ws = __ballot_sync(FULL, st == LRT_ST_SHADE);
+        const unsigned wt = __ballot_sync(FULL, st == LRT_ST_TRAV);
+        if (st == LRT_ST_SHADE && (__popc(ws) >= LRT_SHADE_BATCH || wt == 0)) {
+            unsigned long long hits[LRT_KBUF];
+#pragma unroll
+            for (int i = 0; i < LRT_KBUF; i++) hits[i] = kb[i];
+            const int n = kbuf_count(kb);
+            if (fwd_shade_round(q, hits, n, bvh, a)) {
+                ray_setup(rs, q.o, q.d, q.base);
+                trav_init(bvh, tv, kb);
+                st = LRT_ST_TRAV;
+            } else {
+                fwd_write(q, a, node_visits);
+                st = LRT_ST_FETCH;
+            }
+        }
+    }
 }
 
 } // namespace
@@ -138,9 +258,28 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
     LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     LRT_CUDA_TRY(ctx, cudaMemsetAsync(accum_w, 0, sizeof(float) * (size_t)P, s));
     if (R == 0) return LRT_OK;
+    FwdArgs a;
+    a.R = R; a.ray_o = ray_o; a.ray_o_stride = ray_o_stride; a.ray_d = ray_d; a.bg = bg; a.shs = shs; a.D = D; a.M = M;
+    a.out = out; a.accum_w = accum_w; a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_cnt = hit_cnt; a.cap = cap; a.slot_cnt = slot_cnt;
+    a.grid_w = (ctx->opt_ray_grid_w > 0 && R % ctx->opt_ray_grid_w == 0) ? ctx->opt_ray_grid_w : 0;
+    a.work_counter = nullptr;
     const int TB = 128;
-    k_forward<<<(R + TB - 1) / TB, TB, 0, s>>>(ctx->view(), R, ray_o, ray_o_stride, ray_d, bg, shs, D, M, out, accum_w,
-                                               hit_gidx, hit_t, hit_cnt, cap, slot_cnt);
+    const int S = num_slots(R, a.grid_w);
+    if (ctx->opt_forward_kernel == 0) {
+        k_forward<<<(S + TB - 1) / TB, TB, 0, s>>>(ctx->view(), a);
+    } else {
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 4));
+        LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 4, s));
+        a.work_counter = (int*)ctx->counter.p;
+        if (ctx->fwd_blocks_per_sm == 0) {
+            int nb = 0, sms = 0;
+            LRT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_forward_persistent, TB, 0));
+            LRT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+            ctx->fwd_blocks_per_sm = nb > 0 ? nb : 1; ctx->num_sms = sms > 0 ? sms : 148;
+        }
+        const int grid = min(ctx->num_sms * ctx->fwd_blocks_per_sm, (S + TB - 1) / TB);   // one resident wave, sized to the SM count
+        k_forward_persistent<<<grid, TB, 0, s>>>(ctx->view(), a);
+    }
     ctx->launches += 1;
     LRT_CUDA_TRY(ctx, cudaGetLastError());
     return LRT_OK;

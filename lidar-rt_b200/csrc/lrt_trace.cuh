@@ -5,11 +5,14 @@
 // Differences in HOW (results are identical):
 //   * the reference's any-hit program must see every triangle on the whole ray in every round
 //     (optixIgnoreIntersection never shortens the ray); here subtrees whose entry distance exceeds
-//     the current 16th-nearest hit are culled;
+//     the current 16th-nearest hit are culled, and children are entered nearest-first so that the
+//     bound tightens early;
 //   * the proxy is one analytic quad |u|,|v| <= f per Gaussian instead of two triangles;
 //   * traversal is stackless: the hierarchy is implicit (children of node j at level l are nodes
 //     8j..8j+7 at level l-1), so the only state is (level, node) plus one pending-children byte per
-//     level packed into a 64-bit trail.
+//     level packed into a 64-bit trail. A node with >= 2 pending children is re-evaluated when the
+//     traversal climbs back to it (its 192 B are L1-resident), which both restores front-to-back
+//     order and drops children that fell behind the shrunken bound.
 #pragma once
 
 #include "lrt_common.cuh"
@@ -21,6 +24,13 @@ struct RaySetup {
     float dx, dy, dz;
     float ix, iy, iz;     // 1 / d (clamped away from 0) for the slab tests
     float px, py, pz;     // o' * (1/d)
+};
+
+struct Trav {
+    int level;
+    unsigned node;
+    unsigned pend;                 // children of (level, node) still to consider
+    unsigned long long trail;      // pending-children byte of every ancestor
 };
 
 __device__ __forceinline__ float safe_inv(float d)
@@ -69,11 +79,15 @@ __device__ __forceinline__ void kbuf_insert(unsigned long long (&kb)[LRT_KBUF], 
     }
 }
 
-// 8 slab tests of one node against [0, tmax]; returns the mask of children to visit.
-__device__ __forceinline__ unsigned node_mask(const Node8* __restrict__ node, const RaySetup& r, float tmax)
+// 8 slab tests of one node against [0, tmax]: mask of the children in `pend` the ray enters, and the
+// one it enters first.
+__device__ __forceinline__ unsigned node_eval(const Node8* __restrict__ node, const RaySetup& r, float tmax,
+                                              unsigned pend, int& nearest)
 {
     const float4* p = reinterpret_cast<const float4*>(node);
     unsigned m = 0;
+    float best = 3.0e38f;
+    nearest = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const float4 lx = ld_f4(p + h), ly = ld_f4(p + 2 + h), lz = ld_f4(p + 4 + h);
@@ -87,55 +101,81 @@ __device__ __forceinline__ unsigned node_mask(const Node8* __restrict__ node, co
             const float z0 = fmaf(lzs[c], r.iz, -r.pz), z1 = fmaf(hzs[c], r.iz, -r.pz);
             const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
             const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
-            if (tn <= tf) m |= 1u << (4 * h + c);
+            const bool hit = (tn <= tf) && ((pend >> (4 * h + c)) & 1u);
+            if (hit) {
+                m |= 1u << (4 * h + c);
+                if (tn < best) { best = tn; nearest = 4 * h + c; }
+            }
         }
     }
     return m;
 }
 
-// One round. On return `kb` holds the nearest hits ascending; returns how many are valid (<= 16).
-// 16 valid entries <=> the reference's `payload.cnt >= CHUNK_SIZE` (forward.cu:282).
+__device__ __forceinline__ void trav_init(const BvhView& bvh, Trav& tv, unsigned long long (&kb)[LRT_KBUF])
+{
+#pragma unroll
+    for (int i = 0; i < LRT_KBUF; i++) kb[i] = LRT_KEY_EMPTY;
+    tv.level = bvh.levels - 1; tv.node = 0; tv.pend = 0xffu; tv.trail = 0;
+}
+
+// One node evaluation. Returns true when the round's traversal is complete.
+__device__ __forceinline__ bool trav_step(const BvhView& bvh, const RaySetup& r, unsigned long long (&kb)[LRT_KBUF], Trav& tv)
+{
+    const float tmax = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32));
+    int nearest;
+    unsigned m = node_eval(bvh.nodes + bvh.level_off[tv.level] + tv.node, r, tmax, tv.pend, nearest);
+    if (tv.level == 0) {
+        while (m) {
+            const int c = __ffs(m) - 1; m &= m - 1;
+            float t; int g;
+            if (quad_hit(bvh.rec, (int)(tv.node * 8u + c), r, t, g))      // ties in t' resolve by the caller's Gaussian index
+                kbuf_insert(kb, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g);
+        }
+    }
+    if (m) {                                            // enter the nearest child, remember the others
+        m &= ~(1u << nearest);
+        tv.trail = (tv.trail & ~(0xffull << (8 * tv.level))) | ((unsigned long long)m << (8 * tv.level));
+        tv.node = tv.node * 8u + nearest; tv.level--; tv.pend = 0xffu;
+        return false;
+    }
+    for (;;) {                                          // climb to the nearest ancestor with pending children
+        tv.level++; tv.node >>= 3;
+        if (tv.level >= bvh.levels) return true;
+        const unsigned p = (unsigned)(tv.trail >> (8 * tv.level)) & 0xffu;
+        if (p == 0) continue;
+        if ((p & (p - 1)) == 0) {                       // a single child left: no ordering decision, enter it directly
+            tv.trail &= ~(0xffull << (8 * tv.level));
+            tv.node = tv.node * 8u + (__ffs(p) - 1); tv.level--; tv.pend = 0xffu;
+        } else {
+            tv.pend = p;                                // re-evaluated by the next step: order + culling refresh
+        }
+        return false;
+    }
+}
+
+__device__ __forceinline__ int kbuf_count(const unsigned long long (&kb)[LRT_KBUF])
+{
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < LRT_KBUF; i++) n += kb[i] != LRT_KEY_EMPTY;
+    return n;
+}
+
+// One full round (monolithic kernels). On return `kb` holds the nearest hits ascending; returns how
+// many are valid. 16 valid entries <=> the reference's `payload.cnt >= CHUNK_SIZE` (forward.cu:282).
 __device__ __forceinline__ int trace_round(const BvhView& bvh, const RaySetup& r, unsigned long long (&kb)[LRT_KBUF]
 #ifdef LRT_STATS
                                            , int& node_visits
 #endif
                                            )
 {
-#pragma unroll
-    for (int i = 0; i < LRT_KBUF; i++) kb[i] = LRT_KEY_EMPTY;
-    const int L = bvh.levels;
-    int level = L - 1;
-    unsigned node = 0;
-    unsigned long long trail = 0;
+    Trav tv;
+    trav_init(bvh, tv, kb);
     for (;;) {
-        const float tmax = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32));
-        unsigned m = node_mask(bvh.nodes + bvh.level_off[level] + node, r, tmax);
 #ifdef LRT_STATS
         node_visits++;
 #endif
-        if (level == 0) {
-            while (m) {
-                const int c = __ffs(m) - 1; m &= m - 1;
-                const int prim = (int)(node * 8u + c);
-                float t; int g;
-                if (quad_hit(bvh.rec, prim, r, t, g))     // ties in t' resolve by the caller's Gaussian index
-                    kbuf_insert(kb, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g);
-            }
-        }
-        if (m == 0) {                                   // nothing (left) below this node: climb
-            do {
-                level++; node >>= 3;
-                if (level >= L) goto done;
-                m = (unsigned)(trail >> (8 * level)) & 0xffu;
-            } while (m == 0);
-        }
-        const int c = __ffs(m) - 1; m &= m - 1;          // next pending child
-        trail = (trail & ~(0xffull << (8 * level))) | ((unsigned long long)m << (8 * level));
-        node = node * 8u + c; level--;
+        if (trav_step(bvh, r, kb, tv)) break;
     }
-done:
-    int n = 0;
-#pragma unroll
-    for (int i = 0; i < LRT_KBUF; i++) n += kb[i] != LRT_KEY_EMPTY;
-    return n;
+    return kbuf_count(kb);
 }

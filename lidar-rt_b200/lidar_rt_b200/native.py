@@ -19,7 +19,8 @@ LIB_PATH = os.environ.get("LIDAR_RT_B200_LIB") or os.path.join(os.path.dirname(_
 
 LRT_FLAG_FIX_BG_GRAD = 1
 NUM_CHANNELS = 9
-DEFAULT_HIT_CAP = 64
+DEFAULT_HIT_CAP = 128          # contributing hits recorded per ray for the backward replay (rays beyond it are re-traced)
+OPT_FORWARD_KERNEL, OPT_RAY_GRID_WIDTH, OPT_VECTOR_ATOMICS = 1, 2, 3
 
 
 class LrtError(RuntimeError):
@@ -56,9 +57,10 @@ def load_library() -> ctypes.CDLL:
                                 fp, fp, ip, fp, ip, c_int, ip, c_void_p]
     lib.lrt_backward.argtypes = [c_void_p, c_int, fp, c_int, fp, fp, c_int, fp, fp, fp, fp, fp, c_int, c_int, c_float,
                                  fp, fp, ip, fp, ip, c_int, fp, fp, fp, fp, fp, c_int, c_void_p]
+    lib.lrt_set_option.argtypes = [c_void_p, c_int, c_int]
     lib.lrt_get_info.argtypes = [c_void_p, POINTER(LrtInfo)]
     lib.lrt_get_permutation.argtypes = [c_void_p, c_void_p, c_void_p]
-    for f in (lib.lrt_ctx_create, lib.lrt_ctx_destroy, lib.lrt_build, lib.lrt_refit, lib.lrt_forward, lib.lrt_backward,
+    for f in (lib.lrt_set_option, lib.lrt_ctx_create, lib.lrt_ctx_destroy, lib.lrt_build, lib.lrt_refit, lib.lrt_forward, lib.lrt_backward,
               lib.lrt_get_info, lib.lrt_get_permutation):
         f.restype = c_int
     _lib = lib
@@ -134,6 +136,9 @@ class Context:
         self.generation += 1
         return self.generation
 
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.lrt_set_option(self._h, int(option), int(value)))
+
     def info(self) -> LrtInfo:
         i = LrtInfo()
         self._check(self.lib.lrt_get_info(self._h, byref(i)))
@@ -172,6 +177,7 @@ class Context:
         M = shs.shape[1]
         bg = _f32(bg, "bg").reshape(-1)
         dev = self.device
+        self.set_option(OPT_RAY_GRID_WIDTH, lead[-1] if len(lead) >= 2 else 0)     # (H, W, 3) range image -> 4 x 8 warp tiles
         with torch.cuda.device(dev):
             out = torch.empty(lead + (NUM_CHANNELS,), dtype=torch.float32, device=dev)
             accum = torch.empty(P, dtype=torch.float32, device=dev)
@@ -198,6 +204,7 @@ class Context:
         if fwd_out.numel() != R * NUM_CHANNELS or dL.numel() != R * NUM_CHANNELS:
             raise LrtError("out / dL_dout must be (..., 9) matching the rays")
         dev = self.device
+        self.set_option(OPT_RAY_GRID_WIDTH, lead[-1] if len(lead) >= 2 else 0)
         with torch.cuda.device(dev):
             g_means = torch.empty((P, 3), dtype=torch.float32, device=dev)
             g_shs = torch.empty((P, M, 3), dtype=torch.float32, device=dev)

@@ -1,5 +1,6 @@
-"""One or two frames of the hot path (build + forward + backward) for ncu captures and traversal statistics.
-   python scripts/profile_frame.py [--gaussians 2000000] [--frames 2] [--stats]"""
+"""Frames of the hot path (build + forward + backward) for ncu captures, A/B of tuning options and
+traversal statistics (development aid).
+   python scripts/profile_frame.py [--gaussians 2000000] [--frames 3] [--ab] [--stats]"""
 import argparse, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "lidar-rt_b200"))
@@ -8,9 +9,13 @@ from lidar_rt_b200 import native, synthetic as syn
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--gaussians", type=int, default=2_000_000)
-ap.add_argument("--frames", type=int, default=2)
+ap.add_argument("--frames", type=int, default=3)
 ap.add_argument("--stats", action="store_true")
-ap.add_argument("--no-backward", action="store_true")
+ap.add_argument("--ab", action="store_true", help="time every combination of the tuning options")
+ap.add_argument("--fwd-kernel", type=int, default=1)
+ap.add_argument("--flat", action="store_true", help="pass rays as (R,3): no 4x8 tiles")
+ap.add_argument("--no-vec", action="store_true")
+ap.add_argument("--cap", type=int, default=native.DEFAULT_HIT_CAP)
 a = ap.parse_args()
 BG = np.array([0, 0, 1], np.float32)
 cu = lambda x: torch.as_tensor(np.ascontiguousarray(x), device="cuda")
@@ -19,23 +24,49 @@ means, scales, rots, opac, shs = map(cu, (sc.means, sc.scales, sc.rots, sc.opac,
 ctx = native.Context()
 inc = syn.waymo_inclinations()
 rng = np.random.default_rng(0)
+frames = []
 for f in range(a.frames):
     o, d = syn.lidar_rays(64, 2650, inc, syn.sensor_pose(f))
     dL = np.zeros((64, 2650, 9), np.float32); dL[..., :4] = rng.standard_normal((64, 2650, 4))
-    ro, rd, g = cu(o), cu(d), cu(dL)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    ctx.build(means, scales, rots, opac)
-    torch.cuda.synchronize(); t1 = time.perf_counter()
-    res = ctx.forward(ro, rd, cu(BG), means, scales, rots, opac, shs, 3, want_slots=True)
-    torch.cuda.synchronize(); t2 = time.perf_counter()
-    if not a.no_backward:
-        ctx.backward(ro, rd, cu(BG), means, scales, rots, opac, shs, 3, res["out"], g, hits=res)
-    torch.cuda.synchronize(); t3 = time.perf_counter()
+    frames.append((cu(o), cu(d), cu(dL)))
+bg = cu(BG)
+
+
+def run(fwd_kernel, flat, vec, cap, label, verbose=True):
+    ctx.set_option(native.OPT_FORWARD_KERNEL, fwd_kernel)
+    ctx.set_option(native.OPT_VECTOR_ATOMICS, int(vec))
+    tb, tf, tw = [], [], []
+    for f, (ro, rd, g) in enumerate(frames):
+        if flat:
+            rd = rd.reshape(-1, 3); g = g.reshape(-1, 9)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(); ctx.build(means, scales, rots, opac)
+        e[1].record(); res = ctx.forward(ro, rd, bg, means, scales, rots, opac, shs, 3, cap=cap, want_slots=True)
+        e[2].record(); ctx.backward(ro, rd, bg, means, scales, rots, opac, shs, 3, res["out"], g, hits=res)
+        e[3].record(); torch.cuda.synchronize()
+        if f > 0 or a.frames == 1:
+            tb.append(e[0].elapsed_time(e[1])); tf.append(e[1].elapsed_time(e[2])); tw.append(e[2].elapsed_time(e[3]))
     sl = res["slot_cnt"].cpu().numpy().astype(np.int64); hc = res["hit_cnt"].cpu().numpy()
-    print(f"frame {f}: build {1e3*(t1-t0):.2f} ms fwd {1e3*(t2-t1):.2f} ms bwd {1e3*(t3-t2):.2f} ms | slots/ray {np.mean(sl & 0xffff):.1f} "
-          f"contrib/ray {hc.mean():.1f} max {hc.max()} overflow {(hc > 64).mean():.3f}")
+    print(f"{label:34s} build {np.mean(tb):6.2f} ms  fwd {np.mean(tf):6.2f} ms  bwd {np.mean(tw):6.2f} ms  | slots/ray {np.mean(sl & 0xffff):.1f} "
+          f"contrib/ray {hc.mean():.1f} max {hc.max()} overflow {(hc > cap).mean():.4f}", flush=True)
     if a.stats:
         nodes = sl >> 16
-        print(f"   node visits/ray: mean {nodes.mean():.0f} median {np.median(nodes):.0f} p90 {np.percentile(nodes, 90):.0f} max {nodes.max()}")
-        rows = nodes.reshape(64, 2650).mean(1)
-        print("   node visits by beam row:", np.round(rows[::4]).astype(int))
+        print(f"   node evaluations/ray: mean {nodes.mean():.0f} median {np.median(nodes):.0f} p90 {np.percentile(nodes, 90):.0f} max {nodes.max()}")
+        print("   by beam row (every 4th):", np.round(nodes.reshape(64, 2650).mean(1)[::4]).astype(int))
+    return res
+
+
+if a.ab:
+    ref = None
+    for fk in (0, 1):
+        for flat in (True, False):
+            res = run(fk, flat, True, 128, f"fwd_kernel={fk} tiles={'no' if flat else '4x8'} vec=1 cap=128")
+            out = res["out"].reshape(-1, 9)
+            if ref is None:
+                ref = out.clone()
+            else:
+                print("      identical to first config:", bool(torch.equal(ref, out)))
+    run(1, False, False, 128, "fwd_kernel=1 tiles=4x8 vec=0 cap=128")
+    run(1, False, True, 64, "fwd_kernel=1 tiles=4x8 vec=1 cap=64")
+else:
+    run(a.fwd_kernel, a.flat, not a.no_vec, a.cap, f"fwd_kernel={a.fwd_kernel} tiles={'no' if a.flat else '4x8'} vec={int(not a.no_vec)} cap={a.cap}")
