@@ -99,8 +99,9 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
  *   LRT_OPT_RAY_GRID_WIDTH  W > 0: the R rays of the next calls are a row-major (R / W, W) range image
  *                           (the (H, W, 3) tensors of the reference API); lets a warp take a 4 x 8 tile of
  *                           neighbouring rays. 0 = no structure known (default).
- *   LRT_OPT_VECTOR_ATOMICS  backward: 128-bit vector reductions where alignment allows (default 1) */
-enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3 };
+ *   LRT_OPT_VECTOR_ATOMICS  backward: 128-bit vector reductions where alignment allows (default 1)
+ *   LRT_OPT_MORTON_BITS     63 = 21 bits/axis on cubic cells (default), 30 = 10 bits/axis per-axis extent (next lrt_build) */
+enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4 };
 int lrt_set_option(lrt_ctx* ctx, int option, int value);
 
 /* Introspection for tests / benchmarks (host pointers). */
@@ -115,6 +116,8 @@ typedef struct lrt_info {
     int32_t kernel_launches;      /* kernels launched by this library since context creation */
 } lrt_info;
 int lrt_get_info(const lrt_ctx* ctx, lrt_info* out);
+/* development counters (all zero unless the library was built with -DLRT_STATS); out = 16 host uint64 */
+int lrt_debug_stats(unsigned long long* out, int reset);
 /* sorted position -> caller's Gaussian index, (P) int32 device copy */
 int lrt_get_permutation(const lrt_ctx* ctx, int32_t* perm_out, void* stream);
 

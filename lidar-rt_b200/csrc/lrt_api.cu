@@ -4,6 +4,10 @@
 
 static std::string g_create_error;
 
+#ifdef LRT_STATS
+__device__ unsigned long long g_lrt_stats[16];
+#endif
+
 extern "C" {
 
 int lrt_version(void) { return LRT_VERSION; }
@@ -85,6 +89,7 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
     switch (option) {
     case LRT_OPT_FORWARD_KERNEL: if (value != 0 && value != 1) break; ctx->opt_forward_kernel = value; return LRT_OK;
     case LRT_OPT_RAY_GRID_WIDTH: if (value < 0) break; ctx->opt_ray_grid_w = value; return LRT_OK;
+    case LRT_OPT_MORTON_BITS: if (value != 30 && value != 63) break; ctx->opt_morton_bits = value; return LRT_OK;
     case LRT_OPT_VECTOR_ATOMICS: if (value != 0 && value != 1) break; ctx->opt_vector_atomics = value; return LRT_OK;
     default: break;
     }
@@ -103,6 +108,19 @@ int lrt_get_info(const lrt_ctx* ctx, lrt_info* out)
     out->bytes_workspace = (int64_t)ctx->total_bytes();
     out->builds = ctx->builds; out->refits = ctx->refits;
     out->kernel_launches = ctx->launches;
+    return LRT_OK;
+}
+
+/* development statistics (non-zero only in the -DLRT_STATS build); out = 16 host uint64 */
+int lrt_debug_stats(unsigned long long* out, int reset)
+{
+#ifdef LRT_STATS
+    if (out && cudaMemcpyFromSymbol(out, g_lrt_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return LRT_ERR_CUDA;
+    if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(g_lrt_stats, z, sizeof(z)) != cudaSuccess) return LRT_ERR_CUDA; }
+#else
+    if (out) for (int i = 0; i < 16; i++) out[i] = 0;
+    (void)reset;
+#endif
     return LRT_OK;
 }
 

@@ -81,6 +81,37 @@ __global__ void __launch_bounds__(256) k_morton(int P, const float* __restrict__
     idx[i] = (unsigned)i;
 }
 
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v)
+{
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+// 63-bit keys on CUBIC cells (all axes normalised by the largest extent): a street scene is 220 x 50 x 17 m,
+// per-axis normalisation would spend as many bits on 17 m of height as on 220 m of road.
+__global__ void __launch_bounds__(256) k_morton64(int P, const float* __restrict__ means, const int* __restrict__ b,
+                                                  unsigned long long* __restrict__ keys, unsigned* __restrict__ idx)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float lo[3] = {ord2f(b[0]), ord2f(b[1]), ord2f(b[2])};
+    const float ext = fmaxf(fmaxf(ord2f(b[3]) - lo[0], ord2f(b[4]) - lo[1]), fmaxf(ord2f(b[5]) - lo[2], 1e-20f));
+    unsigned long long q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float t = (means[3 * i + k] - lo[k]) / ext * 2097152.0f;
+        t = fminf(fmaxf(t, 0.0f), 2097151.0f);
+        q[k] = (t == t) ? (unsigned long long)t : 0ull;
+    }
+    keys[i] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    idx[i] = (unsigned)i;
+}
+
 __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigned* __restrict__ perm,
                                                  const float* __restrict__ means, const float* __restrict__ scales,
                                                  const float* __restrict__ rots, const float* __restrict__ opac,
@@ -190,21 +221,31 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
     const int TB = 256;
     if (!refit) {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->perm_b, sizeof(unsigned) * (size_t)P));
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_a, sizeof(unsigned) * (size_t)P));
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_b, sizeof(unsigned) * (size_t)P));
+        const bool wide = ctx->opt_morton_bits > 30;
+        const size_t ksz = wide ? sizeof(unsigned long long) : sizeof(unsigned);
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_a, ksz * (size_t)P));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_b, ksz * (size_t)P));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bounds, sizeof(int) * 8));
         size_t tmp_bytes = 0;
-        cub::DoubleBuffer<unsigned> dk((unsigned*)ctx->keys_a.p, (unsigned*)ctx->keys_b.p);
         cub::DoubleBuffer<unsigned> dv((unsigned*)ctx->perm_b.p, (unsigned*)ctx->perm_a.p);
-        LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, P, 0, 30, s));
+        cub::DoubleBuffer<unsigned> dk32((unsigned*)ctx->keys_a.p, (unsigned*)ctx->keys_b.p);
+        cub::DoubleBuffer<unsigned long long> dk64((unsigned long long*)ctx->keys_a.p, (unsigned long long*)ctx->keys_b.p);
+        if (wide) { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk64, dv, P, 0, 63, s)); }
+        else { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk32, dv, P, 0, 30, s)); }
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sort_tmp, tmp_bytes));
         k_bounds_init<<<1, 32, 0, s>>>((int*)ctx->bounds.p);
         const int gb = min((P + TB - 1) / TB, 148 * 8);
         k_bounds<<<gb, TB, 0, s>>>(P, means, (int*)ctx->bounds.p);
-        k_morton<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
-                                                   (unsigned*)ctx->perm_b.p);
-        LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk, dv, P, 0, 30, s));
-        ctx->launches += 3 + 8;     // + radix sort passes (histogram/scan/onesweep)
+        if (wide) {
+            k_morton64<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned long long*)ctx->keys_a.p,
+                                                         (unsigned*)ctx->perm_b.p);
+            LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk64, dv, P, 0, 63, s));
+        } else {
+            k_morton<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
+                                                       (unsigned*)ctx->perm_b.p);
+            LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk32, dv, P, 0, 30, s));
+        }
+        ctx->launches += 3 + 2 + (wide ? 8 : 4);     // bounds_init, bounds, morton + radix sort (histogram, scan, one onesweep launch per 8-bit digit)
         if (dv.Current() != (unsigned*)ctx->perm_a.p) {          // keep the permutation in perm_a
             LRT_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->perm_a.p, dv.Current(), sizeof(unsigned) * (size_t)P,
                                               cudaMemcpyDeviceToDevice, s));

@@ -172,11 +172,15 @@ __global__ void __launch_bounds__(128) k_forward(BvhView bvh, FwdArgs a)
 // >= LRT_SHADE_BATCH lanes wait for it or nobody can traverse) so that its divergent code is amortised.
 #define LRT_ST_FETCH 0
 #define LRT_ST_TRAV 1
-#define LRT_ST_SHADE 2
-#define LRT_ST_DONE 3
+#define LRT_ST_LEAF 2
+#define LRT_ST_SHADE 3
+#define LRT_ST_DONE 4
 #define LRT_SHADE_BATCH 8
 
-__global__ void __launch_bounds__(128) k_forward_persistent(BvhView bvh, FwdArgs a)
+#ifndef LRT_FWD_MIN_BLOCKS
+#define LRT_FWD_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, LRT_FWD_MIN_BLOCKS) k_forward_persistent(BvhView bvh, FwdArgs a)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(128) k_forward_persistent(BvhView bvh, FwdArgs
     RaySetup rs;
     Trav tv;
     unsigned long long kb[LRT_KBUF];
+    unsigned leaf_mask = 0;
     int node_visits = 0;
     q.r = -1;
     for (;;) {
@@ -211,27 +216,41 @@ __global__ void __launch_bounds__(128) k_forward_persistent(BvhView bvh, FwdArgs
                 }
             }
         }
-        if (__all_sync(FULL, st == LRT_ST_DONE)) break;
-        // 2. one node evaluation for every traversing lane
-        if (st == LRT_ST_TRAV) {
-            node_visits++;
-            if (trav_step(bvh, rs, kb, tv)) st = LRT_ST_SHADE;
-        }
-        // 3. batched shading
-        const unsigned ws = __ballot_sync(FULL, st == LRT_ST_SHADE);
+        // 2. phase vote: the warp executes ONE of {node evaluation, surfel test, shading} per trip — the
+        //    one most lanes are waiting for — so each divergent code path runs with many lanes active
         const unsigned wt = __ballot_sync(FULL, st == LRT_ST_TRAV);
-        if (st == LRT_ST_SHADE && (__popc(ws) >= LRT_SHADE_BATCH || wt == 0)) {
-            unsigned long long hits[LRT_KBUF];
+        const unsigned wl = __ballot_sync(FULL, st == LRT_ST_LEAF);
+        const unsigned ws = __ballot_sync(FULL, st == LRT_ST_SHADE);
+        if ((wt | wl | ws) == 0) {
+            if (__all_sync(FULL, st == LRT_ST_DONE)) break;
+            continue;                                   // only FETCH lanes left (padding slots)
+        }
+        const int nt = __popc(wt), nl = __popc(wl), ns = __popc(ws);
+        if (ns >= LRT_SHADE_BATCH || (nt == 0 && nl == 0)) {
+            if (st == LRT_ST_SHADE) {
+                unsigned long long hits[LRT_KBUF];
 #pragma unroll
-            for (int i = 0; i < LRT_KBUF; i++) hits[i] = kb[i];
-            const int n = kbuf_count(kb);
-            if (fwd_shade_round(q, hits, n, bvh, a)) {
-                ray_setup(rs, q.o, q.d, q.base);
-                trav_init(bvh, tv, kb);
-                st = LRT_ST_TRAV;
-            } else {
-                fwd_write(q, a, node_visits);
-                st = LRT_ST_FETCH;
+                for (int i = 0; i < LRT_KBUF; i++) hits[i] = kb[i];
+                const int n = kbuf_count(kb);
+                if (fwd_shade_round(q, hits, n, bvh, a)) {
+                    ray_setup(rs, q.o, q.d, q.base);
+                    trav_init(bvh, tv, kb);
+                    st = LRT_ST_TRAV;
+                } else {
+                    fwd_write(q, a, node_visits);
+                    st = LRT_ST_FETCH;
+                }
+            }
+        } else if (nl > nt) {
+            if (st == LRT_ST_LEAF) {
+                const int res = trav_leaf_one(bvh, rs, kb, tv, leaf_mask);
+                st = res == 2 ? LRT_ST_LEAF : (res == 1 ? LRT_ST_SHADE : LRT_ST_TRAV);
+            }
+        } else {
+            if (st == LRT_ST_TRAV) {
+                node_visits++;
+                const int res = trav_node(bvh, rs, kb, tv, leaf_mask);
+                st = res == 2 ? LRT_ST_LEAF : (res == 1 ? LRT_ST_SHADE : LRT_ST_TRAV);
             }
         }
     }

@@ -17,6 +17,15 @@
 
 #include "lrt_common.cuh"
 
+#ifdef LRT_STATS
+// development statistics build: [0..7] node evaluations per level, [8] quad tests, [9] quad hits,
+// [10] re-evaluations (climb-backs), [11] rounds
+extern __device__ unsigned long long g_lrt_stats[16];
+#define LRT_STAT(i) atomicAdd(&g_lrt_stats[i], 1ull)
+#else
+#define LRT_STAT(i)
+#endif
+
 #define LRT_KEY_EMPTY 0x5A0E1BCAFFFFFFFFull     // (bits(1e16f) << 32) | 0xffffffff : nothing at t' >= 1e16
 
 struct RaySetup {
@@ -116,6 +125,7 @@ __device__ __forceinline__ void trav_init(const BvhView& bvh, Trav& tv, unsigned
 #pragma unroll
     for (int i = 0; i < LRT_KBUF; i++) kb[i] = LRT_KEY_EMPTY;
     tv.level = bvh.levels - 1; tv.node = 0; tv.pend = 0xffu; tv.trail = 0;
+    LRT_STAT(11);
 }
 
 // One node evaluation. Returns true when the round's traversal is complete.
@@ -123,13 +133,17 @@ __device__ __forceinline__ bool trav_step(const BvhView& bvh, const RaySetup& r,
 {
     const float tmax = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32));
     int nearest;
+    LRT_STAT(tv.level); if (tv.pend != 0xffu) { LRT_STAT(10); }
     unsigned m = node_eval(bvh.nodes + bvh.level_off[tv.level] + tv.node, r, tmax, tv.pend, nearest);
     if (tv.level == 0) {
         while (m) {
             const int c = __ffs(m) - 1; m &= m - 1;
             float t; int g;
-            if (quad_hit(bvh.rec, (int)(tv.node * 8u + c), r, t, g))      // ties in t' resolve by the caller's Gaussian index
+            LRT_STAT(8);
+            if (quad_hit(bvh.rec, (int)(tv.node * 8u + c), r, t, g)) {   // ties in t' resolve by the caller's Gaussian index
+                LRT_STAT(9);
                 kbuf_insert(kb, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g);
+            }
         }
     }
     if (m) {                                            // enter the nearest child, remember the others
@@ -151,6 +165,62 @@ __device__ __forceinline__ bool trav_step(const BvhView& bvh, const RaySetup& r,
         }
         return false;
     }
+}
+
+// ---- split form of trav_step for the persistent kernel: node phase / leaf phase / navigation ----
+// Climb to the nearest ancestor with pending children (or finish). Returns true when the round is complete.
+__device__ __forceinline__ bool trav_climb(const BvhView& bvh, Trav& tv)
+{
+    for (;;) {
+        tv.level++; tv.node >>= 3;
+        if (tv.level >= bvh.levels) return true;
+        const unsigned p = (unsigned)(tv.trail >> (8 * tv.level)) & 0xffu;
+        if (p == 0) continue;
+        if ((p & (p - 1)) == 0) {
+            tv.trail &= ~(0xffull << (8 * tv.level));
+            tv.node = tv.node * 8u + (__ffs(p) - 1); tv.level--; tv.pend = 0xffu;
+        } else {
+            tv.pend = p;
+        }
+        return false;
+    }
+}
+
+// Node phase: evaluate the current node. Returns 0 = keep traversing, 1 = round complete,
+// 2 = at a leaf with candidate surfels in `leaf_mask` (to be consumed by trav_leaf_one).
+__device__ __forceinline__ int trav_node(const BvhView& bvh, const RaySetup& r, const unsigned long long (&kb)[LRT_KBUF], Trav& tv,
+                                         unsigned& leaf_mask)
+{
+    const float tmax = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32));
+    int nearest;
+    LRT_STAT(tv.level); if (tv.pend != 0xffu) { LRT_STAT(10); }
+    unsigned m = node_eval(bvh.nodes + bvh.level_off[tv.level] + tv.node, r, tmax, tv.pend, nearest);
+    if (tv.level == 0) {
+        if (m) { leaf_mask = m; return 2; }
+        return trav_climb(bvh, tv) ? 1 : 0;
+    }
+    if (m) {
+        m &= ~(1u << nearest);
+        tv.trail = (tv.trail & ~(0xffull << (8 * tv.level))) | ((unsigned long long)m << (8 * tv.level));
+        tv.node = tv.node * 8u + nearest; tv.level--; tv.pend = 0xffu;
+        return 0;
+    }
+    return trav_climb(bvh, tv) ? 1 : 0;
+}
+
+// Leaf phase: test ONE candidate surfel of the current leaf. Returns like trav_node (2 = more candidates).
+__device__ __forceinline__ int trav_leaf_one(const BvhView& bvh, const RaySetup& r, unsigned long long (&kb)[LRT_KBUF], Trav& tv,
+                                             unsigned& leaf_mask)
+{
+    const int c = __ffs(leaf_mask) - 1; leaf_mask &= leaf_mask - 1;
+    float t; int g;
+    LRT_STAT(8);
+    if (quad_hit(bvh.rec, (int)(tv.node * 8u + c), r, t, g)) {
+        LRT_STAT(9);
+        kbuf_insert(kb, ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g);
+    }
+    if (leaf_mask) return 2;
+    return trav_climb(bvh, tv) ? 1 : 0;
 }
 
 __device__ __forceinline__ int kbuf_count(const unsigned long long (&kb)[LRT_KBUF])

@@ -16,6 +16,7 @@ ap.add_argument("--fwd-kernel", type=int, default=1)
 ap.add_argument("--flat", action="store_true", help="pass rays as (R,3): no 4x8 tiles")
 ap.add_argument("--no-vec", action="store_true")
 ap.add_argument("--cap", type=int, default=native.DEFAULT_HIT_CAP)
+ap.add_argument("--morton", type=int, default=63)
 a = ap.parse_args()
 BG = np.array([0, 0, 1], np.float32)
 cu = lambda x: torch.as_tensor(np.ascontiguousarray(x), device="cuda")
@@ -32,7 +33,8 @@ for f in range(a.frames):
 bg = cu(BG)
 
 
-def run(fwd_kernel, flat, vec, cap, label, verbose=True):
+def run(fwd_kernel, flat, vec, cap, label, verbose=True, morton=None):
+    ctx.set_option(native.OPT_MORTON_BITS, morton or a.morton)
     ctx.set_option(native.OPT_FORWARD_KERNEL, fwd_kernel)
     ctx.set_option(native.OPT_VECTOR_ATOMICS, int(vec))
     tb, tf, tw = [], [], []
@@ -50,6 +52,9 @@ def run(fwd_kernel, flat, vec, cap, label, verbose=True):
     print(f"{label:34s} build {np.mean(tb):6.2f} ms  fwd {np.mean(tf):6.2f} ms  bwd {np.mean(tw):6.2f} ms  | slots/ray {np.mean(sl & 0xffff):.1f} "
           f"contrib/ray {hc.mean():.1f} max {hc.max()} overflow {(hc > cap).mean():.4f}", flush=True)
     if a.stats:
+        import ctypes
+        st = (ctypes.c_ulonglong * 16)(); ctx.lib.lrt_debug_stats(st, 1); st = np.array(list(st), np.float64) / (a.frames * hc.shape[0])
+        print(f"   per ray: evals by level {np.round(st[:8], 1)} quad tests {st[8]:.1f} quad hits {st[9]:.1f} re-evals {st[10]:.1f} rounds {st[11]:.2f}")
         nodes = sl >> 16
         print(f"   node evaluations/ray: mean {nodes.mean():.0f} median {np.median(nodes):.0f} p90 {np.percentile(nodes, 90):.0f} max {nodes.max()}")
         print("   by beam row (every 4th):", np.round(nodes.reshape(64, 2650).mean(1)[::4]).astype(int))
@@ -67,6 +72,7 @@ if a.ab:
             else:
                 print("      identical to first config:", bool(torch.equal(ref, out)))
     run(1, False, False, 128, "fwd_kernel=1 tiles=4x8 vec=0 cap=128")
-    run(1, False, True, 64, "fwd_kernel=1 tiles=4x8 vec=1 cap=64")
+    run(1, False, True, 128, "fwd_kernel=1 tiles=4x8 morton=30", morton=30)
+    run(1, False, True, 128, "fwd_kernel=1 tiles=4x8 morton=63", morton=63)
 else:
-    run(a.fwd_kernel, a.flat, not a.no_vec, a.cap, f"fwd_kernel={a.fwd_kernel} tiles={'no' if a.flat else '4x8'} vec={int(not a.no_vec)} cap={a.cap}")
+    run(a.fwd_kernel, a.flat, not a.no_vec, a.cap, f"fwd_kernel={a.fwd_kernel} tiles={'no' if a.flat else '4x8'} vec={int(not a.no_vec)} cap={a.cap} morton={a.morton}")
