@@ -176,9 +176,10 @@ __global__ void __launch_bounds__(128) k_forward(BvhView bvh, FwdArgs a)
 #define LRT_ST_SHADE 3
 #define LRT_ST_DONE 4
 #define LRT_SHADE_BATCH 8
+#define LRT_MIN_LANES 5
 
 #ifndef LRT_FWD_MIN_BLOCKS
-#define LRT_FWD_MIN_BLOCKS 1
+#define LRT_FWD_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(128, LRT_FWD_MIN_BLOCKS) k_forward_persistent(BvhView bvh, FwdArgs a)
 {
@@ -216,8 +217,10 @@ __global__ void __launch_bounds__(128, LRT_FWD_MIN_BLOCKS) k_forward_persistent(
                 }
             }
         }
-        // 2. phase vote: the warp executes ONE of {node evaluation, surfel test, shading} per trip — the
-        //    one most lanes are waiting for — so each divergent code path runs with many lanes active
+        // 2. what is waiting? Every trip runs the node-evaluation block for lanes in TRAV and the surfel-test
+        //    block for lanes in LEAF, so every traversing lane advances one step per trip; a block is skipped
+        //    for a trip only when very few lanes want it while many want the other. Shading (long, divergent)
+        //    is batched.
         const unsigned wt = __ballot_sync(FULL, st == LRT_ST_TRAV);
         const unsigned wl = __ballot_sync(FULL, st == LRT_ST_LEAF);
         const unsigned ws = __ballot_sync(FULL, st == LRT_ST_SHADE);
@@ -241,17 +244,19 @@ __global__ void __launch_bounds__(128, LRT_FWD_MIN_BLOCKS) k_forward_persistent(
                     st = LRT_ST_FETCH;
                 }
             }
-        } else if (nl > nt) {
-            if (st == LRT_ST_LEAF) {
-                const int res = trav_leaf_one(bvh, rs, kb, tv, leaf_mask);
-                st = res == 2 ? LRT_ST_LEAF : (res == 1 ? LRT_ST_SHADE : LRT_ST_TRAV);
-            }
-        } else {
-            if (st == LRT_ST_TRAV) {
-                node_visits++;
-                const int res = trav_node(bvh, rs, kb, tv, leaf_mask);
-                st = res == 2 ? LRT_ST_LEAF : (res == 1 ? LRT_ST_SHADE : LRT_ST_TRAV);
-            }
+            continue;
+        }
+        const bool run_leaf = nl > 0 && (nl >= LRT_MIN_LANES || nt < LRT_MIN_LANES);
+        const bool run_node = nt > 0 && (nt >= LRT_MIN_LANES || nl < LRT_MIN_LANES);
+        const int st_in = st;
+        if (run_leaf && st_in == LRT_ST_LEAF) {
+            const int res = trav_leaf_one(bvh, rs, kb, tv, leaf_mask);
+            st = res == 2 ? LRT_ST_LEAF : (res == 1 ? LRT_ST_SHADE : LRT_ST_TRAV);
+        }
+        if (run_node && st_in == LRT_ST_TRAV) {
+            node_visits++;
+            const int res = trav_node(bvh, rs, kb, tv, leaf_mask);
+            st = res == 2 ? LRT_ST_LEAF : (res == 1 ? LRT_ST_SHADE : LRT_ST_TRAV);
         }
     }
 }

@@ -128,6 +128,28 @@ __device__ __forceinline__ void trav_init(const BvhView& bvh, Trav& tv, unsigned
     LRT_STAT(11);
 }
 
+// Climb to the nearest ancestor with pending children (or finish). Returns true when the round is complete.
+// O(1): the trail bytes of all levels between the current one and that ancestor are zero (a level is
+// only left upwards once its byte is consumed), so the target level is the first non-zero byte above.
+__device__ __forceinline__ bool trav_climb(const BvhView& bvh, Trav& tv)
+{
+    const int sh = 8 * (tv.level + 1);
+    const unsigned long long up = sh < 64 ? (tv.trail >> sh) : 0ull;
+    if (up == 0) { tv.level = bvh.levels; return true; }
+    const int k = (__ffsll((long long)up) - 1) >> 3;          // levels to skip above level + 1
+    const int lv = tv.level + 1 + k;
+    tv.node >>= 3 * (k + 1);
+    tv.level = lv;
+    const unsigned p = (unsigned)(tv.trail >> (8 * lv)) & 0xffu;
+    if ((p & (p - 1)) == 0) {                               // a single child left: enter it directly
+        tv.trail &= ~(0xffull << (8 * lv));
+        tv.node = tv.node * 8u + (__ffs(p) - 1); tv.level--; tv.pend = 0xffu;
+    } else {
+        tv.pend = p;                                        // re-evaluated by the next step: order + culling refresh
+    }
+    return false;
+}
+
 // One node evaluation. Returns true when the round's traversal is complete.
 __device__ __forceinline__ bool trav_step(const BvhView& bvh, const RaySetup& r, unsigned long long (&kb)[LRT_KBUF], Trav& tv)
 {
@@ -152,40 +174,10 @@ __device__ __forceinline__ bool trav_step(const BvhView& bvh, const RaySetup& r,
         tv.node = tv.node * 8u + nearest; tv.level--; tv.pend = 0xffu;
         return false;
     }
-    for (;;) {                                          // climb to the nearest ancestor with pending children
-        tv.level++; tv.node >>= 3;
-        if (tv.level >= bvh.levels) return true;
-        const unsigned p = (unsigned)(tv.trail >> (8 * tv.level)) & 0xffu;
-        if (p == 0) continue;
-        if ((p & (p - 1)) == 0) {                       // a single child left: no ordering decision, enter it directly
-            tv.trail &= ~(0xffull << (8 * tv.level));
-            tv.node = tv.node * 8u + (__ffs(p) - 1); tv.level--; tv.pend = 0xffu;
-        } else {
-            tv.pend = p;                                // re-evaluated by the next step: order + culling refresh
-        }
-        return false;
-    }
+    return trav_climb(bvh, tv);
 }
 
 // ---- split form of trav_step for the persistent kernel: node phase / leaf phase / navigation ----
-// Climb to the nearest ancestor with pending children (or finish). Returns true when the round is complete.
-__device__ __forceinline__ bool trav_climb(const BvhView& bvh, Trav& tv)
-{
-    for (;;) {
-        tv.level++; tv.node >>= 3;
-        if (tv.level >= bvh.levels) return true;
-        const unsigned p = (unsigned)(tv.trail >> (8 * tv.level)) & 0xffu;
-        if (p == 0) continue;
-        if ((p & (p - 1)) == 0) {
-            tv.trail &= ~(0xffull << (8 * tv.level));
-            tv.node = tv.node * 8u + (__ffs(p) - 1); tv.level--; tv.pend = 0xffu;
-        } else {
-            tv.pend = p;
-        }
-        return false;
-    }
-}
-
 // Node phase: evaluate the current node. Returns 0 = keep traversing, 1 = round complete,
 // 2 = at a leaf with candidate surfels in `leaf_mask` (to be consumed by trav_leaf_one).
 __device__ __forceinline__ int trav_node(const BvhView& bvh, const RaySetup& r, const unsigned long long (&kb)[LRT_KBUF], Trav& tv,
