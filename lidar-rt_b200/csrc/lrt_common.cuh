@@ -124,6 +124,59 @@ __device__ __forceinline__ void sh_colour(int deg, const float* dirn, const floa
 }
 
 __device__ __forceinline__ float ld_f(const float* p) { return __ldg(p); }
+
+// SH basis only (same expressions as sh_colour); returns the number of active coefficients.
+__device__ __forceinline__ int sh_basis(int deg, const float* dirn, float* b)
+{
+    const float x = dirn[0], y = dirn[1], z = dirn[2];
+    int nb = 1;
+    b[0] = LRT_SH_C0;
+    if (deg > 0) {
+        b[1] = -LRT_SH_C1 * y; b[2] = LRT_SH_C1 * z; b[3] = -LRT_SH_C1 * x; nb = 4;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            b[4] = LRT_SH_C2_0 * xy; b[5] = LRT_SH_C2_1 * yz; b[6] = LRT_SH_C2_2 * (2.0f * zz - xx - yy);
+            b[7] = LRT_SH_C2_3 * xz; b[8] = LRT_SH_C2_4 * (xx - yy); nb = 9;
+            if (deg > 2) {
+                b[9] = LRT_SH_C3_0 * y * (3.0f * xx - yy);
+                b[10] = LRT_SH_C3_1 * xy * z;
+                b[11] = LRT_SH_C3_2 * y * (4.0f * zz - xx - yy);
+                b[12] = LRT_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                b[13] = LRT_SH_C3_4 * x * (4.0f * zz - xx - yy);
+                b[14] = LRT_SH_C3_5 * z * (xx - yy);
+                b[15] = LRT_SH_C3_6 * x * (xx - 3.0f * yy);
+                nb = 16;
+            }
+        }
+    }
+    return nb;
+}
+
+// SH colour streamed straight from global memory (no 48-float staging array): the (M,3) row of one
+// Gaussian is consumed in memory order, which is coefficient order per channel, so every channel sum is
+// accumulated in exactly the order sh_colour() uses. Needs a 16-byte aligned row (M % 4 == 0).
+__device__ __forceinline__ void sh_colour_stream(int deg, const float* dirn, const float* __restrict__ row, float* c)
+{
+    float b[16];
+    const int nb = sh_basis(deg, dirn, b);
+    const int nf = 3 * nb;
+    const float4* p4 = reinterpret_cast<const float4*>(row);
+    float r[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        if (4 * i < nf) {
+            const float4 v = __ldg(p4 + i);
+            const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int idx = 4 * i + e, j = idx / 3, ch = idx % 3;
+                if (idx < nf) r[ch] = (j == 0) ? b[0] * vals[e] : r[ch] + b[j] * vals[e];
+            }
+        }
+    }
+    c[0] = r[0] + 0.5f; c[1] = r[1] + 0.5f; c[2] = r[2] + 0.5f;
+    if (c[0] < 0.0f) c[0] = 0.0f;
+}
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return __ldg(p); }
 
 #define LRT_CUDA_TRY(ctx, call)                                                                     \

@@ -25,11 +25,11 @@ struct lrt_ctx {
     float scale_modifier = 1.0f;
     DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, iperm, sort_tmp, bounds, counter;
     // options (lrt_set_option)
-    int opt_forward_kernel = 1;   // 0: one thread per ray, 1: persistent threads with per-lane refill
+    int opt_forward_kernel = 1;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray
     int opt_ray_grid_w = 0;       // > 0: rays are a row-major range image of this width (enables 4 x 8 warp tiles)
     int opt_vector_atomics = 1;   // backward: red.global.add.v4.f32 where alignment allows
     int opt_morton_bits = 63;     // 63: 21 bits/axis on cubic cells (default); 30: 10 bits/axis, per-axis extent
-    int fwd_blocks_per_sm = 0, num_sms = 0;
+    int fwd_blocks_per_sm = 0, g8_blocks_per_sm = 0, num_sms = 0;
     long long builds = 0, refits = 0;
     int launches = 0;
 

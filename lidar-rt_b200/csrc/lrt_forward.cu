@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(128) k_forward(BvhView bvh, FwdArgs a)
 #pragma unroll
         for (int i = 0; i < LRT_KBUF; i++) hits[i] = kb[i];
         if (!fwd_shade_round(q, hits, n, bvh, a)) break;
+#ifdef LRT_NO_CULL
+        break;       // experiment build: one un-culled enumeration per ray, statistics only
+#endif
     }
     fwd_write(q, a, node_visits);
 }
@@ -175,8 +178,12 @@ __global__ void __launch_bounds__(128) k_forward(BvhView bvh, FwdArgs a)
 #define LRT_ST_LEAF 2
 #define LRT_ST_SHADE 3
 #define LRT_ST_DONE 4
+#ifndef LRT_SHADE_BATCH
 #define LRT_SHADE_BATCH 8
+#endif
+#ifndef LRT_MIN_LANES
 #define LRT_MIN_LANES 5
+#endif
 
 #ifndef LRT_FWD_MIN_BLOCKS
 #define LRT_FWD_MIN_BLOCKS 3
@@ -261,6 +268,217 @@ __global__ void __launch_bounds__(128, LRT_FWD_MIN_BLOCKS) k_forward_persistent(
     }
 }
 
+// ---- kernel C ("G8"): 8 lanes per ray, 4 rays per warp, persistent with per-group refill.
+// The node is 8 wide, so lane c of a group owns child c: a node evaluation is ONE slab test per lane
+// (instead of 8 per lane), the 8 surfels of a leaf are tested in parallel, the 16-entry k-buffer lives
+// 2 entries per lane (sorted insertion = two ballots + three shuffles), and a round's 16 hits are
+// shaded 8 at a time before an in-order fold composites them. Per-lane state shrinks from ~170 to
+// ~90 registers (twice the resident warps) and the dependent chain of a traversal step from ~200
+// to ~40 instructions. Arithmetic per hit is unchanged, so results are bit-identical to kernels A/B.
+#ifndef LRT_G8_MIN_BLOCKS
+#define LRT_G8_MIN_BLOCKS 6
+#endif
+#define G8_ST_FETCH 0
+#define G8_ST_TRAV 1
+#define G8_ST_SHADE 2
+#define G8_ST_DONE 3
+#define G8_F_DPT_OK 1u
+#define G8_F_OK 2u
+
+struct G8Slot { float dpt, alpha, c0, c1, c2; int g; unsigned flags; };
+
+// shade ONE k-buffer slot (everything of forward.cu:207-266 that does not depend on earlier slots)
+__device__ __forceinline__ void g8_shade_slot(unsigned long long key, bool valid, const FwdRay& q, const BvhView& bvh, const FwdArgs& a,
+                                              G8Slot& o)
+{
+    o.flags = 0; o.dpt = 0.f; o.alpha = 0.f; o.c0 = o.c1 = o.c2 = 0.f; o.g = -1;
+    if (!valid) return;
+    const int g = (int)(unsigned)(key & 0xffffffffull);
+    o.g = g;
+    o.dpt = __uint_as_float((unsigned)(key >> 32)) + q.base;                      // forward.cu:212
+    if (o.dpt < LRT_MIN_T) return;                                                // :214
+    o.flags |= G8_F_DPT_OK;
+    const float x0 = q.o[0] + o.dpt * q.d[0], x1 = q.o[1] + o.dpt * q.d[1], x2 = q.o[2] + o.dpt * q.d[2];
+    const int prim = __ldg(bvh.iperm + g);
+    const float4 a0 = ld_f4(&bvh.rec[prim].r0), a1 = ld_f4(&bvh.rec[prim].r1);
+    const float4 a2 = ld_f4(&bvh.rec[prim].r2), a3 = ld_f4(&bvh.rec[prim].r3);
+    const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
+    const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;                            // :139
+    const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+    const float cosv = -((a0.x - q.o[0]) * a3.x + (a0.y - q.o[1]) * a3.y + (a0.z - q.o[2]) * a3.z);
+    if (cosv == 0.0f) return;                                                     // :233-237
+    const float rho = u * u + v * v;
+    const float power = -0.5f * rho;
+    if (power > 0.0f) return;
+    const float G = expf(power);
+    o.alpha = fminf(LRT_ALPHA_MAX, a1.w * G);                                     // :249
+    if (o.alpha < 1.0f / 255.0f) return;
+    o.flags |= G8_F_OK;
+    float c[3];
+    if ((a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)) {
+        sh_colour_stream(a.D, q.dirn, a.shs + (size_t)g * a.M * 3, c);
+    } else {
+        const int nb = (a.D + 1) * (a.D + 1);
+        float sh[48]; bool cl;
+        load_sh(a.shs, g, a.M, nb, sh);
+        sh_colour<false>(a.D, q.dirn, sh, c, cl, nullptr);
+    }
+    o.c0 = c[0]; o.c1 = c[1]; o.c2 = c[2];
+}
+
+__global__ void __launch_bounds__(128, LRT_G8_MIN_BLOCKS) k_forward_g8(BvhView bvh, FwdArgs a)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7, gsh = 8 * grp;
+    const unsigned gmask = 0xffu << gsh;
+    const int S = num_slots(a.R, a.grid_w);
+    int st = G8_ST_FETCH;                         // group-uniform
+    FwdRay q;                                     // replicated on the 8 lanes of the group
+    RaySetup rs;
+    Trav tv;
+    unsigned long long k0 = LRT_KEY_EMPTY, k1 = LRT_KEY_EMPTY;   // k-buffer entries [sub] and [sub + 8]
+    float tmax = LRT_TMAX;                        // t' of entry 15 (replicated)
+    int node_visits = 0;
+    q.r = -1;
+    for (;;) {
+        __syncwarp(FULL);
+        // 1. refill idle groups (one atomic per warp)
+        const unsigned need = __ballot_sync(FULL, st == G8_ST_FETCH);
+        if (need) {
+            int base_slot = 0;
+            const int leader = __ffs(need) - 1;
+            if (lane == leader) base_slot = atomicAdd(a.work_counter, __popc(need) >> 3);
+            base_slot = __shfl_sync(FULL, base_slot, leader);
+            if (st == G8_ST_FETCH) {
+                const int s = base_slot + (__popc(need & ((1u << gsh) - 1u)) >> 3);
+                if (s >= S) st = G8_ST_DONE;
+                else {
+                    const int r = slot_to_ray(s, a.R, a.grid_w);
+                    if (r >= 0) {
+                        fwd_ray_init(q, r, a);
+                        ray_setup(rs, q.o, q.d, q.base);
+                        tv.level = bvh.levels - 1; tv.node = 0; tv.pend = 0xffu; tv.trail = 0;
+                        k0 = k1 = LRT_KEY_EMPTY; tmax = LRT_TMAX;
+                        node_visits = 0;
+                        LRT_STAT(11);
+                        st = G8_ST_TRAV;
+                    }
+                }
+            }
+        }
+        const unsigned wt = __ballot_sync(FULL, st == G8_ST_TRAV);
+        const unsigned ws = __ballot_sync(FULL, st == G8_ST_SHADE);
+        if ((wt | ws) == 0) {
+            if (__all_sync(FULL, st == G8_ST_DONE)) break;
+            continue;
+        }
+        // 2. traversal step: lane `sub` owns child `sub` of the group's current node
+        if (st == G8_ST_TRAV) {
+            node_visits++;
+            LRT_STAT(tv.level); if (tv.pend != 0xffu) { LRT_STAT(10); }
+            const Node8* nd = bvh.nodes + bvh.level_off[tv.level] + tv.node;
+            const float lx = ld_f(nd->lox + sub), ly = ld_f(nd->loy + sub), lz = ld_f(nd->loz + sub);
+            const float hx = ld_f(nd->hix + sub), hy = ld_f(nd->hiy + sub), hz = ld_f(nd->hiz + sub);
+            const float x0 = fmaf(lx, rs.ix, -rs.px), x1 = fmaf(hx, rs.ix, -rs.px);
+            const float y0 = fmaf(ly, rs.iy, -rs.py), y1 = fmaf(hy, rs.iy, -rs.py);
+            const float z0 = fmaf(lz, rs.iz, -rs.pz), z1 = fmaf(hz, rs.iz, -rs.pz);
+            const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+            const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+            const bool hit = (tn <= tf) && ((tv.pend >> sub) & 1u);
+            unsigned m = (__ballot_sync(gmask, hit) >> gsh) & 0xffu;
+            bool done = false;
+            if (tv.level == 0) {
+                if (m) {                                                   // the leaf's candidate surfels, in parallel
+                    float t = 0.f; int g = 0; bool qh = false;
+                    if (hit) { LRT_STAT(8); qh = quad_hit(bvh.rec, (int)(tv.node * 8u + sub), rs, t, g); if (qh) { LRT_STAT(9); } }
+                    unsigned qm = (__ballot_sync(gmask, qh) >> gsh) & 0xffu;
+                    while (qm) {                                           // distributed sorted insertion, one hit at a time
+                        const int src = __ffs(qm) - 1; qm &= qm - 1;
+                        const unsigned xh = __shfl_sync(gmask, __float_as_uint(t), src, 8);
+                        const unsigned xl = __shfl_sync(gmask, (unsigned)g, src, 8);
+                        const unsigned long long x = ((unsigned long long)xh << 32) | xl;
+                        const int pos = __popc(__ballot_sync(gmask, k0 < x) & gmask) + __popc(__ballot_sync(gmask, k1 < x) & gmask);
+                        const unsigned long long up0 = __shfl_up_sync(gmask, k0, 1, 8);
+                        const unsigned long long up1 = __shfl_up_sync(gmask, k1, 1, 8);
+                        const unsigned long long k0_7 = __shfl_sync(gmask, k0, 7, 8);
+                        if (pos < LRT_KBUF) {
+                            k0 = sub < pos ? k0 : (sub == pos ? x : up0);
+                            k1 = sub + 8 < pos ? k1 : (sub + 8 == pos ? x : (sub == 0 ? k0_7 : up1));
+                        }
+                        tmax = __uint_as_float(__shfl_sync(gmask, (unsigned)(k1 >> 32), 7, 8));
+                    }
+                }
+                done = trav_climb(bvh, tv);
+            } else if (m) {
+                // nearest entered child: redux-min over (tn bits | child) of the entering lanes
+                const unsigned key = hit ? ((__float_as_uint(tn) & ~7u) | (unsigned)sub) : 0xffffffffu;
+                const int c = (int)(__reduce_min_sync(gmask, key) & 7u);
+                m &= ~(1u << c);
+                tv.trail = (tv.trail & ~(0xffull << (8 * tv.level))) | ((unsigned long long)m << (8 * tv.level));
+                tv.node = tv.node * 8u + c; tv.level--; tv.pend = 0xffu;
+            } else {
+                done = trav_climb(bvh, tv);
+            }
+            if (done) st = G8_ST_SHADE;
+        }
+        // 3. shading: when at least two groups wait for it, or nothing else can run
+        const unsigned ws2 = __ballot_sync(FULL, st == G8_ST_SHADE);
+        const unsigned wt2 = __ballot_sync(FULL, st == G8_ST_TRAV);
+        if (st == G8_ST_SHADE && (__popc(ws2) >= 16 || wt2 == 0)) {
+            const int n = __popc(__ballot_sync(gmask, k0 != LRT_KEY_EMPTY) & gmask) + __popc(__ballot_sync(gmask, k1 != LRT_KEY_EMPTY) & gmask);
+            G8Slot sa, sb;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                G8Slot t_;
+                g8_shade_slot(pass ? k1 : k0, sub + 8 * pass < n, q, bvh, a, t_);
+                if (pass) sb = t_; else sa = t_;
+            }
+            bool terminated = false;
+            for (int i = 0; i < n; i++) {                                   // in-order fold (forward.cu:201-280)
+                const int src = i & 7; const bool second = i >= 8;
+                const float dpt_i = __shfl_sync(gmask, second ? sb.dpt : sa.dpt, src, 8);
+                const unsigned fl_i = __shfl_sync(gmask, second ? sb.flags : sa.flags, src, 8);
+                q.nslots++;
+                q.dpt = dpt_i;
+                if (!(fl_i & G8_F_DPT_OK)) continue;                                          // :214
+                const int g_i = __shfl_sync(gmask, second ? sb.g : sa.g, src, 8);
+                if (g_i == q.last) continue;                                                  // :220-224
+                q.last = g_i;
+                if (!(fl_i & G8_F_OK)) continue;
+                const float alpha = __shfl_sync(gmask, second ? sb.alpha : sa.alpha, src, 8);
+                q.testT = q.T * (1.0f - alpha);
+                if (q.testT < LRT_T_MIN) { terminated = true; break; }                        // :253-257
+                const float w = alpha * q.T;
+                const float c0 = __shfl_sync(gmask, second ? sb.c0 : sa.c0, src, 8);
+                const float c1 = __shfl_sync(gmask, second ? sb.c1 : sa.c1, src, 8);
+                const float c2 = __shfl_sync(gmask, second ? sb.c2 : sa.c2, src, 8);
+                q.C0 += w * c0; q.C1 += w * c1; q.C2 += w * c2;
+                q.Dp += w * dpt_i; q.W += w;
+                if (sub == src) {
+                    atomicAdd(a.accum_w + g_i, w);                                            // :272
+                    if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
+                        a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g_i;
+                        a.hit_t[(size_t)q.ncontrib * a.R + q.r] = dpt_i;
+                    }
+                }
+                q.ncontrib++;
+                q.T = q.testT;
+            }
+            if (!(terminated || q.testT < LRT_T_MIN || n < LRT_KBUF)) {                       // :282-291
+                q.base = (float)((double)q.dpt + LRT_STEP_EPS);
+                ray_setup(rs, q.o, q.d, q.base);
+                tv.level = bvh.levels - 1; tv.node = 0; tv.pend = 0xffu; tv.trail = 0;
+                k0 = k1 = LRT_KEY_EMPTY; tmax = LRT_TMAX;
+                LRT_STAT(11);
+                st = G8_ST_TRAV;
+            } else {
+                if (sub == 0) fwd_write(q, a, node_visits);
+                st = G8_ST_FETCH;
+            }
+        }
+    }
+}
+
 } // namespace
 
 int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
@@ -291,6 +509,18 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
     const int S = num_slots(R, a.grid_w);
     if (ctx->opt_forward_kernel == 0) {
         k_forward<<<(S + TB - 1) / TB, TB, 0, s>>>(ctx->view(), a);
+    } else if (ctx->opt_forward_kernel == 2) {
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 4));
+        LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 4, s));
+        a.work_counter = (int*)ctx->counter.p;
+        if (ctx->g8_blocks_per_sm == 0) {
+            int nb = 0, sms = 0;
+            LRT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_forward_g8, TB, 0));
+            LRT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+            ctx->g8_blocks_per_sm = nb > 0 ? nb : 1; ctx->num_sms = sms > 0 ? sms : 148;
+        }
+        const int grid = min(ctx->num_sms * ctx->g8_blocks_per_sm, (S + 15) / 16);      // 16 rays in flight per 128-thread block
+        k_forward_g8<<<grid, TB, 0, s>>>(ctx->view(), a);
     } else {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 4));
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 4, s));

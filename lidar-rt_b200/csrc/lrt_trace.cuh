@@ -153,7 +153,11 @@ __device__ __forceinline__ bool trav_climb(const BvhView& bvh, Trav& tv)
 // One node evaluation. Returns true when the round's traversal is complete.
 __device__ __forceinline__ bool trav_step(const BvhView& bvh, const RaySetup& r, unsigned long long (&kb)[LRT_KBUF], Trav& tv)
 {
+#ifdef LRT_NO_CULL   // experiment: enumerate every hit on the ray (what the reference's any-hit program sees)
+    const float tmax = LRT_TMAX;
+#else
     const float tmax = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32));
+#endif
     int nearest;
     LRT_STAT(tv.level); if (tv.pend != 0xffu) { LRT_STAT(10); }
     unsigned m = node_eval(bvh.nodes + bvh.level_off[tv.level] + tv.node, r, tmax, tv.pend, nearest);

@@ -63,16 +63,15 @@ def run(fwd_kernel, flat, vec, cap, label, verbose=True, morton=None):
 
 if a.ab:
     ref = None
-    for fk in (0, 1):
-        for flat in (True, False):
+    for fk in (0, 1, 2):
+        for flat in ((True, False) if fk < 2 else (False,)):
             res = run(fk, flat, True, 128, f"fwd_kernel={fk} tiles={'no' if flat else '4x8'} vec=1 cap=128")
             out = res["out"].reshape(-1, 9)
             if ref is None:
                 ref = out.clone()
             else:
                 print("      identical to first config:", bool(torch.equal(ref, out)))
-    run(1, False, False, 128, "fwd_kernel=1 tiles=4x8 vec=0 cap=128")
-    run(1, False, True, 128, "fwd_kernel=1 tiles=4x8 morton=30", morton=30)
-    run(1, False, True, 128, "fwd_kernel=1 tiles=4x8 morton=63", morton=63)
+    run(2, False, True, 128, "fwd_kernel=2 tiles=4x8 morton=30", morton=30)
+    run(2, True, True, 128, "fwd_kernel=2 tiles=no")
 else:
     run(a.fwd_kernel, a.flat, not a.no_vec, a.cap, f"fwd_kernel={a.fwd_kernel} tiles={'no' if a.flat else '4x8'} vec={int(not a.no_vec)} cap={a.cap} morton={a.morton}")

@@ -138,6 +138,32 @@ def test_backward_list_replay_equals_retrace_and_overflow(ctx):
     assert np.abs(e["g_opac"] - a["g_opac"]).max() > 1e-4
 
 
+def test_all_forward_kernels_and_options_agree_bitwise(ctx):
+    """LRT_OPT_FORWARD_KERNEL 0/1/2, ray tiles on/off, Morton 30/63: tuning knobs must not change a single bit."""
+    from lidar_rt_b200 import native
+    sc = syn.make_street_scene(60000, seed=12)
+    o, d = syn.ray_patch(32, 96, frame=1)
+    ref = None
+    try:
+        for kernel in (0, 1, 2):
+            for tiled in (True, False):
+                for morton in (63, 30):
+                    ctx.set_option(native.OPT_FORWARD_KERNEL, kernel)
+                    ctx.set_option(native.OPT_MORTON_BITS, morton)
+                    dd = d if tiled else d.reshape(-1, 3)
+                    res = run_cuda(ctx, o, dd, as_dict(sc), 3, cap=128)
+                    valid = np.arange(res["hit_gidx"].shape[0])[:, None] < res["hit_cnt"][None, :]
+                    key = (res["out"], res["hit_cnt"], res["slot_cnt"], np.where(valid, res["hit_gidx"], -1), np.where(valid, res["hit_t"], 0.0))
+                    if ref is None:
+                        ref = key
+                    else:
+                        for a_, b_ in zip(ref, key):
+                            assert np.array_equal(a_, b_), f"kernel={kernel} tiled={tiled} morton={morton} differs"
+    finally:
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 1); ctx.set_option(native.OPT_MORTON_BITS, 63)
+    assert_close(res["accum_w"], run_cuda(ctx, o, d, as_dict(sc), 3)["accum_w"], 1e-5, 1e-5, "accum (atomic order)")
+
+
 def test_refit_matches_rebuild(ctx):
     sc = syn.make_street_scene(30000, seed=9, n_actors=1, per_actor=2000)
     o, d = syn.ray_patch(16, 128)
