@@ -36,7 +36,8 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
 {
     if (!ctx) return LRT_OK;
     cudaSetDevice(ctx->device);
-    DevBuf* bufs[] = {&ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds, &ctx->counter};
+    DevBuf* bufs[] = {&ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
+                      &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     delete ctx;
     return LRT_OK;
@@ -87,7 +88,7 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
 {
     if (!ctx) return LRT_ERR_INVALID;
     switch (option) {
-    case LRT_OPT_FORWARD_KERNEL: if (value < 0 || value > 2) break; ctx->opt_forward_kernel = value; return LRT_OK;
+    case LRT_OPT_FORWARD_KERNEL: if (value < 0 || value > 3) break; ctx->opt_forward_kernel = value; return LRT_OK;
     case LRT_OPT_RAY_GRID_WIDTH: if (value < 0) break; ctx->opt_ray_grid_w = value; return LRT_OK;
     case LRT_OPT_MORTON_BITS: if (value != 30 && value != 63) break; ctx->opt_morton_bits = value; return LRT_OK;
     case LRT_OPT_VECTOR_ATOMICS: if (value != 0 && value != 1) break; ctx->opt_vector_atomics = value; return LRT_OK;

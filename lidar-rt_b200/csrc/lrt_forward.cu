@@ -139,11 +139,10 @@ __host__ __device__ __forceinline__ int num_slots(int R, int grid_w)
     return ((H + 3) >> 2) * ((grid_w + 7) >> 3) * 32;
 }
 
-// ---- kernel A: one thread per ray, whole ray in one go (simple; kept as the comparison baseline)
-__global__ void __launch_bounds__(128) k_forward(BvhView bvh, FwdArgs a)
+// ---- kernel A: one thread per ray, whole ray in one go (simple; kept as the comparison baseline and as the
+// fallback of the wavefront path)
+__device__ __forceinline__ void forward_one_ray(const BvhView& bvh, const FwdArgs& a, int r)
 {
-    const int r = slot_to_ray(blockIdx.x * blockDim.x + threadIdx.x, a.R, a.grid_w);
-    if (r < 0) return;
     FwdRay q;
     fwd_ray_init(q, r, a);
     int node_visits = 0;
@@ -165,6 +164,13 @@ __global__ void __launch_bounds__(128) k_forward(BvhView bvh, FwdArgs a)
 #endif
     }
     fwd_write(q, a, node_visits);
+}
+
+__global__ void __launch_bounds__(128) k_forward(BvhView bvh, FwdArgs a)
+{
+    const int r = slot_to_ray(blockIdx.x * blockDim.x + threadIdx.x, a.R, a.grid_w);
+    if (r < 0) return;
+    forward_one_ray(bvh, a, r);
 }
 
 // ---- kernel B: persistent threads. Rays differ 20x in traversal length (sky vs. long grazing rays), so
@@ -479,6 +485,8 @@ __global__ void __launch_bounds__(128, LRT_G8_MIN_BLOCKS) k_forward_g8(BvhView b
     }
 }
 
+#include "lrt_wavefront.cuh"
+
 } // namespace
 
 int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
@@ -509,6 +517,41 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
     const int S = num_slots(R, a.grid_w);
     if (ctx->opt_forward_kernel == 0) {
         k_forward<<<(S + TB - 1) / TB, TB, 0, s>>>(ctx->view(), a);
+    } else if (ctx->opt_forward_kernel == 3) {
+        // wavefront: level-by-level work lists, per-ray hit bins, warp-per-ray compositing
+        WfBufs w;
+        const long long cap_items = (long long)R * 160 + 1024;
+        if (cap_items > 0x3fffffffLL) { ctx->set_error("lrt_forward: too many rays for the wavefront work lists"); return LRT_ERR_INVALID; }
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_rs, sizeof(RaySetup) * (size_t)R));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_a, sizeof(uint2) * (size_t)cap_items));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_b, sizeof(uint2) * (size_t)cap_items));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_hit_count, sizeof(int) * (size_t)R));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_bins, sizeof(unsigned long long) * (size_t)R * WF_HCAP));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_fb, sizeof(int) * (size_t)R));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 16));
+        LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 16, s));
+        w.rs = (RaySetup*)ctx->wf_rs.p; w.list_a = (uint2*)ctx->wf_list_a.p; w.list_b = (uint2*)ctx->wf_list_b.p;
+        w.cap_items = (int)cap_items; w.counts = (int*)ctx->counter.p; w.hit_count = (int*)ctx->wf_hit_count.p;
+        w.bins = (unsigned long long*)ctx->wf_bins.p; w.fb_list = (int*)ctx->wf_fb.p;
+        if (ctx->num_sms == 0) {
+            int sms = 0;
+            LRT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+            ctx->num_sms = sms > 0 ? sms : 148;
+        }
+        const BvhView bv = ctx->view();
+        const int G = ctx->num_sms * 8;                                 // grid-stride kernels: 8 blocks of 256 threads per SM
+        k_wf_setup<<<(R + 255) / 256, 256, 0, s>>>(a, w);
+        const uint2* in = nullptr; const int* in_count = nullptr;
+        uint2* bufs[2] = {w.list_a, w.list_b};
+        int flip = 0;
+        for (int level = bv.levels - 1; level >= 1; level--) {
+            k_wf_level<<<G, 256, 0, s>>>(bv, a, w, level, in, in_count, bufs[flip], w.counts + (level - 1));
+            in = bufs[flip]; in_count = w.counts + (level - 1); flip ^= 1;
+        }
+        k_wf_leaf<<<G, 256, 0, s>>>(bv, a, w, in, in_count);
+        k_wf_shade<<<min((S + 3) / 4, ctx->num_sms * 8), 128, 0, s>>>(bv, a, w);
+        k_wf_fallback<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
+        ctx->launches += 3 + bv.levels;
     } else if (ctx->opt_forward_kernel == 2) {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 4));
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 4, s));

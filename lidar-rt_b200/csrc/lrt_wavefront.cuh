@@ -1,0 +1,256 @@
+// lrt_wavefront.cuh — forward "kernel D": breadth-first wavefront traversal + warp-per-ray compositing.
+// Included by lrt_forward.cu inside its anonymous namespace (uses FwdArgs, FwdRay, G8Slot, g8_shade_slot).
+//
+// Why: per-ray traversal (kernels A/B/C) keeps a warp's lanes in different places of different trees:
+// measured 9-15 active lanes per instruction and ~3-5e9 warp instructions per frame however the loop is
+// organised. The reference semantics do not need a per-ray loop at all: a round's k-buffer is "the 16
+// nearest proxy hits beyond the re-basing point", and the whole ray carries only ~40 proxy hits in this
+// workload. So:
+//   1. k_wf_level (one launch per hierarchy level, top-down): one thread per (ray, node) work item,
+//      evaluates the node's 8 child boxes and appends one item per entered child with a warp-aggregated
+//      atomic — every lane runs the same straight-line code, no state machine, no culling needed.
+//   2. k_wf_leaf: one thread per (ray, leaf) item: 8 surfel boxes, exact quad tests, hits appended to the
+//      ray's bin as 64-bit keys (t bits, Gaussian id).
+//   3. k_wf_shade: one warp per ray: sorts the bin (shared memory bitonic), then replays the reference's
+//      rounds exactly: round 1 = the 16 smallest keys; every later round re-tests a 32-hit window of the
+//      sorted bin from the re-based origin o' = o + base d (same arithmetic as the per-ray kernels, so t',
+//      the epsilon gap and duplicate suppression are reproduced bit for bit), shades 16 slots in parallel
+//      and folds them in order with shuffles.
+//   4. k_wf_fallback: rays the wavefront cannot guarantee (bin or work-list overflow, window guard) are
+//      traced by the per-ray code path. Same results, just slower; normally a handful of rays.
+#pragma once
+
+#define WF_HCAP 256                 // hit-bin capacity per ray (full, un-culled ray: ~40 hits on street scenes)
+#define WF_TAINT 0x40000000         // hit_count flag: work item or hit dropped -> fallback
+#define WF_WINDOW_MARGIN 1e-3f
+
+struct WfBufs {
+    RaySetup* rs;                   // (R) per-ray slab constants for base = 0
+    uint2* list_a; uint2* list_b;   // ping-pong work lists {ray, node}
+    int cap_items;
+    int* counts;                    // [0..7] items per level, [8] fallback count
+    int* hit_count;                 // (R) hits in bin | WF_TAINT
+    unsigned long long* bins;       // (R, WF_HCAP)
+    int* fb_list;                   // (R) fallback ray ids
+};
+
+__global__ void __launch_bounds__(256) k_wf_setup(FwdArgs a, WfBufs w)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    float o[3], d[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { o[k] = a.ray_o[(size_t)r * a.ray_o_stride + k]; d[k] = a.ray_d[3 * (size_t)r + k]; }
+    RaySetup rs;
+    ray_setup(rs, o, d, 0.0f);
+    w.rs[r] = rs;
+    w.hit_count[r] = 0;
+}
+
+// One (ray, node) item per thread at `level` >= 1. in == nullptr: the implicit root list (every ray, node 0)
+// in 4x8 tile order.
+__global__ void __launch_bounds__(256) k_wf_level(BvhView bvh, FwdArgs a, WfBufs w, int level, const uint2* __restrict__ in,
+                                                 const int* __restrict__ in_count, uint2* __restrict__ out, int* __restrict__ out_count)
+{
+    const int n_in = in ? min(*in_count, w.cap_items) : num_slots(a.R, a.grid_w);
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n_in; base += gridDim.x * blockDim.x) {
+        const int i = base + lane;
+        int ray = -1; unsigned node = 0;
+        if (i < n_in) {
+            if (in) { const uint2 it = in[i]; ray = (int)it.x; node = it.y; }
+            else ray = slot_to_ray(i, a.R, a.grid_w);
+        }
+        unsigned m = 0;
+        if (ray >= 0) {
+            const RaySetup rs = w.rs[ray];
+            int nearest;
+            m = node_eval(bvh.nodes + bvh.level_off[level] + node, rs, LRT_TMAX, 0xffu, nearest);
+        }
+        // warp-aggregated append: exclusive scan of the per-lane child counts
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        int wbase = 0;
+        if (lane == 31) wbase = atomicAdd(out_count, total);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        int off = wbase + incl - cnt;
+        if (cnt) {
+            if (off + cnt <= w.cap_items) {
+                while (m) { const int c = __ffs(m) - 1; m &= m - 1; out[off++] = make_uint2((unsigned)ray, node * 8u + c); }
+            } else {
+                atomicOr(w.hit_count + ray, WF_TAINT);          // work list full: this ray goes to the fallback
+            }
+        }
+    }
+}
+
+// One (ray, leaf) item per thread: the leaf's 8 surfel boxes, then the exact quad test (same arithmetic
+// as the per-ray kernels), hits appended to the ray's bin.
+__global__ void __launch_bounds__(256) k_wf_leaf(BvhView bvh, FwdArgs a, WfBufs w, const uint2* __restrict__ in, const int* __restrict__ in_count)
+{
+    const int n_in = in ? min(*in_count, w.cap_items) : num_slots(a.R, a.grid_w);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+        int ray; unsigned node = 0;
+        if (in) { const uint2 it = in[i]; ray = (int)it.x; node = it.y; }
+        else ray = slot_to_ray(i, a.R, a.grid_w);
+        if (ray < 0) continue;
+        const RaySetup rs = w.rs[ray];
+        int nearest;
+        unsigned m = node_eval(bvh.nodes + bvh.level_off[0] + node, rs, LRT_TMAX, 0xffu, nearest);
+        while (m) {
+            const int c = __ffs(m) - 1; m &= m - 1;
+            float t; int g;
+            if (quad_hit(bvh.rec, (int)(node * 8u + c), rs, t, g)) {
+                const int pos = atomicAdd(w.hit_count + ray, 1) & (WF_TAINT - 1);
+                if (pos < WF_HCAP) w.bins[(size_t)ray * WF_HCAP + pos] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+            }
+        }
+    }
+}
+
+// warp-wide bitonic sort of one 64-bit key per lane (ascending)
+__device__ __forceinline__ unsigned long long warp_sort32(unsigned long long k, int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, stride);
+            const bool up = ((lane & size) == 0);
+            const bool lower = ((lane & stride) == 0);
+            const bool take_min = (up == lower);
+            k = take_min ? (k < other ? k : other) : (k < other ? other : k);
+        }
+    }
+    return k;
+}
+
+// One warp per ray. smem: 4 warps x WF_HCAP keys.
+__global__ void __launch_bounds__(128) k_wf_shade(BvhView bvh, FwdArgs a, WfBufs w)
+{
+    __shared__ unsigned long long s_keys[4][WF_HCAP];
+    __shared__ float s_cw[4][WF_HCAP], s_cd[4][WF_HCAP];      // contributing hits of the current ray: weight, depth,
+    __shared__ int s_cg[4][WF_HCAP];                            // Gaussian id — committed only when the ray completes
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned long long* keys = s_keys[wib];
+    float* cw = s_cw[wib]; float* cd = s_cd[wib]; int* cg = s_cg[wib];
+    const int S = num_slots(a.R, a.grid_w);
+    for (int s = blockIdx.x * 4 + wib; s < S; s += gridDim.x * 4) {
+        const int r = slot_to_ray(s, a.R, a.grid_w);
+        if (r < 0) continue;                                       // warp-uniform
+        const int hc = w.hit_count[r];
+        if ((hc & WF_TAINT) || hc > WF_HCAP) {                     // not representable here: per-ray fallback
+            if (lane == 0) w.fb_list[atomicAdd(w.counts + 8, 1)] = r;
+            continue;
+        }
+        const int n = hc;
+        // ---- load + sort the bin (bitonic over the next power of two, in shared memory)
+        int m = 32; while (m < n) m <<= 1;
+        for (int i = lane; i < m; i += 32) keys[i] = i < n ? w.bins[(size_t)r * WF_HCAP + i] : LRT_KEY_EMPTY;
+        __syncwarp(FULL);
+        for (int size = 2; size <= m; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = lane; i < (m >> 1); i += 32) {
+                    const int lo = ((i / stride) * stride * 2) + (i % stride), hi = lo + stride;
+                    const unsigned long long x = keys[lo], y = keys[hi];
+                    const bool up = ((lo & size) == 0);
+                    if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+                }
+                __syncwarp(FULL);
+            }
+        }
+        // ---- the reference's round loop (forward.cu:195-292)
+        FwdRay q;
+        fwd_ray_init(q, r, a);
+        bool fallback = false;
+        int start = 0;                                             // round 1: slots = keys[0..15]
+        for (int round = 0;; round++) {
+            unsigned long long slot_key = LRT_KEY_EMPTY;           // lane i < 16 holds slot i of this round
+            int nvalid;
+            if (round == 0) {
+                slot_key = lane < n ? keys[lane] : LRT_KEY_EMPTY;  // lanes 16..31 hold entries 16..31 (unused)
+                nvalid = n;
+            } else {
+                // window: 32 bin entries from the first with t >= base - margin, re-tested from o' = o + base d
+                RaySetup rs;
+                ray_setup(rs, q.o, q.d, q.base);
+                const float thr = q.base - (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
+                int below = 0;
+                for (int i = lane; i < n; i += 32) below += __uint_as_float((unsigned)(keys[i] >> 32)) < thr;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) below += __shfl_xor_sync(FULL, below, o);
+                start = below;
+                unsigned long long nk = LRT_KEY_EMPTY;
+                const int idx = start + lane;
+                if (idx < n) {
+                    const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
+                    float t; int g2;
+                    if (quad_hit(bvh.rec, __ldg(bvh.iperm + g), rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                }
+                // guard: everything that could rank among the 16 nearest must be inside the window
+                const float t_last = (start + 31 < n) ? __uint_as_float((unsigned)(keys[start + 31] >> 32)) : 3.0e38f;
+                nk = warp_sort32(nk, lane);
+                slot_key = nk;
+                nvalid = __popc(__ballot_sync(FULL, nk != LRT_KEY_EMPTY));
+                if (start + 32 < n) {
+                    const unsigned long long k16 = __shfl_sync(FULL, nk, 15);
+                    const float t16 = (k16 != LRT_KEY_EMPTY) ? __uint_as_float((unsigned)(k16 >> 32)) + q.base : 3.0e38f;
+                    if (nvalid < LRT_KBUF || !(t_last - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16))) { fallback = true; break; }
+                }
+            }
+            const int nr = nvalid < LRT_KBUF ? nvalid : LRT_KBUF;   // slots of this round
+            G8Slot sl;
+            g8_shade_slot(slot_key, lane < nr, q, bvh, a, sl);
+            bool terminated = false;
+            for (int i = 0; i < nr; i++) {                          // in-order fold (forward.cu:201-280)
+                const float dpt_i = __shfl_sync(FULL, sl.dpt, i);
+                const unsigned fl_i = __shfl_sync(FULL, sl.flags, i);
+                q.nslots++;
+                q.dpt = dpt_i;
+                if (!(fl_i & G8_F_DPT_OK)) continue;
+                const int g_i = __shfl_sync(FULL, sl.g, i);
+                if (g_i == q.last) continue;
+                q.last = g_i;
+                if (!(fl_i & G8_F_OK)) continue;
+                const float alpha = __shfl_sync(FULL, sl.alpha, i);
+                q.testT = q.T * (1.0f - alpha);
+                if (q.testT < LRT_T_MIN) { terminated = true; break; }
+                const float wgt = alpha * q.T;
+                const float c0 = __shfl_sync(FULL, sl.c0, i), c1 = __shfl_sync(FULL, sl.c1, i), c2 = __shfl_sync(FULL, sl.c2, i);
+                q.C0 += wgt * c0; q.C1 += wgt * c1; q.C2 += wgt * c2;
+                q.Dp += wgt * dpt_i; q.W += wgt;
+                if (lane == i) { cw[q.ncontrib] = wgt; cd[q.ncontrib] = dpt_i; cg[q.ncontrib] = g_i; }   // ncontrib <= n <= WF_HCAP
+                q.ncontrib++;
+                q.T = q.testT;
+            }
+            if (terminated || q.testT < LRT_T_MIN || nvalid < LRT_KBUF) break;      // forward.cu:282-285
+            q.base = (float)((double)q.dpt + LRT_STEP_EPS);                          // :288
+        }
+        __syncwarp(FULL);
+        if (fallback) {                                            // nothing of this ray has been committed yet
+            if (lane == 0) w.fb_list[atomicAdd(w.counts + 8, 1)] = r;
+            continue;
+        }
+        for (int k = lane; k < q.ncontrib; k += 32) {              // commit: accum weights (forward.cu:272) + hit list
+            atomicAdd(a.accum_w + cg[k], cw[k]);
+            if (a.hit_gidx != nullptr && k < a.cap) {
+                a.hit_gidx[(size_t)k * a.R + r] = cg[k];
+                a.hit_t[(size_t)k * a.R + r] = cd[k];
+            }
+        }
+        if (lane == 0) fwd_write(q, a, 0);
+        __syncwarp(FULL);
+    }
+}
+
+// Rays the wavefront handed back (normally none or a handful): the per-ray code path, one thread per ray.
+__global__ void __launch_bounds__(128) k_wf_fallback(BvhView bvh, FwdArgs a, WfBufs w)
+{
+    const int n = min(w.counts[8], a.R);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) forward_one_ray(bvh, a, w.fb_list[i]);
+}

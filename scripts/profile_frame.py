@@ -63,8 +63,8 @@ def run(fwd_kernel, flat, vec, cap, label, verbose=True, morton=None):
 
 if a.ab:
     ref = None
-    for fk in (0, 1, 2):
-        for flat in ((True, False) if fk < 2 else (False,)):
+    for fk in (3, 0, 1, 2):
+        for flat in ((True, False) if fk in (0, 3) else (False,)):
             res = run(fk, flat, True, 128, f"fwd_kernel={fk} tiles={'no' if flat else '4x8'} vec=1 cap=128")
             out = res["out"].reshape(-1, 9)
             if ref is None:

@@ -139,13 +139,13 @@ def test_backward_list_replay_equals_retrace_and_overflow(ctx):
 
 
 def test_all_forward_kernels_and_options_agree_bitwise(ctx):
-    """LRT_OPT_FORWARD_KERNEL 0/1/2, ray tiles on/off, Morton 30/63: tuning knobs must not change a single bit."""
+    """LRT_OPT_FORWARD_KERNEL 0/1/2/3, ray tiles on/off, Morton 30/63: tuning knobs must not change a single bit."""
     from lidar_rt_b200 import native
     sc = syn.make_street_scene(60000, seed=12)
     o, d = syn.ray_patch(32, 96, frame=1)
     ref = None
     try:
-        for kernel in (0, 1, 2):
+        for kernel in (0, 1, 2, 3):
             for tiled in (True, False):
                 for morton in (63, 30):
                     ctx.set_option(native.OPT_FORWARD_KERNEL, kernel)
