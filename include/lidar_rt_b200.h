@@ -116,6 +116,8 @@ typedef struct lrt_info {
     int32_t kernel_launches;      /* kernels launched by this library since context creation */
 } lrt_info;
 int lrt_get_info(const lrt_ctx* ctx, lrt_info* out);
+/* development aid: work counters of the last forward (wavefront: [0..7] items per level, [8] fallback rays) */
+int lrt_debug_counters(const lrt_ctx* ctx, int* out);
 /* development counters (all zero unless the library was built with -DLRT_STATS); out = 16 host uint64 */
 int lrt_debug_stats(unsigned long long* out, int reset);
 /* sorted position -> caller's Gaussian index, (P) int32 device copy */

@@ -112,6 +112,17 @@ int lrt_get_info(const lrt_ctx* ctx, lrt_info* out)
     return LRT_OK;
 }
 
+/* development aid: the context's 16 work counters of the last forward (wavefront: [0..7] items per level,
+ * [8] rays handed to the per-ray fallback). Synchronises the device. */
+int lrt_debug_counters(const lrt_ctx* ctx, int* out)
+{
+    if (!ctx || !out) return LRT_ERR_INVALID;
+    for (int i = 0; i < 16; i++) out[i] = 0;
+    if (!ctx->counter.p || ctx->counter.cap < sizeof(int) * 16) return LRT_OK;
+    if (cudaDeviceSynchronize() != cudaSuccess) return LRT_ERR_CUDA;
+    return cudaMemcpy(out, ctx->counter.p, sizeof(int) * 16, cudaMemcpyDeviceToHost) == cudaSuccess ? LRT_OK : LRT_ERR_CUDA;
+}
+
 /* development statistics (non-zero only in the -DLRT_STATS build); out = 16 host uint64 */
 int lrt_debug_stats(unsigned long long* out, int reset)
 {

@@ -75,6 +75,28 @@ __device__ __forceinline__ bool quad_hit(const SurfelRec* __restrict__ rec, int 
     return t < LRT_TMAX;
 }
 
+// Candidate test for the wavefront's hit bins: the same plane hit, but with the quad bounds relaxed by a
+// margin far above fp32 rounding, so that the bin is a SUPERSET of what the exact test accepts from any
+// re-based origin on this ray. The exact quad_hit() decides, per round, which candidates are slots.
+__device__ __forceinline__ bool quad_candidate(const SurfelRec* __restrict__ rec, int prim, const RaySetup& r, float& t_out, int& g_out)
+{
+    const float4 a0 = ld_f4(&rec[prim].r0), a3 = ld_f4(&rec[prim].r3);
+    const float c0 = a0.x - r.ox, c1 = a0.y - r.oy, c2 = a0.z - r.oz;
+    const float den = a3.x * r.dx + a3.y * r.dy + a3.z * r.dz;
+    const float num = a3.x * c0 + a3.y * c1 + a3.z * c2;
+    const float t = num / den;
+    if (!(t > -1e-3f)) return false;
+    const float4 a1 = ld_f4(&rec[prim].r1), a2 = ld_f4(&rec[prim].r2);
+    const float r0 = (r.ox + t * r.dx) - a0.x, r1 = (r.oy + t * r.dy) - a0.y, r2 = (r.oz + t * r.dz) - a0.z;
+    const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
+    const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+    const float lim = a0.w + 1e-3f * (1.0f + a0.w);
+    if (!(fabsf(u) <= lim && fabsf(v) <= lim)) return false;
+    t_out = fmaxf(t, 0.0f);
+    g_out = __float_as_int(a2.w);
+    return t < LRT_TMAX;
+}
+
 // Sorted insertion into the register-resident k-buffer (ascending 64-bit keys = (t' bits, Gaussian id)).
 __device__ __forceinline__ void kbuf_insert(unsigned long long (&kb)[LRT_KBUF], unsigned long long key)
 {

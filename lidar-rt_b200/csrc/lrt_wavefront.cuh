@@ -12,15 +12,14 @@
 //   2. k_wf_leaf: one thread per (ray, leaf) item: 8 surfel boxes, exact quad tests, hits appended to the
 //      ray's bin as 64-bit keys (t bits, Gaussian id).
 //   3. k_wf_shade: one warp per ray: sorts the bin (shared memory bitonic), then replays the reference's
-//      rounds exactly: round 1 = the 16 smallest keys; every later round re-tests a 32-hit window of the
-//      sorted bin from the re-based origin o' = o + base d (same arithmetic as the per-ray kernels, so t',
+//      rounds exactly: every round re-tests a 32-candidate window of the sorted bin from the (re-based) origin o' = o + base d (same arithmetic as the per-ray kernels, so t',
 //      the epsilon gap and duplicate suppression are reproduced bit for bit), shades 16 slots in parallel
 //      and folds them in order with shuffles.
 //   4. k_wf_fallback: rays the wavefront cannot guarantee (bin or work-list overflow, window guard) are
 //      traced by the per-ray code path. Same results, just slower; normally a handful of rays.
 #pragma once
 
-#define WF_HCAP 256                 // hit-bin capacity per ray (full, un-culled ray: ~40 hits on street scenes)
+#define WF_HCAP 512                 // candidate-bin capacity per ray (full, un-culled ray: ~40 candidates on street scenes)
 #define WF_TAINT 0x40000000         // hit_count flag: work item or hit dropped -> fallback
 #define WF_WINDOW_MARGIN 1e-3f
 
@@ -89,7 +88,7 @@ __global__ void __launch_bounds__(256) k_wf_level(BvhView bvh, FwdArgs a, WfBufs
 }
 
 // One (ray, leaf) item per thread: the leaf's 8 surfel boxes, then the exact quad test (same arithmetic
-// as the per-ray kernels), hits appended to the ray's bin.
+// as the per-ray kernels, bounds relaxed: the bin holds CANDIDATES), appended to the ray's bin.
 __global__ void __launch_bounds__(256) k_wf_leaf(BvhView bvh, FwdArgs a, WfBufs w, const uint2* __restrict__ in, const int* __restrict__ in_count)
 {
     const int n_in = in ? min(*in_count, w.cap_items) : num_slots(a.R, a.grid_w);
@@ -104,7 +103,7 @@ __global__ void __launch_bounds__(256) k_wf_leaf(BvhView bvh, FwdArgs a, WfBufs 
         while (m) {
             const int c = __ffs(m) - 1; m &= m - 1;
             float t; int g;
-            if (quad_hit(bvh.rec, (int)(node * 8u + c), rs, t, g)) {
+            if (quad_candidate(bvh.rec, (int)(node * 8u + c), rs, t, g)) {
                 const int pos = atomicAdd(w.hit_count + ray, 1) & (WF_TAINT - 1);
                 if (pos < WF_HCAP) w.bins[(size_t)ray * WF_HCAP + pos] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
             }
@@ -168,40 +167,46 @@ __global__ void __launch_bounds__(128) k_wf_shade(BvhView bvh, FwdArgs a, WfBufs
         FwdRay q;
         fwd_ray_init(q, r, a);
         bool fallback = false;
-        int start = 0;                                             // round 1: slots = keys[0..15]
         for (int round = 0;; round++) {
             unsigned long long slot_key = LRT_KEY_EMPTY;           // lane i < 16 holds slot i of this round
             int nvalid;
-            if (round == 0) {
-                slot_key = lane < n ? keys[lane] : LRT_KEY_EMPTY;  // lanes 16..31 hold entries 16..31 (unused)
-                nvalid = n;
-            } else {
-                // window: 32 bin entries from the first with t >= base - margin, re-tested from o' = o + base d
+            {
+                // Candidates are re-tested, exactly, from o' = o + base d, 32 at a time in bin order starting at
+                // the first one with t >= base - margin; the 32 best (t', id) keys are kept (bitonic merge). The
+                // scan stops when the bin is exhausted or when the next unexamined candidate lies safely beyond
+                // the 16th best — so the round's slots are exactly the 16 nearest hits of the re-based ray.
                 RaySetup rs;
                 ray_setup(rs, q.o, q.d, q.base);
-                const float thr = q.base - (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
+                const float thr = q.base - 2.0f * (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
                 int below = 0;
                 for (int i = lane; i < n; i += 32) below += __uint_as_float((unsigned)(keys[i] >> 32)) < thr;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) below += __shfl_xor_sync(FULL, below, o);
-                start = below;
-                unsigned long long nk = LRT_KEY_EMPTY;
-                const int idx = start + lane;
-                if (idx < n) {
-                    const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
-                    float t; int g2;
-                    if (quad_hit(bvh.rec, __ldg(bvh.iperm + g), rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                int pos = below;
+                unsigned long long best = LRT_KEY_EMPTY;
+                for (;;) {
+                    unsigned long long nk = LRT_KEY_EMPTY;
+                    const int idx = pos + lane;
+                    if (idx < n) {
+                        const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
+                        float t; int g2;
+                        if (quad_hit(bvh.rec, __ldg(bvh.iperm + g), rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                    }
+                    nk = warp_sort32(nk, lane);
+                    const unsigned long long rev = __shfl_sync(FULL, nk, 31 - lane);      // bitonic merge: 32 smallest of best U nk
+                    best = warp_sort32(best < rev ? best : rev, lane);
+                    pos += 32;
+                    if (pos >= n) break;                                                   // bin exhausted: exact
+                    const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
+                    if (k16 != LRT_KEY_EMPTY) {
+                        const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
+                        const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
+                        if (t_next - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) break;   // nothing further can rank in the first 16
+                    }
                 }
-                // guard: everything that could rank among the 16 nearest must be inside the window
-                const float t_last = (start + 31 < n) ? __uint_as_float((unsigned)(keys[start + 31] >> 32)) : 3.0e38f;
-                nk = warp_sort32(nk, lane);
-                slot_key = nk;
-                nvalid = __popc(__ballot_sync(FULL, nk != LRT_KEY_EMPTY));
-                if (start + 32 < n) {
-                    const unsigned long long k16 = __shfl_sync(FULL, nk, 15);
-                    const float t16 = (k16 != LRT_KEY_EMPTY) ? __uint_as_float((unsigned)(k16 >> 32)) + q.base : 3.0e38f;
-                    if (nvalid < LRT_KBUF || !(t_last - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16))) { fallback = true; break; }
-                }
+                slot_key = best;
+                nvalid = __popc(__ballot_sync(FULL, best != LRT_KEY_EMPTY));
+                // nvalid == 32 only says ">= 32": the round logic below only distinguishes < 16 from >= 16
             }
             const int nr = nvalid < LRT_KBUF ? nvalid : LRT_KBUF;   // slots of this round
             G8Slot sl;

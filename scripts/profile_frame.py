@@ -12,7 +12,7 @@ ap.add_argument("--gaussians", type=int, default=2_000_000)
 ap.add_argument("--frames", type=int, default=3)
 ap.add_argument("--stats", action="store_true")
 ap.add_argument("--ab", action="store_true", help="time every combination of the tuning options")
-ap.add_argument("--fwd-kernel", type=int, default=1)
+ap.add_argument("--fwd-kernel", type=int, default=3)
 ap.add_argument("--flat", action="store_true", help="pass rays as (R,3): no 4x8 tiles")
 ap.add_argument("--no-vec", action="store_true")
 ap.add_argument("--cap", type=int, default=native.DEFAULT_HIT_CAP)
