@@ -184,6 +184,56 @@ __global__ void __launch_bounds__(128) k_wf_shade(BvhView bvh, FwdArgs a, WfBufs
                 for (int o = 16; o; o >>= 1) below += __shfl_xor_sync(FULL, below, o);
                 int pos = below;
                 unsigned long long best = LRT_KEY_EMPTY;
+                // Fast path: candidates are stored in ascending original depth, and re-testing from a point on
+                // the same ray preserves that order except between near-ties. So append the valid re-tested keys
+                // in bin order (ballot compaction) and only verify that they came out sorted; the general
+                // sort + bitonic-merge path below runs only if that check fails.
+                int have = 0;
+                bool sorted_ok = true;
+                const int pos0 = pos;
+                for (;;) {
+                    unsigned long long nk = LRT_KEY_EMPTY;
+                    const int idx = pos + lane;
+                    if (idx < n) {
+                        const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
+                        float t; int g2;
+                        if (quad_hit(bvh.rec, __ldg(bvh.iperm + g), rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                    }
+                    const unsigned vm = __ballot_sync(FULL, nk != LRT_KEY_EMPTY);
+                    const int want = lane - have;                                   // lane takes the want-th valid key of this window
+                    const int src = (want >= 0 && want < __popc(vm)) ? (int)__fns(vm, 0, want + 1) : -1;
+                    const unsigned long long got = __shfl_sync(FULL, nk, src < 0 ? 0 : src);
+                    if (src >= 0) best = got;
+                    have = min(32, have + __popc(vm));
+                    pos += 32;
+                    if (pos >= n || have >= 32) break;
+                    if (have >= LRT_KBUF) {
+                        const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
+                        const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
+                        const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
+                        if (t_next - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) break;
+                    }
+                }
+                {
+                    const unsigned long long prev = __shfl_up_sync(FULL, best, 1);
+                    const bool bad = lane > 0 && lane < have && prev > best;
+                    sorted_ok = __ballot_sync(FULL, bad) == 0;
+                    // the scan may have stopped at 32 collected keys with candidates left: then the 16th must still be
+                    // safely in front of the first unexamined candidate
+                    if (sorted_ok && pos < n) {
+                        const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
+                        const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
+                        const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
+                        if (!(have >= LRT_KBUF && t_next - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16))) sorted_ok = false;
+                    }
+                    if (sorted_ok && have >= 32) {                                  // valid keys beyond the 32nd were dropped: they must
+                        const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1), k32 = __shfl_sync(FULL, best, 31);   // lie safely behind the 16th
+                        const float t16 = __uint_as_float((unsigned)(k16 >> 32)), t32 = __uint_as_float((unsigned)(k32 >> 32));
+                        if (!(t32 - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16 + q.base))) sorted_ok = false;
+                    }
+                }
+                if (!sorted_ok) {                                                   // general path (near-ties re-ordered by re-basing)
+                pos = pos0; best = LRT_KEY_EMPTY;
                 for (;;) {
                     unsigned long long nk = LRT_KEY_EMPTY;
                     const int idx = pos + lane;
@@ -203,6 +253,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(BvhView bvh, FwdArgs a, WfBufs
                         const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
                         if (t_next - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) break;   // nothing further can rank in the first 16
                     }
+                }
                 }
                 slot_key = best;
                 nvalid = __popc(__ballot_sync(FULL, best != LRT_KEY_EMPTY));
