@@ -95,13 +95,16 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
                  float* dL_drots, int flags, void* stream);
 
 /* Tuning knobs; none of them changes results.
- *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill (default)
+ *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill, 2 = 8 lanes per ray,
+ *                           3 = breadth-first wavefront + warp-per-ray compositing (default)
  *   LRT_OPT_RAY_GRID_WIDTH  W > 0: the R rays of the next calls are a row-major (R / W, W) range image
  *                           (the (H, W, 3) tensors of the reference API); lets a warp take a 4 x 8 tile of
  *                           neighbouring rays. 0 = no structure known (default).
  *   LRT_OPT_VECTOR_ATOMICS  backward: 128-bit vector reductions where alignment allows (default 1)
+ *   LRT_OPT_BACKWARD_KERNEL 0 = one thread per ray replays its hit list, 1 = one warp per ray, one hit per lane (default)
  *   LRT_OPT_MORTON_BITS     63 = 21 bits/axis on cubic cells (default), 30 = 10 bits/axis per-axis extent (next lrt_build) */
-enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4 };
+enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,
+                  LRT_OPT_BACKWARD_KERNEL = 5 };
 int lrt_set_option(lrt_ctx* ctx, int option, int value);
 
 /* Introspection for tests / benchmarks (host pointers). */

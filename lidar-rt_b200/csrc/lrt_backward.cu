@@ -268,6 +268,90 @@ __global__ void __launch_bounds__(128) k_backward_list(BwArgs a)
     }
 }
 
+// One WARP per ray: the ray's recorded hits are processed 32 at a time, one hit per lane. What a hit needs
+// from its predecessors — transmittance T_k and the running sums of w c, w n, w depth — comes from warp
+// scans (a product scan of (1 - alpha) and seven sum scans), after which every lane runs the same per-hit
+// VJP code as the serial replay. The scans associate differently from the serial loop (ulp-level), which
+// is below the float-atomic reordering noise the gradients carry anyway.
+__global__ void __launch_bounds__(128) k_backward_warp(BwArgs a)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < a.R; r += warps_per_grid) {
+        const int cnt = a.hit_cnt[r];
+        if (cnt <= 0 || cnt > a.cap) continue;              // overflowed rays are handled by k_backward_trace
+        const float o[3] = {a.ray_o[(size_t)r * a.ray_o_stride], a.ray_o[(size_t)r * a.ray_o_stride + 1], a.ray_o[(size_t)r * a.ray_o_stride + 2]};
+        const float d[3] = {a.ray_d[3 * (size_t)r], a.ray_d[3 * (size_t)r + 1], a.ray_d[3 * (size_t)r + 2]};
+        const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        const float dirn[3] = {d[0] / dl, d[1] / dl, d[2] / dl};
+        const float bg[3] = {a.bg[0], a.bg[1], a.bg[2]};
+        RayState base;
+        ray_state_init(base, r, a.fwd_out, a.dL);
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int k = k0 + lane;
+            const bool active = k < cnt;
+            int g = 0; float dpt = 0.f;
+            float alpha = 0.f, wc[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
+            if (active) {
+                g = a.hit_gidx[(size_t)k * a.R + r];
+                dpt = a.hit_t[(size_t)k * a.R + r];
+                // pass 1: alpha, colour and normal of this hit (same arithmetic as hit_backward)
+                const float mu_[3] = {ld_f(a.means + 3 * (size_t)g), ld_f(a.means + 3 * (size_t)g + 1), ld_f(a.means + 3 * (size_t)g + 2)};
+                const float2 sc2 = __ldg(reinterpret_cast<const float2*>(a.scales + 2 * (size_t)g));
+                const float4 q4 = __ldg(reinterpret_cast<const float4*>(a.rots + 4 * (size_t)g));
+                const float sc_[2] = {sc2.x, sc2.y};
+                const float q_[4] = {q4.x, q4.y, q4.z, q4.w};
+                Derived s;
+                derive_surfel(mu_, sc_, q_, ld_f(a.opac + g), a.mod, s);
+                const float rr0 = (o[0] + dpt * d[0]) - s.mu[0], rr1 = (o[1] + dpt * d[1]) - s.mu[1], rr2 = (o[2] + dpt * d[2]) - s.mu[2];
+                const float u = s.Lu[0] * rr0 + s.Lu[1] * rr1 + s.Lu[2] * rr2;
+                const float v = s.Lv[0] * rr0 + s.Lv[1] * rr1 + s.Lv[2] * rr2;
+                alpha = fminf(LRT_ALPHA_MAX, s.op * expf(-0.5f * (u * u + v * v)));
+                if ((a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)) {
+                    sh_colour_stream(a.D, dirn, a.shs + (size_t)g * a.M * 3, wc);
+                } else {
+                    float sh[48]; bool cl;
+                    load_sh_bw(a.shs, g, a.M, (a.D + 1) * (a.D + 1), sh);
+                    sh_colour<false>(a.D, dirn, sh, wc, cl, nullptr);
+                }
+                nrm[0] = s.n[0]; nrm[1] = s.n[1]; nrm[2] = s.n[2];
+            }
+            // transmittance before each hit: exclusive product scan of (1 - alpha)
+            float om = active ? 1.0f - alpha : 1.0f, pr = om;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) { const float t = __shfl_up_sync(FULL, pr, sft); if (lane >= sft) pr *= t; }
+            float excl = __shfl_up_sync(FULL, pr, 1); if (lane == 0) excl = 1.0f;
+            const float T = base.T * excl;
+            const float w = alpha * T;
+            // exclusive sums of w c, w n, w depth
+            float v7[7] = {w * wc[0], w * wc[1], w * wc[2], w * nrm[0], w * nrm[1], w * nrm[2], w * dpt};
+            float ex7[7], tot7[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                float x = v7[j];
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) { const float t = __shfl_up_sync(FULL, x, sft); if (lane >= sft) x += t; }
+                tot7[j] = __shfl_sync(FULL, x, 31);
+                ex7[j] = x - v7[j];
+            }
+            if (active) {
+                RayState st = base;
+                st.T = T;
+                st.C[0] = base.C[0] + ex7[0]; st.C[1] = base.C[1] + ex7[1]; st.C[2] = base.C[2] + ex7[2];
+                st.N[0] = base.N[0] + ex7[3]; st.N[1] = base.N[1] + ex7[4]; st.N[2] = base.N[2] + ex7[5];
+                st.Dp = base.Dp + ex7[6];
+                hit_backward<false>(g, dpt, o, d, dirn, a.means, a.scales, a.rots, a.opac, a.shs, a.D, a.M, a.mod, bg, a.flags, st, a.go);
+            }
+            // carry to the next 32 hits
+            base.T *= __shfl_sync(FULL, pr, 31);
+            base.C[0] += tot7[0]; base.C[1] += tot7[1]; base.C[2] += tot7[2];
+            base.N[0] += tot7[3]; base.N[1] += tot7[4]; base.N[2] += tot7[5];
+            base.Dp += tot7[6];
+        }
+    }
+}
+
 // only_overflow: process just the rays whose forward list overflowed
 __global__ void __launch_bounds__(128) k_backward_trace(BvhView bvh, BwArgs a, int only_overflow)
 {
@@ -347,7 +431,16 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
     const int TB = 128, GB = (R + TB - 1) / TB;
     const bool can_trace = ctx->built && ctx->P == P && ctx->scale_modifier == mod;
     if (have_lists) {
-        k_backward_list<<<GB, TB, 0, s>>>(a);
+        if (ctx->opt_backward_kernel == 1) {
+            if (ctx->num_sms == 0) {
+                int sms = 0;
+                LRT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+                ctx->num_sms = sms > 0 ? sms : 148;
+            }
+            k_backward_warp<<<min((R + 3) / 4, ctx->num_sms * 16), TB, 0, s>>>(a);
+        } else {
+            k_backward_list<<<GB, TB, 0, s>>>(a);
+        }
         ctx->launches += 1;
         // Rays whose list overflowed need the structure that produced them. The caller (host
         // wrapper) guarantees it is current; without one they cannot be differentiated.

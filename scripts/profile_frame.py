@@ -17,6 +17,7 @@ ap.add_argument("--flat", action="store_true", help="pass rays as (R,3): no 4x8 
 ap.add_argument("--no-vec", action="store_true")
 ap.add_argument("--cap", type=int, default=native.DEFAULT_HIT_CAP)
 ap.add_argument("--morton", type=int, default=63)
+ap.add_argument("--bwd-kernel", type=int, default=1)
 a = ap.parse_args()
 BG = np.array([0, 0, 1], np.float32)
 cu = lambda x: torch.as_tensor(np.ascontiguousarray(x), device="cuda")
@@ -36,6 +37,7 @@ bg = cu(BG)
 def run(fwd_kernel, flat, vec, cap, label, verbose=True, morton=None):
     ctx.set_option(native.OPT_MORTON_BITS, morton or a.morton)
     ctx.set_option(native.OPT_FORWARD_KERNEL, fwd_kernel)
+    ctx.set_option(native.OPT_BACKWARD_KERNEL, a.bwd_kernel)
     ctx.set_option(native.OPT_VECTOR_ATOMICS, int(vec))
     tb, tf, tw = [], [], []
     for f, (ro, rd, g) in enumerate(frames):
@@ -74,4 +76,4 @@ if a.ab:
     run(2, False, True, 128, "fwd_kernel=2 tiles=4x8 morton=30", morton=30)
     run(2, True, True, 128, "fwd_kernel=2 tiles=no")
 else:
-    run(a.fwd_kernel, a.flat, not a.no_vec, a.cap, f"fwd_kernel={a.fwd_kernel} tiles={'no' if a.flat else '4x8'} vec={int(not a.no_vec)} cap={a.cap} morton={a.morton}")
+    run(a.fwd_kernel, a.flat, not a.no_vec, a.cap, f"fwd_kernel={a.fwd_kernel} tiles={'no' if a.flat else '4x8'} vec={int(not a.no_vec)} cap={a.cap} morton={a.morton} bwd_kernel={a.bwd_kernel}")

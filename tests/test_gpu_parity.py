@@ -164,6 +164,22 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
     assert_close(res["accum_w"], run_cuda(ctx, o, d, as_dict(sc), 3)["accum_w"], 1e-5, 1e-5, "accum (atomic order)")
 
 
+def test_backward_kernels_agree(ctx):
+    """thread-per-ray list replay vs warp-per-ray scans: same gradients up to summation order."""
+    from lidar_rt_b200 import native
+    sc = syn.make_street_scene(60000, seed=13)
+    o, d = syn.ray_patch(32, 96, frame=3)
+    rng = np.random.default_rng(13)
+    dL = np.zeros((32 * 96, 9), np.float32); dL[:, :4] = rng.standard_normal((32 * 96, 4)); dL[:, 5:8] = 0.1 * rng.standard_normal((32 * 96, 3))
+    try:
+        ctx.set_option(native.OPT_BACKWARD_KERNEL, 0); a = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
+        ctx.set_option(native.OPT_BACKWARD_KERNEL, 1); b = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
+    finally:
+        ctx.set_option(native.OPT_BACKWARD_KERNEL, 1)
+    for k in ("means", "shs", "opac", "scales", "rots"):
+        grad_close(b[f"g_{k}"], a[f"g_{k}"], 2e-4, f"d_{k}")
+
+
 def test_refit_matches_rebuild(ctx):
     sc = syn.make_street_scene(30000, seed=9, n_actors=1, per_actor=2000)
     o, d = syn.ray_patch(16, 128)
