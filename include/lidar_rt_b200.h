@@ -101,7 +101,7 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
  *                           (the (H, W, 3) tensors of the reference API); lets a warp take a 4 x 8 tile of
  *                           neighbouring rays. 0 = no structure known (default).
  *   LRT_OPT_VECTOR_ATOMICS  backward: 128-bit vector reductions where alignment allows (default 1)
- *   LRT_OPT_BACKWARD_KERNEL 0 = one thread per ray replays its hit list, 1 = one warp per ray, one hit per lane (default)
+ *   LRT_OPT_BACKWARD_KERNEL 0 = one thread per ray replays its hit list (default), 1 = one warp per ray, one hit per lane
  *   LRT_OPT_MORTON_BITS     63 = 21 bits/axis on cubic cells (default), 30 = 10 bits/axis per-axis extent (next lrt_build) */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,
                   LRT_OPT_BACKWARD_KERNEL = 5 };

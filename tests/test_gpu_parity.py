@@ -175,7 +175,7 @@ def test_backward_kernels_agree(ctx):
         ctx.set_option(native.OPT_BACKWARD_KERNEL, 0); a = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
         ctx.set_option(native.OPT_BACKWARD_KERNEL, 1); b = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
     finally:
-        ctx.set_option(native.OPT_BACKWARD_KERNEL, 1)
+        ctx.set_option(native.OPT_BACKWARD_KERNEL, 0)
     for k in ("means", "shs", "opac", "scales", "rots"):
         grad_close(b[f"g_{k}"], a[f"g_{k}"], 2e-4, f"d_{k}")
 
