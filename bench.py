@@ -285,6 +285,8 @@ def run_b200(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     for i in range(Wm):
         step_kernels(i)
+    if world > 1:                                  # communicator set-up is not part of a sweep: warm the gather path once
+        gather_frames(torch.zeros((K, H, W, 9), device=dev), K * world, rank, world)
     barrier()
     sampler.start()
     launches0 = ctx.info().kernel_launches

@@ -129,7 +129,10 @@ __device__ __forceinline__ unsigned long long warp_sort32(unsigned long long k, 
 }
 
 // One warp per ray. smem: 4 warps x WF_HCAP keys.
-__global__ void __launch_bounds__(128) k_wf_shade(BvhView bvh, FwdArgs a, WfBufs w)
+#ifndef LRT_SHADE_MIN_BLOCKS
+#define LRT_SHADE_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView bvh, FwdArgs a, WfBufs w)
 {
     __shared__ unsigned long long s_keys[4][WF_HCAP];
     __shared__ float s_cw[4][WF_HCAP], s_cd[4][WF_HCAP];      // contributing hits of the current ray: weight, depth,
