@@ -6,8 +6,9 @@
 //
 // Pipeline (all on the caller's stream, no host sync):
 //   k_bounds   : min/max of the means                          read 12 B/Gaussian
-//   k_morton   : 30-bit Morton key of each mean + identity     read 12 B, write 8 B
-//   cub radix  : sort (key, index) pairs, 4 passes of 8 bits
+//   k_morton*  : space-filling-curve key of each mean + identity   read 12 B, write 8-12 B
+//                (32-bit cubic-cell keys by default; 30-bit and 63-bit Morton selectable)
+//   cub radix  : sort (key, index) pairs, 8 bits per pass
 //   k_records  : gather raw parameters through the permutation, derive the surfel frame,
 //                write the 64 B record in Morton order and the padded quad AABB into its
 //                level-0 node slot                              read 40 B, write 64 + 24 B
@@ -109,6 +110,48 @@ __global__ void __launch_bounds__(256) k_morton64(int P, const float* __restrict
         q[k] = (t == t) ? (unsigned long long)t : 0ull;
     }
     keys[i] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+    idx[i] = (unsigned)i;
+}
+
+// 32-bit keys with the bits dealt to the axes so that cells stay (nearly) cubic: starting from the scene box,
+// every key bit halves the currently longest cell edge (ties: x, y, z). A street scene (220 x 50 x 17 m) gets
+// 12/10/10-ish bits instead of 10/10/10 on stretched cells, at half the radix-sort passes of the 63-bit keys.
+__global__ void __launch_bounds__(256) k_morton32(int P, const float* __restrict__ means, const int* __restrict__ b,
+                                                  unsigned* __restrict__ keys, unsigned* __restrict__ idx)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float lo[3], ext[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { lo[k] = ord2f(b[k]); ext[k] = fmaxf(ord2f(b[3 + k]) - lo[k], 1e-20f); }
+    // the same plan for every thread (depends on the scene box only)
+    float cell[3] = {ext[0], ext[1], ext[2]};
+    int nb[3] = {0, 0, 0};
+    unsigned char plan[32];
+#pragma unroll
+    for (int bit = 0; bit < 32; bit++) {
+        int ax = 0;
+        if (cell[1] > cell[ax]) ax = 1;
+        if (cell[2] > cell[ax]) ax = 2;
+        plan[bit] = (unsigned char)ax; cell[ax] *= 0.5f; nb[ax]++;
+    }
+    unsigned q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float scale = (float)(1u << min(nb[k], 24));
+        float t = (means[3 * i + k] - lo[k]) / ext[k] * scale;
+        t = fminf(fmaxf(t, 0.0f), scale - 1.0f);
+        q[k] = (t == t) ? (unsigned)t : 0u;
+        if (nb[k] > 24) q[k] <<= (nb[k] - 24);
+    }
+    unsigned key = 0; int used[3] = {0, 0, 0};
+#pragma unroll
+    for (int bit = 0; bit < 32; bit++) {
+        const int ax = plan[bit];
+        used[ax]++;
+        key = (key << 1) | ((q[ax] >> (nb[ax] - used[ax])) & 1u);
+    }
+    keys[i] = key;
     idx[i] = (unsigned)i;
 }
 
@@ -221,7 +264,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
     const int TB = 256;
     if (!refit) {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->perm_b, sizeof(unsigned) * (size_t)P));
-        const bool wide = ctx->opt_morton_bits > 30;
+        const bool wide = ctx->opt_morton_bits > 32;
         const size_t ksz = wide ? sizeof(unsigned long long) : sizeof(unsigned);
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_a, ksz * (size_t)P));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_b, ksz * (size_t)P));
@@ -230,8 +273,9 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
         cub::DoubleBuffer<unsigned> dv((unsigned*)ctx->perm_b.p, (unsigned*)ctx->perm_a.p);
         cub::DoubleBuffer<unsigned> dk32((unsigned*)ctx->keys_a.p, (unsigned*)ctx->keys_b.p);
         cub::DoubleBuffer<unsigned long long> dk64((unsigned long long*)ctx->keys_a.p, (unsigned long long*)ctx->keys_b.p);
+        const int bits32 = ctx->opt_morton_bits == 32 ? 32 : 30;
         if (wide) { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk64, dv, P, 0, 63, s)); }
-        else { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk32, dv, P, 0, 30, s)); }
+        else { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk32, dv, P, 0, bits32, s)); }
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sort_tmp, tmp_bytes));
         k_bounds_init<<<1, 32, 0, s>>>((int*)ctx->bounds.p);
         const int gb = min((P + TB - 1) / TB, 148 * 8);
@@ -241,9 +285,13 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
                                                          (unsigned*)ctx->perm_b.p);
             LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk64, dv, P, 0, 63, s));
         } else {
-            k_morton<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
-                                                       (unsigned*)ctx->perm_b.p);
-            LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk32, dv, P, 0, 30, s));
+            if (bits32 == 32)
+                k_morton32<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
+                                                             (unsigned*)ctx->perm_b.p);
+            else
+                k_morton<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
+                                                           (unsigned*)ctx->perm_b.p);
+            LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk32, dv, P, 0, bits32, s));
         }
         ctx->launches += 3 + 2 + (wide ? 8 : 4);     // bounds_init, bounds, morton + radix sort (histogram, scan, one onesweep launch per 8-bit digit)
         if (dv.Current() != (unsigned*)ctx->perm_a.p) {          // keep the permutation in perm_a

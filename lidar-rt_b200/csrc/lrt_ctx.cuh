@@ -30,7 +30,7 @@ struct lrt_ctx {
     int opt_ray_grid_w = 0;       // > 0: rays are a row-major range image of this width (enables 4 x 8 warp tiles)
     int opt_backward_kernel = 0;  // 0: one thread per ray replays its hit list (default, measured faster), 1: one warp per ray, one hit per lane (scans)
     int opt_vector_atomics = 1;   // backward: red.global.add.v4.f32 where alignment allows
-    int opt_morton_bits = 63;     // 63: 21 bits/axis on cubic cells (default); 30: 10 bits/axis, per-axis extent
+    int opt_morton_bits = 32;     // 32: 32-bit cubic-cell keys (default); 63: 21 bits/axis on cubic cells; 30: 10 bits/axis, per-axis extent
     int fwd_blocks_per_sm = 0, g8_blocks_per_sm = 0, num_sms = 0;
     long long builds = 0, refits = 0;
     int launches = 0;

@@ -128,19 +128,16 @@ __device__ __forceinline__ unsigned long long warp_sort32(unsigned long long k, 
     return k;
 }
 
-// One warp per ray. smem: 4 warps x WF_HCAP keys.
+// One warp per ray. smem: 4 warps x WF_HCAP keys (16 KB).
 #ifndef LRT_SHADE_MIN_BLOCKS
-#define LRT_SHADE_MIN_BLOCKS 3
+#define LRT_SHADE_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView bvh, FwdArgs a, WfBufs w)
 {
     __shared__ unsigned long long s_keys[4][WF_HCAP];
-    __shared__ float s_cw[4][WF_HCAP], s_cd[4][WF_HCAP];      // contributing hits of the current ray: weight, depth,
-    __shared__ int s_cg[4][WF_HCAP];                            // Gaussian id — committed only when the ray completes
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned long long* keys = s_keys[wib];
-    float* cw = s_cw[wib]; float* cd = s_cd[wib]; int* cg = s_cg[wib];
     const int S = num_slots(a.R, a.grid_w);
     for (int s = blockIdx.x * 4 + wib; s < S; s += gridDim.x * 4) {
         const int r = slot_to_ray(s, a.R, a.grid_w);
@@ -169,7 +166,6 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
         // ---- the reference's round loop (forward.cu:195-292)
         FwdRay q;
         fwd_ray_init(q, r, a);
-        bool fallback = false;
         for (int round = 0;; round++) {
             unsigned long long slot_key = LRT_KEY_EMPTY;           // lane i < 16 holds slot i of this round
             int nvalid;
@@ -283,24 +279,18 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
                 const float c0 = __shfl_sync(FULL, sl.c0, i), c1 = __shfl_sync(FULL, sl.c1, i), c2 = __shfl_sync(FULL, sl.c2, i);
                 q.C0 += wgt * c0; q.C1 += wgt * c1; q.C2 += wgt * c2;
                 q.Dp += wgt * dpt_i; q.W += wgt;
-                if (lane == i) { cw[q.ncontrib] = wgt; cd[q.ncontrib] = dpt_i; cg[q.ncontrib] = g_i; }   // ncontrib <= n <= WF_HCAP
+                if (lane == i) {                                     // the owner of the slot commits it (forward.cu:272 + hit list);
+                    atomicAdd(a.accum_w + g_i, wgt);                  // a ray is only handed to the fallback BEFORE its first round
+                    if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
+                        a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g_i;
+                        a.hit_t[(size_t)q.ncontrib * a.R + q.r] = dpt_i;
+                    }
+                }
                 q.ncontrib++;
                 q.T = q.testT;
             }
             if (terminated || q.testT < LRT_T_MIN || nvalid < LRT_KBUF) break;      // forward.cu:282-285
             q.base = (float)((double)q.dpt + LRT_STEP_EPS);                          // :288
-        }
-        __syncwarp(FULL);
-        if (fallback) {                                            // nothing of this ray has been committed yet
-            if (lane == 0) w.fb_list[atomicAdd(w.counts + 8, 1)] = r;
-            continue;
-        }
-        for (int k = lane; k < q.ncontrib; k += 32) {              // commit: accum weights (forward.cu:272) + hit list
-            atomicAdd(a.accum_w + cg[k], cw[k]);
-            if (a.hit_gidx != nullptr && k < a.cap) {
-                a.hit_gidx[(size_t)k * a.R + r] = cg[k];
-                a.hit_t[(size_t)k * a.R + r] = cd[k];
-            }
         }
         if (lane == 0) fwd_write(q, a, 0);
         __syncwarp(FULL);

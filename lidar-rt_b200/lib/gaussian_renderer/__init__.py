@@ -72,10 +72,11 @@ def raytracing(frame, gaussian_assets, sensor, background, args, scaling_modifie
         obj_rot.append(r1.expand(r2.shape[0], -1))
         rot_local.append(r2)
         all_shs.append(pc.get_features)
-    means3D = torch.cat(all_means, 0)
-    opacity = torch.cat(all_opac, 0)
-    scales = torch.cat(all_scales, 0)
-    shs = torch.cat(all_shs, 0)
+    _cat = lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs, 0)      # one asset: no 232 B/Gaussian copy (+ its backward)
+    means3D = _cat(all_means)
+    opacity = _cat(all_opac)
+    scales = _cat(all_scales)
+    shs = _cat(all_shs)
     dynamic = bool(getattr(args, "dynamic", False)) if args is not None else False
     if decomp == "background" or not dynamic:                      # reference :117-130
         rotations = rot_local[0] if len(rot_local) == 1 else torch.cat(rot_local, 0)

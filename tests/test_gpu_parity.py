@@ -147,7 +147,7 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
     try:
         for kernel in (0, 1, 2, 3):
             for tiled in (True, False):
-                for morton in (63, 30):
+                for morton in (32, 63, 30):
                     ctx.set_option(native.OPT_FORWARD_KERNEL, kernel)
                     ctx.set_option(native.OPT_MORTON_BITS, morton)
                     dd = d if tiled else d.reshape(-1, 3)
@@ -160,7 +160,7 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
                         for a_, b_ in zip(ref, key):
                             assert np.array_equal(a_, b_), f"kernel={kernel} tiled={tiled} morton={morton} differs"
     finally:
-        ctx.set_option(native.OPT_FORWARD_KERNEL, 3); ctx.set_option(native.OPT_MORTON_BITS, 63)
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 3); ctx.set_option(native.OPT_MORTON_BITS, 32)
     assert_close(res["accum_w"], run_cuda(ctx, o, d, as_dict(sc), 3)["accum_w"], 1e-5, 1e-5, "accum (atomic order)")
 
 
