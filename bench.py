@@ -319,9 +319,9 @@ def run_b200(args, rank, world, local_rank):
         evs[j][2].record(); ctx.backward(o_dev[i], d_dev[i], bg, means, scales, rots, opac, shs, D, f["out"], dL_dev[i], hits=f)
         evs[j][3].record()
     torch.cuda.synchronize()
-    t_build = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    t_fwd = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    t_bwd = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+    t_build = float(np.median([e[0].elapsed_time(e[1]) for e in evs]))       # medians: robust to an allocator hiccup
+    t_fwd = float(np.median([e[1].elapsed_time(e[2]) for e in evs]))
+    t_bwd = float(np.median([e[2].elapsed_time(e[3]) for e in evs]))
     f = ctx.forward(o_dev[Wm], d_dev[Wm], bg, means, scales, rots, opac, shs, D, want_slots=True)
     Ksum = float(f["slot_cnt"].sum().item()); Kcsum = float(f["hit_cnt"].sum().item())
     overflow = float((f["hit_cnt"] > f["cap"]).float().mean().item())
@@ -356,10 +356,28 @@ def run_b200(args, rank, world, local_rank):
     d2h = out_host.numel() * 4 + 4
     bg_cpu = torch.tensor(BG)
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = {}
+
+    def stage(i):
+        """H2D of step i's inputs from pinned memory on the copy stream (overlaps the previous step's kernels)."""
+        if i >= n_frames:
+            return
+        with torch.cuda.stream(copy_stream):
+            rd = d_pin[i].to(dev, non_blocking=True)
+            centre = o_pin[i].to(dev, non_blocking=True).reshape(3)
+            dL = dL_pin[i].to(dev, non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        staged[i] = (rd, centre, dL, ev)
+
     def step_e2e(i):
-        rd = d_pin[i].to(dev, non_blocking=True)
-        centre = o_pin[i].to(dev, non_blocking=True).reshape(3)
-        dL = dL_pin[i].to(dev, non_blocking=True)
+        if i not in staged:
+            stage(i)
+        rd, centre, dL, ev = staged.pop(i)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        for t_ in (rd, centre, dL):
+            t_.record_stream(torch.cuda.current_stream(dev))
+        stage(i + 1)                                              # next frame's copies run under this frame's kernels
         ro = centre[None, None].expand(H, W, 3)
         for p in asset.parameters():
             p.grad = None
@@ -372,6 +390,7 @@ def run_b200(args, rank, world, local_rank):
 
     for i in range(Wm):
         step_e2e(i)
+    staged.clear()                # every timed step's H2D copy happens inside the timed region
     barrier()
     t0 = time.perf_counter()
     for i in range(Wm, Wm + K):
@@ -383,7 +402,7 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_e2e = float(t.item())
     e2e = {"value": world * K * R / t_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": 1e3 * t_e2e / K, "api": "lib.gaussian_renderer.raytracing() + loss.backward()"}
+           "ms_per_step": 1e3 * t_e2e / K, "api": "lib.gaussian_renderer.raytracing() + loss.backward(); next frame's H2D prefetched on a copy stream"}
 
     # ---- 4. CPU baseline (rank 0, N = 1 only)
     cpu = None
