@@ -34,16 +34,16 @@ def cu(x):
     return torch.as_tensor(np.ascontiguousarray(x), device="cuda")
 
 
-def run_cuda(ctx, o, d, sc, D, dL=None, cap=64, use_lists=True, refit=False, flags=0):
+def run_cuda(ctx, o, d, sc, D, dL=None, cap=64, use_lists=True, refit=False, flags=0, mod=1.0):
     means, scales, rots, opac, shs = (cu(sc[k]) for k in ("means", "scales", "rots", "opac", "shs"))
-    ctx.build(means, scales, rots, opac, refit=refit)
+    ctx.build(means, scales, rots, opac, scale_modifier=mod, refit=refit)
     ro, rd, bg = cu(o), cu(d), cu(BG)
-    f = ctx.forward(ro, rd, bg, means, scales, rots, opac, shs, D, cap=cap, want_slots=True)
+    f = ctx.forward(ro, rd, bg, means, scales, rots, opac, shs, D, scale_modifier=mod, cap=cap, want_slots=True)
     res = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in f.items()}
     res["out"] = res["out"].reshape(-1, 9)
     if dL is not None:
         g = ctx.backward(ro, rd, bg, means, scales, rots, opac, shs, D, f["out"], cu(dL).reshape(f["out"].shape),
-                         hits=f if use_lists else None, flags=flags)
+                         hits=f if use_lists else None, flags=flags, scale_modifier=mod)
         res.update({f"g_{k}": v.cpu().numpy() for k, v in g.items()})
         res["g_opac"] = res["g_opac"].reshape(-1)
     return res
@@ -263,3 +263,87 @@ def test_autograd_surface_end_to_end():
     for t in (asset._xyz, asset._scaling, asset._rotation, asset._opacity, asset._features):
         assert t.grad is not None and torch.isfinite(t.grad).all() and t.grad.abs().sum() > 0
     assert pkg["means3D"].grad is None or torch.isfinite(pkg["means3D"].grad).all()
+
+
+# ------------------------------------------------------------------------------------------- edge cases
+def _vs_oracle(ctx, oracle32, o, d, sc, D, mod=1.0, with_grad=True, seed=0):
+    R = np.asarray(d).reshape(-1, 3).shape[0]
+    rng = np.random.default_rng(seed)
+    dL = np.zeros((R, 9), np.float32); dL[:, :4] = rng.standard_normal((R, 4))
+    res = run_cuda(ctx, o, d, sc, D, dL if with_grad else None, cap=128, mod=mod)
+    args = (o, d, BG, sc["means"], sc["scales"], sc["rots"], sc["opac"], sc["shs"], D)
+    f = oracle32.forward(*args, flags=ORC_BVH, cap=128, scale_modifier=mod)
+    assert hit_lists(res) == oracle_lists(f)
+    assert np.array_equal(res["slot_cnt"], f["slot_cnt"])
+    assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
+    if with_grad:
+        b = oracle32.backward(*args, f["out"], dL, flags=ORC_BVH, scale_modifier=mod)
+        for k in ("means", "shs", "opac", "scales", "rots"):
+            grad_close(res[f"g_{k}"], b[k], GRAD_REL, f"d_{k}")
+    return res
+
+
+def test_per_ray_origins_and_unnormalised_directions(ctx, oracle32):
+    """ray_o (R,3) with a different origin per ray (stride 3) and |d| != 1 (t is the ray parameter; SH uses d/|d|)."""
+    sc = as_dict(syn.make_street_scene(40000, seed=21))
+    _, d = syn.ray_patch(16, 64, frame=1)
+    d = d.reshape(-1, 3) * np.linspace(0.5, 2.0, 16 * 64, dtype=np.float32)[:, None]
+    rng = np.random.default_rng(21)
+    o = (rng.uniform(-1.5, 1.5, (16 * 64, 3)) * np.array([1.0, 1.0, 0.3])).astype(np.float32)
+    _vs_oracle(ctx, oracle32, o, d, sc, 2)
+
+
+def test_scale_modifier(ctx, oracle32):
+    sc = as_dict(syn.make_street_scene(30000, seed=22))
+    o, d = syn.ray_patch(16, 64)
+    a = _vs_oracle(ctx, oracle32, o, d, sc, 3, mod=1.4)
+    b = _vs_oracle(ctx, oracle32, o, d, sc, 3, mod=1.0, with_grad=False)
+    assert not np.array_equal(a["out"], b["out"])
+
+
+@pytest.mark.parametrize("P", [1, 7, 8, 9, 65, 513])
+def test_tiny_and_ragged_sizes(ctx, oracle32, P):
+    """Gaussian counts around the 8-wide node boundaries, single rays, empty ray sets."""
+    full = syn.make_street_scene(2000, seed=23, extent=10.0, scale_mult=0.3)
+    sc = {k: v[:P].copy() for k, v in as_dict(full).items()}
+    sc["means"][:, :2] *= 0.05; sc["means"][:, 2] = np.linspace(2.0, 6.0, P)       # stacked in front of +z
+    sc["rots"][:] = np.array([1.0, 0.02, -0.03, 0.0], np.float32)
+    o = np.zeros((1, 3), np.float32)
+    d = np.array([[0.0, 0.0, 1.0], [0.01, 0.0, 1.0], [0.3, 0.3, 1.0]], np.float32)
+    _vs_oracle(ctx, oracle32, o, d, sc, 3)
+    _vs_oracle(ctx, oracle32, o, d[:1], sc, 0)
+    means, scales, rots, opac, shs = (cu(sc[k]) for k in ("means", "scales", "rots", "opac", "shs"))
+    ctx.build(means, scales, rots, opac)
+    f = ctx.forward(cu(o), cu(d[:0]), cu(BG), means, scales, rots, opac, shs, 3)          # R = 0
+    assert f["out"].shape == (0, 9) and float(f["accum_w"].abs().sum()) == 0.0
+
+
+def test_invalid_opacities_are_never_hit(ctx, oracle32):
+    """opacity < 1/255 -> NaN proxy in the reference (log of < 1): such Gaussians exist but are never hit."""
+    sc = as_dict(syn.make_street_scene(20000, seed=24))
+    sc["opac"][::3] = 0.002
+    o, d = syn.ray_patch(16, 64)
+    res = _vs_oracle(ctx, oracle32, o, d, sc, 3)
+    assert np.all(res["accum_w"][::3] == 0) and np.all(res["g_opac"][::3] == 0)
+
+
+def test_error_behaviour(ctx):
+    from lidar_rt_b200 import native
+    sc = as_dict(syn.make_street_scene(1000, seed=25, extent=10.0))
+    means, scales, rots, opac, shs = (cu(sc[k]) for k in ("means", "scales", "rots", "opac", "shs"))
+    o, d = syn.ray_patch(4, 8)
+    fresh = native.Context()
+    with pytest.raises(native.LrtError, match="lrt_build"):                                 # no structure yet
+        fresh.forward(cu(o), cu(d), cu(BG), means, scales, rots, opac, shs, 3)
+    fresh.build(means, scales, rots, opac)
+    with pytest.raises(native.LrtError, match="P differs"):
+        fresh.forward(cu(o), cu(d), cu(BG), means[:500], scales[:500], rots[:500], opac[:500], shs[:500], 3)
+    with pytest.raises(native.LrtError, match="D <= 3"):
+        fresh.forward(cu(o), cu(d), cu(BG), means, scales, rots, opac, shs, 4)
+    with pytest.raises(native.LrtError, match="float32"):
+        fresh.forward(cu(o), cu(d).double(), cu(BG), means, scales, rots, opac, shs, 3)
+    with pytest.raises(native.LrtError, match="num_points, 3"):
+        fresh.build(means.reshape(-1), scales, rots, opac)
+    with pytest.raises(native.LrtError, match="refit"):
+        native.Context().build(means, scales, rots, opac, refit=True)
+    fresh.close()
