@@ -90,6 +90,7 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
     switch (option) {
     case LRT_OPT_FORWARD_KERNEL: if (value < 0 || value > 3) break; ctx->opt_forward_kernel = value; return LRT_OK;
     case LRT_OPT_RAY_GRID_WIDTH: if (value < 0) break; ctx->opt_ray_grid_w = value; return LRT_OK;
+    case LRT_OPT_WAVEFRONT_SHADE: if (value != 0 && value != 1) break; ctx->opt_wavefront_shade = value; return LRT_OK;
     case LRT_OPT_BACKWARD_KERNEL: if (value != 0 && value != 1) break; ctx->opt_backward_kernel = value; return LRT_OK;
     case LRT_OPT_MORTON_BITS: if (value != 30 && value != 32 && value != 63) break; ctx->opt_morton_bits = value; return LRT_OK;
     case LRT_OPT_VECTOR_ATOMICS: if (value != 0 && value != 1) break; ctx->opt_vector_atomics = value; return LRT_OK;

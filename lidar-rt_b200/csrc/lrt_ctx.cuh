@@ -28,6 +28,7 @@ struct lrt_ctx {
     // options (lrt_set_option)
     int opt_forward_kernel = 3;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray, 3: wavefront
     int opt_ray_grid_w = 0;       // > 0: rays are a row-major range image of this width (enables 4 x 8 warp tiles)
+    int opt_wavefront_shade = 1;  // wavefront compositing: 0 = one warp per ray (k_wf_shade), 1 = warp-sort + one thread per ray
     int opt_backward_kernel = 0;  // 0: one thread per ray replays its hit list (default, measured faster), 1: one warp per ray, one hit per lane (scans)
     int opt_vector_atomics = 1;   // backward: red.global.add.v4.f32 where alignment allows
     int opt_morton_bits = 32;     // 32: 32-bit cubic-cell keys (default); 63: 21 bits/axis on cubic cells; 30: 10 bits/axis, per-axis extent

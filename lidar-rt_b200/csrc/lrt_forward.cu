@@ -499,6 +499,11 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
     if (!ctx->built) { ctx->set_error("lrt_forward: no acceleration structure (call lrt_build first)"); return LRT_ERR_STATE; }
     if (P != ctx->P) { ctx->set_error("lrt_forward: P differs from the built structure"); return LRT_ERR_STATE; }
     if (mod != ctx->scale_modifier) { ctx->set_error("lrt_forward: scale_modifier differs from the built structure"); return LRT_ERR_STATE; }
+    if (R == 0 && accum_w) {                                   // empty ray set: only the per-Gaussian weights exist
+        LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        LRT_CUDA_TRY(ctx, cudaMemsetAsync(accum_w, 0, sizeof(float) * (size_t)P, s));
+        return LRT_OK;
+    }
     if (R < 0 || !ray_d || !ray_o || !bg || !shs || !out || !accum_w) { ctx->set_error("lrt_forward: null argument"); return LRT_ERR_INVALID; }
     if (ray_o_stride != 0 && ray_o_stride != 3) { ctx->set_error("lrt_forward: ray_o_stride must be 0 or 3"); return LRT_ERR_INVALID; }
     if (D < 0 || D > 3 || M < (D + 1) * (D + 1)) { ctx->set_error("lrt_forward: need 0 <= D <= 3 and M >= (D+1)^2"); return LRT_ERR_INVALID; }
@@ -549,7 +554,13 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             in = bufs[flip]; in_count = w.counts + (level - 1); flip ^= 1;
         }
         k_wf_leaf<<<G, 256, 0, s>>>(bv, a, w, in, in_count);
-        k_wf_shade<<<min((S + 3) / 4, ctx->num_sms * 8), 128, 0, s>>>(bv, a, w);
+        if (ctx->opt_wavefront_shade == 0) {
+            k_wf_shade<<<min((S + 3) / 4, ctx->num_sms * 8), 128, 0, s>>>(bv, a, w);
+        } else {
+            k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w);
+            k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
+            ctx->launches += 1;
+        }
         k_wf_fallback<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
         ctx->launches += 3 + bv.levels;
     } else if (ctx->opt_forward_kernel == 2) {

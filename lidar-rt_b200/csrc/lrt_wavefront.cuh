@@ -297,6 +297,90 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
     }
 }
 
+// ---- split compositing (default): k_wf_sort (one warp per ray: bitonic sort of the bin, written back) followed by
+// k_wf_composite (one THREAD per ray). With traversal gone, what is left per ray is a walk over a short sorted
+// candidate list — 16 lanes of a warp shading while 32 replicate the fold (k_wf_shade) costs ~3x the instructions
+// of simply letting each lane walk its own ray's list.
+__global__ void __launch_bounds__(128) k_wf_sort(FwdArgs a, WfBufs w)
+{
+    __shared__ unsigned long long s_keys[4][WF_HCAP];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned long long* keys = s_keys[wib];
+    for (int r = blockIdx.x * 4 + wib; r < a.R; r += gridDim.x * 4) {
+        const int hc = w.hit_count[r];
+        if ((hc & WF_TAINT) || hc > WF_HCAP || hc <= 1) continue;
+        const int n = hc;
+        unsigned long long* bin = w.bins + (size_t)r * WF_HCAP;
+        if (n <= 32) {                                             // one key per lane: register sort
+            unsigned long long k = lane < n ? bin[lane] : LRT_KEY_EMPTY;
+            k = warp_sort32(k, lane);
+            if (lane < n) bin[lane] = k;
+            continue;
+        }
+        int m = 64; while (m < n) m <<= 1;
+        for (int i = lane; i < m; i += 32) keys[i] = i < n ? bin[i] : LRT_KEY_EMPTY;
+        __syncwarp(FULL);
+        for (int size = 2; size <= m; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = lane; i < (m >> 1); i += 32) {
+                    const int lo = ((i / stride) * stride * 2) + (i % stride), hi = lo + stride;
+                    const unsigned long long x = keys[lo], y = keys[hi];
+                    const bool up = ((lo & size) == 0);
+                    if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+                }
+                __syncwarp(FULL);
+            }
+        }
+        for (int i = lane; i < n; i += 32) bin[i] = keys[i];
+        __syncwarp(FULL);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_wf_composite(BvhView bvh, FwdArgs a, WfBufs w)
+{
+    const int S = num_slots(a.R, a.grid_w);
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        const int r = slot_to_ray(s, a.R, a.grid_w);
+        if (r < 0) continue;
+        const int hc = w.hit_count[r];
+        if ((hc & WF_TAINT) || hc > WF_HCAP) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }
+        const int n = hc;
+        const unsigned long long* __restrict__ bin = w.bins + (size_t)r * WF_HCAP;       // sorted by (t from o, id)
+        FwdRay q;
+        fwd_ray_init(q, r, a);
+        int pos = 0;                                               // first candidate that can still matter
+        for (;;) {
+            // the round's k-buffer: exact re-test of the candidates from o' = o + base d, in bin order, kept as the
+            // (at most) 16 smallest (t', id); stop once the next candidate lies safely behind the 16th
+            RaySetup rs;
+            ray_setup(rs, q.o, q.d, q.base);
+            const float thr = q.base - 2.0f * (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
+            while (pos < n && __uint_as_float((unsigned)(bin[pos] >> 32)) < thr) pos++;
+            unsigned long long kb[LRT_KBUF];
+            int cnt = 0;
+            for (int i = pos; i < n; i++) {
+                const unsigned long long ck = bin[i];
+                if (cnt == LRT_KBUF) {
+                    const float t16 = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32)) + q.base;
+                    if (__uint_as_float((unsigned)(ck >> 32)) - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) break;
+                }
+                const int g = (int)(unsigned)(ck & 0xffffffffull);
+                float t; int g2;
+                if (!quad_hit(bvh.rec, __ldg(bvh.iperm + g), rs, t, g2)) continue;
+                const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                if (cnt == LRT_KBUF) { if (key >= kb[LRT_KBUF - 1]) continue; cnt--; }      // replaces the current 16th
+                int j = cnt;
+                while (j > 0 && kb[j - 1] > key) { kb[j] = kb[j - 1]; j--; }                 // near-sorted input: usually 0 shifts
+                kb[j] = key;
+                cnt++;
+            }
+            if (!fwd_shade_round(q, kb, cnt, bvh, a)) break;
+        }
+        fwd_write(q, a, 0);
+    }
+}
+
 // Rays the wavefront handed back (normally none or a handful): the per-ray code path, one thread per ray.
 __global__ void __launch_bounds__(128) k_wf_fallback(BvhView bvh, FwdArgs a, WfBufs w)
 {

@@ -18,6 +18,7 @@ ap.add_argument("--no-vec", action="store_true")
 ap.add_argument("--cap", type=int, default=native.DEFAULT_HIT_CAP)
 ap.add_argument("--morton", type=int, default=32)
 ap.add_argument("--bwd-kernel", type=int, default=0)
+ap.add_argument("--shade", type=int, default=1)
 a = ap.parse_args()
 BG = np.array([0, 0, 1], np.float32)
 cu = lambda x: torch.as_tensor(np.ascontiguousarray(x), device="cuda")
@@ -38,6 +39,7 @@ def run(fwd_kernel, flat, vec, cap, label, verbose=True, morton=None):
     ctx.set_option(native.OPT_MORTON_BITS, morton or a.morton)
     ctx.set_option(native.OPT_FORWARD_KERNEL, fwd_kernel)
     ctx.set_option(native.OPT_BACKWARD_KERNEL, a.bwd_kernel)
+    ctx.set_option(native.OPT_WAVEFRONT_SHADE, a.shade)
     ctx.set_option(native.OPT_VECTOR_ATOMICS, int(vec))
     tb, tf, tw = [], [], []
     for f, (ro, rd, g) in enumerate(frames):
@@ -76,4 +78,4 @@ if a.ab:
     run(2, False, True, 128, "fwd_kernel=2 tiles=4x8 morton=30", morton=30)
     run(2, True, True, 128, "fwd_kernel=2 tiles=no")
 else:
-    run(a.fwd_kernel, a.flat, not a.no_vec, a.cap, f"fwd_kernel={a.fwd_kernel} tiles={'no' if a.flat else '4x8'} vec={int(not a.no_vec)} cap={a.cap} morton={a.morton} bwd_kernel={a.bwd_kernel}")
+    run(a.fwd_kernel, a.flat, not a.no_vec, a.cap, f"fwd_kernel={a.fwd_kernel} tiles={'no' if a.flat else '4x8'} vec={int(not a.no_vec)} cap={a.cap} morton={a.morton} bwd_kernel={a.bwd_kernel} shade={a.shade}")

@@ -148,8 +148,10 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
         for kernel in (0, 1, 2, 3):
             for tiled in (True, False):
                 for morton in (32, 63, 30):
+                  for shade in ((0, 1) if kernel == 3 else (1,)):
                     ctx.set_option(native.OPT_FORWARD_KERNEL, kernel)
                     ctx.set_option(native.OPT_MORTON_BITS, morton)
+                    ctx.set_option(native.OPT_WAVEFRONT_SHADE, shade)
                     dd = d if tiled else d.reshape(-1, 3)
                     res = run_cuda(ctx, o, dd, as_dict(sc), 3, cap=128)
                     valid = np.arange(res["hit_gidx"].shape[0])[:, None] < res["hit_cnt"][None, :]
@@ -158,9 +160,9 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
                         ref = key
                     else:
                         for a_, b_ in zip(ref, key):
-                            assert np.array_equal(a_, b_), f"kernel={kernel} tiled={tiled} morton={morton} differs"
+                            assert np.array_equal(a_, b_), f"kernel={kernel} tiled={tiled} morton={morton} shade={shade} differs"
     finally:
-        ctx.set_option(native.OPT_FORWARD_KERNEL, 3); ctx.set_option(native.OPT_MORTON_BITS, 32)
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 3); ctx.set_option(native.OPT_MORTON_BITS, 32); ctx.set_option(native.OPT_WAVEFRONT_SHADE, 1)
     assert_close(res["accum_w"], run_cuda(ctx, o, d, as_dict(sc), 3)["accum_w"], 1e-5, 1e-5, "accum (atomic order)")
 
 
@@ -343,7 +345,7 @@ def test_error_behaviour(ctx):
     with pytest.raises(native.LrtError, match="float32"):
         fresh.forward(cu(o), cu(d).double(), cu(BG), means, scales, rots, opac, shs, 3)
     with pytest.raises(native.LrtError, match="num_points, 3"):
-        fresh.build(means.reshape(-1), scales, rots, opac)
+        fresh.build(means[None], scales, rots, opac)
     with pytest.raises(native.LrtError, match="refit"):
         native.Context().build(means, scales, rots, opac, refit=True)
     fresh.close()
