@@ -354,7 +354,7 @@ def run_b200(args, rank, world, local_rank):
     out_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()      # intensity, raydrop, depth
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     d2h = out_host.numel() * 4 + 4
-    bg_cpu = torch.tensor(BG)
+    bg_cpu = torch.tensor(BG, device=dev)            # train.py:104-106 creates the background on the device too
 
     copy_stream = torch.cuda.Stream(device=dev)
     staged = {}
