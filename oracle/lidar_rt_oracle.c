@@ -128,7 +128,8 @@ static void derive(const real* mu, const real* sc, const real* q, real op, real 
         for (int k = 0; k < 3; k++)
             o->v[c][k] = (lx[c] * (o->tu[k] * ax) + ly[c] * (o->tv[k] * ay)) + mu[k];
     for (int k = 0; k < 3; k++) {
-        const real e = R_FABS(o->tu[k]) * ax + R_FABS(o->tv[k]) * ay;
+        /* candidate-filter box: must contain the analytic quad (half-extent mod*s*f) AND the reference triangles (s*f) */
+        const real e = (R_FABS(o->tu[k]) * ax + R_FABS(o->tv[k]) * ay) * (mod > (real)1 ? mod : (real)1);
         const real pad = (real)1e-4 + (real)1e-5 * (R_FABS(mu[k]) + e);
         o->lo[k] = mu[k] - e - pad; o->hi[k] = mu[k] + e + pad;
     }

@@ -131,6 +131,17 @@ def test_config1_forward_vs_reference_and_bvh_filter_is_exact(oracle32):
     assert np.array_equal(brute["slot_cnt"], bvh["slot_cnt"])
 
 
+def test_bvh_filter_is_exact_with_scale_modifier_and_per_ray_origins(oracle32):
+    sc = syn.make_street_scene(8000, seed=31, extent=40.0)
+    _, d = syn.ray_patch(8, 32)
+    d = d.reshape(-1, 3)
+    o = np.random.default_rng(31).uniform(-1, 1, d.shape).astype(np.float32)
+    for mod in (0.7, 1.0, 1.4):
+        args = (o, d, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, 2)
+        a = oracle32.forward(*args, flags=0, scale_modifier=mod, cap=96); b = oracle32.forward(*args, flags=ORC_BVH, scale_modifier=mod, cap=96)
+        assert np.array_equal(a["out"], b["out"]) and np.array_equal(a["hit_list"], b["hit_list"]) and np.array_equal(a["slot_cnt"], b["slot_cnt"])
+
+
 @pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built (needs /root/reference)")
 def test_live_reference_random_scenes(oracle32):
     ref = Ref()
