@@ -36,7 +36,7 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
 {
     if (!ctx) return LRT_OK;
     cudaSetDevice(ctx->device);
-    DevBuf* bufs[] = {&ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
+    DevBuf* bufs[] = {&ctx->leafq, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
                       &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     delete ctx;

@@ -116,40 +116,49 @@ __global__ void __launch_bounds__(256) k_morton64(int P, const float* __restrict
 // 32-bit keys with the bits dealt to the axes so that cells stay (nearly) cubic: starting from the scene box,
 // every key bit halves the currently longest cell edge (ties: x, y, z). A street scene (220 x 50 x 17 m) gets
 // 12/10/10-ish bits instead of 10/10/10 on stretched cells, at half the radix-sort passes of the 63-bit keys.
-__global__ void __launch_bounds__(256) k_morton32(int P, const float* __restrict__ means, const int* __restrict__ b,
-                                                  unsigned* __restrict__ keys, unsigned* __restrict__ idx)
+// plan[bit] = (axis << 8) | shift : key bit (31 - bit) is bit `shift` of the quantised coordinate of `axis`.
+// Computed once per build by one thread from the scene box; plan[32..34] = bits per axis.
+__global__ void k_morton_plan(const int* __restrict__ b, int* __restrict__ plan)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    float lo[3], ext[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) { lo[k] = ord2f(b[k]); ext[k] = fmaxf(ord2f(b[3 + k]) - lo[k], 1e-20f); }
-    // the same plan for every thread (depends on the scene box only)
-    float cell[3] = {ext[0], ext[1], ext[2]};
-    int nb[3] = {0, 0, 0};
-    unsigned char plan[32];
-#pragma unroll
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float cell[3]; int nb[3] = {0, 0, 0}; int ax_of[32];
+    for (int k = 0; k < 3; k++) cell[k] = fmaxf(ord2f(b[3 + k]) - ord2f(b[k]), 1e-20f);
     for (int bit = 0; bit < 32; bit++) {
         int ax = 0;
         if (cell[1] > cell[ax]) ax = 1;
         if (cell[2] > cell[ax]) ax = 2;
-        plan[bit] = (unsigned char)ax; cell[ax] *= 0.5f; nb[ax]++;
+        ax_of[bit] = ax; cell[ax] *= 0.5f; nb[ax]++;
     }
+    int used[3] = {0, 0, 0};
+    for (int bit = 0; bit < 32; bit++) { const int ax = ax_of[bit]; used[ax]++; plan[bit] = (ax << 8) | (nb[ax] - used[ax]); }
+    for (int k = 0; k < 3; k++) plan[32 + k] = nb[k];
+}
+
+__global__ void __launch_bounds__(256) k_morton32(int P, const float* __restrict__ means, const int* __restrict__ b,
+                                                  const int* __restrict__ plan, unsigned* __restrict__ keys, unsigned* __restrict__ idx)
+{
+    __shared__ int s_plan[35];
+    if (threadIdx.x < 35) s_plan[threadIdx.x] = plan[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
     unsigned q[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const float scale = (float)(1u << min(nb[k], 24));
-        float t = (means[3 * i + k] - lo[k]) / ext[k] * scale;
+        const float lo = ord2f(b[k]), ext = fmaxf(ord2f(b[3 + k]) - lo, 1e-20f);
+        const int nbk = s_plan[32 + k];
+        const float scale = (float)(1u << min(nbk, 24));
+        float t = (means[3 * i + k] - lo) / ext * scale;
         t = fminf(fmaxf(t, 0.0f), scale - 1.0f);
         q[k] = (t == t) ? (unsigned)t : 0u;
-        if (nb[k] > 24) q[k] <<= (nb[k] - 24);
+        if (nbk > 24) q[k] <<= (nbk - 24);
     }
-    unsigned key = 0; int used[3] = {0, 0, 0};
+    unsigned key = 0;
 #pragma unroll
     for (int bit = 0; bit < 32; bit++) {
-        const int ax = plan[bit];
-        used[ax]++;
-        key = (key << 1) | ((q[ax] >> (nb[ax] - used[ax])) & 1u);
+        const int pl = s_plan[bit], ax = pl >> 8, sh = pl & 0xff;
+        const unsigned v = ax == 0 ? q[0] : (ax == 1 ? q[1] : q[2]);
+        key = (key << 1) | ((v >> sh) & 1u);
     }
     keys[i] = key;
     idx[i] = (unsigned)i;
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
                                                  const float* __restrict__ means, const float* __restrict__ scales,
                                                  const float* __restrict__ rots, const float* __restrict__ opac,
                                                  float mod, SurfelRec* __restrict__ rec, Node8* __restrict__ leaf,
-                                                 int* __restrict__ iperm)
+                                                 int* __restrict__ iperm, LeafQ* __restrict__ leafq)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P_pad) return;
@@ -208,6 +217,31 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
     const int c = i & 7;
     n.lox[c] = lo[0]; n.loy[c] = lo[1]; n.loz[c] = lo[2];
     n.hix[c] = hi[0]; n.hiy[c] = hi[1]; n.hiz[c] = hi[2];
+    // compact copy: bounds of the 8 surfels of this leaf (the 8 threads are consecutive lanes), then 8-bit boxes
+    const bool empty = lo[0] == FLT_MAX;
+    LeafQ& lq = leafq[i >> 3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float l = empty ? FLT_MAX : lo[k], h = empty ? -FLT_MAX : hi[k];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+        }
+        const bool none = l > h;                                     // all 8 slots empty
+        const float base = none ? FLT_MAX : l;
+        const float sc = none ? 0.0f : fmaxf((h - l) * (1.0f / 255.0f), 1e-30f);
+        int ql = 255, qh = 0;                                        // empty slot: inverted byte box (decodes inside the leaf box,
+        if (!empty) {                                                // its surfel fails the exact test)
+            ql = (int)floorf((lo[k] - base) / sc); ql = min(max(ql, 0), 255);
+            while (ql > 0 && fmaf((float)ql, sc, base) > lo[k]) ql--;
+            qh = (int)ceilf((hi[k] - base) / sc); qh = min(max(qh, 0), 255);
+            while (qh < 255 && fmaf((float)qh, sc, base) < hi[k]) qh++;
+            if (fmaf((float)qh, sc, base) < hi[k]) { ql = 0; qh = 255; }   // cannot happen with sc >= (h-l)/255; belt and braces
+        }
+        lq.qlo[k][c] = (unsigned char)ql; lq.qhi[k][c] = (unsigned char)qh;
+        if (c == 0) { lq.lo[k] = base; lq.sc[k] = sc; }
+    }
 }
 
 // level l >= 1: child c of node j is the union of the 8 boxes of node 8j+c one level below
@@ -261,6 +295,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->nodes, sizeof(Node8) * (size_t)total));
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->perm_a, sizeof(unsigned) * (size_t)P));
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->iperm, sizeof(int) * (size_t)P));
+    LRT_CUDA_TRY(ctx, ctx->reserve(ctx->leafq, sizeof(LeafQ) * (size_t)(P_pad / 8)));
     const int TB = 256;
     if (!refit) {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->perm_b, sizeof(unsigned) * (size_t)P));
@@ -268,7 +303,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
         const size_t ksz = wide ? sizeof(unsigned long long) : sizeof(unsigned);
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_a, ksz * (size_t)P));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->keys_b, ksz * (size_t)P));
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bounds, sizeof(int) * 8));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bounds, sizeof(int) * 64));
         size_t tmp_bytes = 0;
         cub::DoubleBuffer<unsigned> dv((unsigned*)ctx->perm_b.p, (unsigned*)ctx->perm_a.p);
         cub::DoubleBuffer<unsigned> dk32((unsigned*)ctx->keys_a.p, (unsigned*)ctx->keys_b.p);
@@ -285,9 +320,11 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
                                                          (unsigned*)ctx->perm_b.p);
             LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk64, dv, P, 0, 63, s));
         } else {
-            if (bits32 == 32)
-                k_morton32<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
-                                                             (unsigned*)ctx->perm_b.p);
+            if (bits32 == 32) {
+                k_morton_plan<<<1, 32, 0, s>>>((const int*)ctx->bounds.p, (int*)ctx->bounds.p + 8);
+                k_morton32<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (const int*)ctx->bounds.p + 8,
+                                                             (unsigned*)ctx->keys_a.p, (unsigned*)ctx->perm_b.p);
+            }
             else
                 k_morton<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
                                                            (unsigned*)ctx->perm_b.p);
@@ -301,7 +338,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
     }
     Node8* nodes = (Node8*)ctx->nodes.p;
     k_records<<<(P_pad + TB - 1) / TB, TB, 0, s>>>(P, P_pad, (const unsigned*)ctx->perm_a.p, means, scales, rots, opac,
-                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0], (int*)ctx->iperm.p);
+                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0], (int*)ctx->iperm.p, (LeafQ*)ctx->leafq.p);
     for (int l = 1; l < L; l++)
         k_fit<<<(cnt[l] * 8 + TB - 1) / TB, TB, 0, s>>>(cnt[l], cnt[l - 1], nodes + off[l - 1], nodes + off[l]);
     ctx->launches += L;

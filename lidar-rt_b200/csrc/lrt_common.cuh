@@ -46,10 +46,20 @@ struct __align__(16) SurfelRec { float4 r0, r1, r2, r3; };
 // 8-wide node: child boxes as SoA, 192 B = 12 x 128-bit loads.
 struct __align__(16) Node8 { float lox[8], loy[8], loz[8], hix[8], hiy[8], hiz[8]; };
 
+// Compact leaf for the wavefront's leaf kernel: the 8 surfel boxes of a level-0 node quantised to 8 bits per
+// coordinate inside the leaf's own box (80 B instead of 192 B; the kernel is L2-bandwidth bound). Conservative:
+// decoded lo <= true lo and decoded hi >= true hi, verified at build time with the decode expression itself.
+struct __align__(16) LeafQ {
+    float lo[3], sc[3];            // box = lo + q * sc
+    unsigned char qlo[3][8], qhi[3][8];
+    float pad[2];
+};
+
 struct BvhView {
     const SurfelRec* rec;         // (P_pad)
     const Node8* nodes;           // all levels, level 0 (children = surfels) first
     const int* iperm;             // (P) caller's Gaussian index -> position in Morton order
+    const LeafQ* leafq;           // (P_pad / 8) compact level-0 nodes
     int level_off[LRT_MAX_LEVELS];
     int levels;
     int P;

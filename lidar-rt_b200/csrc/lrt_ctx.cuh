@@ -23,6 +23,7 @@ struct lrt_ctx {
     long long n_nodes = 0;
     bool built = false;
     float scale_modifier = 1.0f;
+    DevBuf leafq;
     DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, iperm, sort_tmp, bounds, counter;
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb;   // wavefront forward workspace
     // options (lrt_set_option)
@@ -55,7 +56,7 @@ struct lrt_ctx {
     }
     size_t total_bytes() const
     {
-        return rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + iperm.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
+        return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + iperm.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap;
     }
     BvhView view() const
@@ -64,6 +65,7 @@ struct lrt_ctx {
         v.rec = (const SurfelRec*)rec.p;
         v.nodes = (const Node8*)nodes.p;
         v.iperm = (const int*)iperm.p;
+        v.leafq = (const LeafQ*)leafq.p;
         for (int i = 0; i < LRT_MAX_LEVELS; i++) v.level_off[i] = level_off[i];
         v.levels = levels;
         v.P = P;

@@ -87,6 +87,32 @@ __global__ void __launch_bounds__(256) k_wf_level(BvhView bvh, FwdArgs a, WfBufs
     }
 }
 
+// 8 slab tests against the byte-quantised boxes of a compact leaf.
+__device__ __forceinline__ unsigned leafq_eval(const LeafQ* __restrict__ lq, const RaySetup& r)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(lq);
+    const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
+    const float lox = __uint_as_float(w0.x), loy = __uint_as_float(w0.y), loz = __uint_as_float(w0.z);
+    const float scx = __uint_as_float(w0.w), scy = __uint_as_float(w1.x), scz = __uint_as_float(w1.y);
+    // bytes: qlo[3][8] = w1.z w1.w | w2.x w2.y | w2.z w2.w ; qhi[3][8] = w3.x w3.y | w3.z w3.w | w4.x w4.y
+    const unsigned ql[6] = {w1.z, w1.w, w2.x, w2.y, w2.z, w2.w}, qh[6] = {w3.x, w3.y, w3.z, w3.w, w4.x, w4.y};
+    unsigned m = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int wi = c >> 2, sh = 8 * (c & 3);
+        const float lx = fmaf((float)((ql[0 + wi] >> sh) & 0xffu), scx, lox), hx = fmaf((float)((qh[0 + wi] >> sh) & 0xffu), scx, lox);
+        const float ly = fmaf((float)((ql[2 + wi] >> sh) & 0xffu), scy, loy), hy = fmaf((float)((qh[2 + wi] >> sh) & 0xffu), scy, loy);
+        const float lz = fmaf((float)((ql[4 + wi] >> sh) & 0xffu), scz, loz), hz = fmaf((float)((qh[4 + wi] >> sh) & 0xffu), scz, loz);
+        const float x0 = fmaf(lx, r.ix, -r.px), x1 = fmaf(hx, r.ix, -r.px);
+        const float y0 = fmaf(ly, r.iy, -r.py), y1 = fmaf(hy, r.iy, -r.py);
+        const float z0 = fmaf(lz, r.iz, -r.pz), z1 = fmaf(hz, r.iz, -r.pz);
+        const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+        const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), LRT_TMAX));
+        if (tn <= tf) m |= 1u << c;
+    }
+    return m;
+}
+
 // One (ray, leaf) item per thread: the leaf's 8 surfel boxes, then the exact quad test (same arithmetic
 // as the per-ray kernels, bounds relaxed: the bin holds CANDIDATES), appended to the ray's bin.
 __global__ void __launch_bounds__(256) k_wf_leaf(BvhView bvh, FwdArgs a, WfBufs w, const uint2* __restrict__ in, const int* __restrict__ in_count)
@@ -98,8 +124,7 @@ __global__ void __launch_bounds__(256) k_wf_leaf(BvhView bvh, FwdArgs a, WfBufs 
         else ray = slot_to_ray(i, a.R, a.grid_w);
         if (ray < 0) continue;
         const RaySetup rs = w.rs[ray];
-        int nearest;
-        unsigned m = node_eval(bvh.nodes + bvh.level_off[0] + node, rs, LRT_TMAX, 0xffu, nearest);
+        unsigned m = leafq_eval(bvh.leafq + node, rs);
         while (m) {
             const int c = __ffs(m) - 1; m &= m - 1;
             float t; int g;
