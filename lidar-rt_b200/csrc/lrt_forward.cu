@@ -531,7 +531,11 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_a, sizeof(uint2) * (size_t)cap_items));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_b, sizeof(uint2) * (size_t)cap_items));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_hit_count, sizeof(int) * (size_t)R));
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_bins, sizeof(unsigned long long) * (size_t)R * WF_HCAP));
+        // bin capacity: 2048 candidates per ray while that stays under ~6 GB, never below what the shared-memory sort takes
+        int hcap = WF_HCAP_MAX;
+        while (hcap > WF_HCAP && (size_t)R * hcap * sizeof(unsigned long long) > ((size_t)6 << 30)) hcap >>= 1;
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_bins, sizeof(unsigned long long) * (size_t)R * hcap));
+        w.hcap = hcap;
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_fb, sizeof(int) * (size_t)R));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 16));
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 16, s));

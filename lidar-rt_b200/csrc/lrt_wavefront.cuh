@@ -19,7 +19,9 @@
 //      traced by the per-ray code path. Same results, just slower; normally a handful of rays.
 #pragma once
 
-#define WF_HCAP 512                 // candidate-bin capacity per ray (full, un-culled ray: ~40 candidates on street scenes)
+#define WF_HCAP 512                 // bins up to this size are sorted in shared memory (and are all k_wf_shade can take)
+#define WF_HCAP_MAX 2048            // bin capacity per ray in memory (a full, un-culled ray carries ~40 candidates on street scenes;
+                                    // a few grazing rays reach several hundred); beyond it the ray goes to the per-ray fallback
 #define WF_TAINT 0x40000000         // hit_count flag: work item or hit dropped -> fallback
 #define WF_WINDOW_MARGIN 1e-3f
 
@@ -29,7 +31,8 @@ struct WfBufs {
     int cap_items;
     int* counts;                    // [0..7] items per level, [8] fallback count
     int* hit_count;                 // (R) hits in bin | WF_TAINT
-    unsigned long long* bins;       // (R, WF_HCAP)
+    unsigned long long* bins;       // (R, hcap)
+    int hcap;                       // bin capacity (<= WF_HCAP_MAX)
     int* fb_list;                   // (R) fallback ray ids
 };
 
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(256) k_wf_leaf(BvhView bvh, FwdArgs a, WfBufs 
             float t; int g;
             if (quad_candidate(bvh.rec, (int)(node * 8u + c), rs, t, g)) {
                 const int pos = atomicAdd(w.hit_count + ray, 1) & (WF_TAINT - 1);
-                if (pos < WF_HCAP) w.bins[(size_t)ray * WF_HCAP + pos] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                if (pos < w.hcap) w.bins[(size_t)ray * w.hcap + pos] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
             }
         }
     }
@@ -168,14 +171,14 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
         const int r = slot_to_ray(s, a.R, a.grid_w);
         if (r < 0) continue;                                       // warp-uniform
         const int hc = w.hit_count[r];
-        if ((hc & WF_TAINT) || hc > WF_HCAP) {                     // not representable here: per-ray fallback
+        if ((hc & WF_TAINT) || hc > WF_HCAP || hc > w.hcap) {        // not representable here: per-ray fallback
             if (lane == 0) w.fb_list[atomicAdd(w.counts + 8, 1)] = r;
             continue;
         }
         const int n = hc;
         // ---- load + sort the bin (bitonic over the next power of two, in shared memory)
         int m = 32; while (m < n) m <<= 1;
-        for (int i = lane; i < m; i += 32) keys[i] = i < n ? w.bins[(size_t)r * WF_HCAP + i] : LRT_KEY_EMPTY;
+        for (int i = lane; i < m; i += 32) keys[i] = i < n ? w.bins[(size_t)r * w.hcap + i] : LRT_KEY_EMPTY;
         __syncwarp(FULL);
         for (int size = 2; size <= m; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -334,9 +337,9 @@ __global__ void __launch_bounds__(128) k_wf_sort(FwdArgs a, WfBufs w)
     unsigned long long* keys = s_keys[wib];
     for (int r = blockIdx.x * 4 + wib; r < a.R; r += gridDim.x * 4) {
         const int hc = w.hit_count[r];
-        if ((hc & WF_TAINT) || hc > WF_HCAP || hc <= 1) continue;
+        if ((hc & WF_TAINT) || hc > w.hcap || hc <= 1) continue;
         const int n = hc;
-        unsigned long long* bin = w.bins + (size_t)r * WF_HCAP;
+        unsigned long long* bin = w.bins + (size_t)r * w.hcap;
         if (n <= 32) {                                             // one key per lane: register sort
             unsigned long long k = lane < n ? bin[lane] : LRT_KEY_EMPTY;
             k = warp_sort32(k, lane);
@@ -344,20 +347,24 @@ __global__ void __launch_bounds__(128) k_wf_sort(FwdArgs a, WfBufs w)
             continue;
         }
         int m = 64; while (m < n) m <<= 1;
-        for (int i = lane; i < m; i += 32) keys[i] = i < n ? bin[i] : LRT_KEY_EMPTY;
+        // shared memory for the common sizes; the few bins beyond WF_HCAP are sorted in place in global memory
+        // (padding entries up to m live in the bin itself: m <= hcap because hcap is a power of two)
+        unsigned long long* buf = (m <= WF_HCAP) ? keys : bin;
+        if (buf == keys) { for (int i = lane; i < m; i += 32) keys[i] = i < n ? bin[i] : LRT_KEY_EMPTY; }
+        else { for (int i = n + lane; i < m; i += 32) bin[i] = LRT_KEY_EMPTY; }
         __syncwarp(FULL);
         for (int size = 2; size <= m; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 for (int i = lane; i < (m >> 1); i += 32) {
                     const int lo = ((i / stride) * stride * 2) + (i % stride), hi = lo + stride;
-                    const unsigned long long x = keys[lo], y = keys[hi];
+                    const unsigned long long x = buf[lo], y = buf[hi];
                     const bool up = ((lo & size) == 0);
-                    if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+                    if ((x > y) == up) { buf[lo] = y; buf[hi] = x; }
                 }
                 __syncwarp(FULL);
             }
         }
-        for (int i = lane; i < n; i += 32) bin[i] = keys[i];
+        if (buf == keys) { for (int i = lane; i < n; i += 32) bin[i] = keys[i]; }
         __syncwarp(FULL);
     }
 }
@@ -369,9 +376,9 @@ __global__ void __launch_bounds__(128) k_wf_composite(BvhView bvh, FwdArgs a, Wf
         const int r = slot_to_ray(s, a.R, a.grid_w);
         if (r < 0) continue;
         const int hc = w.hit_count[r];
-        if ((hc & WF_TAINT) || hc > WF_HCAP) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }
+        if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }
         const int n = hc;
-        const unsigned long long* __restrict__ bin = w.bins + (size_t)r * WF_HCAP;       // sorted by (t from o, id)
+        const unsigned long long* __restrict__ bin = w.bins + (size_t)r * w.hcap;       // sorted by (t from o, id)
         FwdRay q;
         fwd_ray_init(q, r, a);
         int pos = 0;                                               // first candidate that can still matter

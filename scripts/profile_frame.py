@@ -52,9 +52,11 @@ def run(fwd_kernel, flat, vec, cap, label, verbose=True, morton=None):
         e[3].record(); torch.cuda.synchronize()
         if f > 0 or a.frames == 1:
             tb.append(e[0].elapsed_time(e[1])); tf.append(e[1].elapsed_time(e[2])); tw.append(e[2].elapsed_time(e[3]))
+    import ctypes as _ct
+    _c = (_ct.c_int * 16)(); ctx.lib.lrt_debug_counters(ctx._h, _c)
     sl = res["slot_cnt"].cpu().numpy().astype(np.int64); hc = res["hit_cnt"].cpu().numpy()
     print(f"{label:34s} build {np.mean(tb):6.2f} ms  fwd {np.mean(tf):6.2f} ms  bwd {np.mean(tw):6.2f} ms  | slots/ray {np.mean(sl & 0xffff):.1f} "
-          f"contrib/ray {hc.mean():.1f} max {hc.max()} overflow {(hc > cap).mean():.4f}", flush=True)
+          f"contrib/ray {hc.mean():.1f} max {hc.max()} overflow {(hc > cap).mean():.4f} fallback rays (last frame) {_c[8]}", flush=True)
     if a.stats:
         import ctypes
         st = (ctypes.c_ulonglong * 16)(); ctx.lib.lrt_debug_stats(st, 1); st = np.array(list(st), np.float64) / (a.frames * hc.shape[0])
