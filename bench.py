@@ -333,18 +333,36 @@ def run_b200(args, rank, world, local_rank):
     B_build = P * (40 + 64 + 24) + 2 * P * 8 * 4 + (P / 7.0) * 192
     peak, peak_src = measured_peak()
     phases = {"build": (t_build, B_build), "forward": (t_fwd, B_fwd), "backward": (t_bwd, B_bwd)}
-    dom = max(phases, key=lambda k: phases[k][0])
+    # live per-kernel device times: CUDA events recorded by the library around every launch, on the launch stream
+    ctx.set_option(native.OPT_KERNEL_TIMING, 1)
+    ctx.kernel_times()
+    for i in range(Wm, Wm + K):
+        step_kernels(i)
+    kt = ctx.kernel_times()
+    ctx.set_option(native.OPT_KERNEL_TIMING, 0)
+    kernels = {k: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K} for k, v in kt.items()}
+    # algorithmic bytes of the kernels that own a SURVEY §8d term (per step): the backward replay owns B_bwd; the
+    # forward bytes are split: candidate geometry (K x 40 B) to the leaf kernel, rays + SH + outputs to the composite
+    kalg = {"k_backward_list": B_bwd, "k_wf_leaf": Ksum * 40, "k_wf_composite": R * (12 + 36) + Kcsum * (nsh + 8),
+            "k_records": P * (40 + 64 + 24 + 4 + 10), "radix_sort": 2 * P * 8 * 4}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else "forward"
+    dom_ms = kernels[dom]["ms_per_step"] if kernels else t_fwd
+    dom_bytes = kalg.get(dom, 0.0)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            tj = json.load(open(tpath))
+            traffic = tj.get("kernels", {}).get(dom, None)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": phases[dom][1] / (phases[dom][0] * 1e-3) / 1e9, "peak": peak,
-                "unit": "GB/s", "frac": phases[dom][1] / (phases[dom][0] * 1e-3) / 1e9 / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes": phases[dom][1], "ms": phases[dom][0],
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "ms": dom_ms,
+                "kernels": {k: dict(v, algorithmic_bytes=kalg.get(k), gbs=(kalg[k] / (v["ms_per_step"] * 1e-3) / 1e9 if k in kalg and v["ms_per_step"] > 0 else None))
+                            for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_per_step"])},
                 "phases": {k: {"ms": v[0], "algorithmic_bytes": v[1], "gbs": v[1] / (v[0] * 1e-3) / 1e9} for k, v in phases.items()},
+                "step_algorithmic_bytes": B_fwd + B_bwd + B_build,
                 "step_frac_of_peak": (B_fwd + B_bwd + B_build) / (ms_step * 1e-3) / 1e9 / peak,
                 "hits_per_ray_evaluated": Ksum / R, "hits_per_ray_contributing": Kcsum / R, "hit_list_overflow_frac": overflow}
 

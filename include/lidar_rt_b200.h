@@ -102,11 +102,12 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
  *                           neighbouring rays. 0 = no structure known (default).
  *   LRT_OPT_VECTOR_ATOMICS  backward: 128-bit vector reductions where alignment allows (default 1)
  *   LRT_OPT_BACKWARD_KERNEL 0 = one thread per ray replays its hit list (default), 1 = one warp per ray, one hit per lane
+ *   LRT_OPT_KERNEL_TIMING   1 = record CUDA events around every kernel launch (read with lrt_get_kernel_times)
  *   LRT_OPT_WAVEFRONT_SHADE wavefront compositing: 0 = one warp per ray, 1 = warp sort + one thread per ray (default)
  *   LRT_OPT_MORTON_BITS     32 = 32-bit keys, bits dealt to the axes so cells stay cubic (default); 63 = 21 bits/axis on
  *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build) */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,
-                  LRT_OPT_BACKWARD_KERNEL = 5, LRT_OPT_WAVEFRONT_SHADE = 6 };
+                  LRT_OPT_BACKWARD_KERNEL = 5, LRT_OPT_WAVEFRONT_SHADE = 6, LRT_OPT_KERNEL_TIMING = 7 };
 int lrt_set_option(lrt_ctx* ctx, int option, int value);
 
 /* Introspection for tests / benchmarks (host pointers). */
@@ -121,6 +122,9 @@ typedef struct lrt_info {
     int32_t kernel_launches;      /* kernels launched by this library since context creation */
 } lrt_info;
 int lrt_get_info(const lrt_ctx* ctx, lrt_info* out);
+/* Live per-kernel device times since the previous call (needs LRT_OPT_KERNEL_TIMING = 1); host pointers:
+ * names_out = cap x 32 chars, ms_out / count_out = cap entries. Returns the number of kernels reported. */
+int lrt_get_kernel_times(lrt_ctx* ctx, char* names_out, float* ms_out, int* count_out, int cap);
 /* development aid: work counters of the last forward (wavefront: [0..7] items per level, [8] fallback rays) */
 int lrt_debug_counters(const lrt_ctx* ctx, int* out);
 /* development counters (all zero unless the library was built with -DLRT_STATS); out = 16 host uint64 */

@@ -36,6 +36,8 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
 {
     if (!ctx) return LRT_OK;
     cudaSetDevice(ctx->device);
+    for (auto& t : ctx->spans) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     DevBuf* bufs[] = {&ctx->leafq, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
                       &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -90,6 +92,7 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
     switch (option) {
     case LRT_OPT_FORWARD_KERNEL: if (value < 0 || value > 3) break; ctx->opt_forward_kernel = value; return LRT_OK;
     case LRT_OPT_RAY_GRID_WIDTH: if (value < 0) break; ctx->opt_ray_grid_w = value; return LRT_OK;
+    case LRT_OPT_KERNEL_TIMING: if (value != 0 && value != 1) break; ctx->opt_kernel_timing = value; return LRT_OK;
     case LRT_OPT_WAVEFRONT_SHADE: if (value != 0 && value != 1) break; ctx->opt_wavefront_shade = value; return LRT_OK;
     case LRT_OPT_BACKWARD_KERNEL: if (value != 0 && value != 1) break; ctx->opt_backward_kernel = value; return LRT_OK;
     case LRT_OPT_MORTON_BITS: if (value != 30 && value != 32 && value != 63) break; ctx->opt_morton_bits = value; return LRT_OK;
@@ -112,6 +115,30 @@ int lrt_get_info(const lrt_ctx* ctx, lrt_info* out)
     out->builds = ctx->builds; out->refits = ctx->refits;
     out->kernel_launches = ctx->launches;
     return LRT_OK;
+}
+
+/* Live per-kernel device times (LRT_OPT_KERNEL_TIMING = 1): sums the CUDA-event spans recorded since the last call,
+ * per kernel name. Synchronises the events. names_out: `cap` slots of 32 chars; ms_out / count_out: `cap` entries.
+ * Returns the number of distinct kernels (<= cap) or a negative status. */
+int lrt_get_kernel_times(lrt_ctx* ctx, char* names_out, float* ms_out, int* count_out, int cap)
+{
+    if (!ctx || !names_out || !ms_out || !count_out || cap <= 0) return LRT_ERR_INVALID;
+    std::map<std::string, std::pair<double, int>> acc;
+    for (auto& t : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            auto& e = acc[t.name]; e.first += ms; e.second += 1;
+        }
+        ctx->event_pool.push_back(t.a); ctx->event_pool.push_back(t.b);
+    }
+    ctx->spans.clear();
+    int n = 0;
+    for (auto& kv : acc) {
+        if (n >= cap) break;
+        snprintf(names_out + 32 * n, 32, "%s", kv.first.c_str());
+        ms_out[n] = (float)kv.second.first; count_out[n] = kv.second.second; n++;
+    }
+    return n;
 }
 
 /* development aid: the context's 16 work counters of the last forward (wavefront: [0..7] items per level,

@@ -437,17 +437,17 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
                 LRT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
                 ctx->num_sms = sms > 0 ? sms : 148;
             }
-            k_backward_warp<<<min((R + 3) / 4, ctx->num_sms * 16), TB, 0, s>>>(a);
+            ctx->span_begin("k_backward_warp", s); k_backward_warp<<<min((R + 3) / 4, ctx->num_sms * 16), TB, 0, s>>>(a); ctx->span_end(s);
         } else {
-            k_backward_list<<<GB, TB, 0, s>>>(a);
+            ctx->span_begin("k_backward_list", s); k_backward_list<<<GB, TB, 0, s>>>(a); ctx->span_end(s);
         }
         ctx->launches += 1;
         // Rays whose list overflowed need the structure that produced them. The caller (host
         // wrapper) guarantees it is current; without one they cannot be differentiated.
-        if (can_trace) { k_backward_trace<<<GB, TB, 0, s>>>(ctx->view(), a, 1); ctx->launches += 1; }
+        if (can_trace) { ctx->span_begin("k_backward_trace", s); k_backward_trace<<<GB, TB, 0, s>>>(ctx->view(), a, 1); ctx->span_end(s); ctx->launches += 1; }
     } else {
         if (!can_trace) { ctx->set_error("lrt_backward: no hit lists given and no matching acceleration structure built"); return LRT_ERR_STATE; }
-        k_backward_trace<<<GB, TB, 0, s>>>(ctx->view(), a, 0);
+        ctx->span_begin("k_backward_trace", s); k_backward_trace<<<GB, TB, 0, s>>>(ctx->view(), a, 0); ctx->span_end(s);
         ctx->launches += 1;
     }
     LRT_CUDA_TRY(ctx, cudaGetLastError());

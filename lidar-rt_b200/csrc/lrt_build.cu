@@ -314,7 +314,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sort_tmp, tmp_bytes));
         k_bounds_init<<<1, 32, 0, s>>>((int*)ctx->bounds.p);
         const int gb = min((P + TB - 1) / TB, 148 * 8);
-        k_bounds<<<gb, TB, 0, s>>>(P, means, (int*)ctx->bounds.p);
+        ctx->span_begin("k_bounds", s); k_bounds<<<gb, TB, 0, s>>>(P, means, (int*)ctx->bounds.p); ctx->span_end(s);
         if (wide) {
             k_morton64<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned long long*)ctx->keys_a.p,
                                                          (unsigned*)ctx->perm_b.p);
@@ -328,7 +328,9 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
             else
                 k_morton<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
                                                            (unsigned*)ctx->perm_b.p);
+            ctx->span_begin("radix_sort", s);
             LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk32, dv, P, 0, bits32, s));
+            ctx->span_end(s);
         }
         ctx->launches += 3 + 2 + (wide ? 8 : 4);     // bounds_init, bounds, morton + radix sort (histogram, scan, one onesweep launch per 8-bit digit)
         if (dv.Current() != (unsigned*)ctx->perm_a.p) {          // keep the permutation in perm_a
@@ -337,10 +339,13 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
         }
     }
     Node8* nodes = (Node8*)ctx->nodes.p;
-    k_records<<<(P_pad + TB - 1) / TB, TB, 0, s>>>(P, P_pad, (const unsigned*)ctx->perm_a.p, means, scales, rots, opac,
-                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0], (int*)ctx->iperm.p, (LeafQ*)ctx->leafq.p);
-    for (int l = 1; l < L; l++)
+    ctx->span_begin("k_records", s); k_records<<<(P_pad + TB - 1) / TB, TB, 0, s>>>(P, P_pad, (const unsigned*)ctx->perm_a.p, means, scales, rots, opac,
+                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0], (int*)ctx->iperm.p, (LeafQ*)ctx->leafq.p); ctx->span_end(s);
+    for (int l = 1; l < L; l++) {
+        ctx->span_begin("k_fit", s);
         k_fit<<<(cnt[l] * 8 + TB - 1) / TB, TB, 0, s>>>(cnt[l], cnt[l - 1], nodes + off[l - 1], nodes + off[l]);
+        ctx->span_end(s);
+    }
     ctx->launches += L;
     LRT_CUDA_TRY(ctx, cudaGetLastError());
 

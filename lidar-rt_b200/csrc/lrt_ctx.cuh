@@ -4,6 +4,8 @@
 #pragma once
 
 #include <string>
+#include <vector>
+#include <map>
 #include <cstdio>
 #include "../../include/lidar_rt_b200.h"
 #include "lrt_common.cuh"
@@ -36,6 +38,31 @@ struct lrt_ctx {
     int fwd_blocks_per_sm = 0, g8_blocks_per_sm = 0, num_sms = 0;
     long long builds = 0, refits = 0;
     int launches = 0;
+
+    // optional live per-kernel timing (LRT_OPT_KERNEL_TIMING): CUDA events around every launch, on the launch stream
+    int opt_kernel_timing = 0;
+    struct TimedSpan { const char* name; cudaEvent_t a, b; };
+    std::vector<TimedSpan> spans;           // spans of the calls since the last lrt_get_kernel_times
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t take_event()
+    {
+        cudaEvent_t e = nullptr;
+        if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    void span_begin(const char* name, cudaStream_t s)
+    {
+        if (!opt_kernel_timing) return;
+        TimedSpan t; t.name = name; t.a = take_event(); t.b = take_event();
+        cudaEventRecord(t.a, s);
+        spans.push_back(t);
+    }
+    void span_end(cudaStream_t s)
+    {
+        if (!opt_kernel_timing || spans.empty()) return;
+        cudaEventRecord(spans.back().b, s);
+    }
 
     void set_error(const char* what, cudaError_t e)
     {

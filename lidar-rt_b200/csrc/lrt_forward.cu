@@ -521,7 +521,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
     const int TB = 128;
     const int S = num_slots(R, a.grid_w);
     if (ctx->opt_forward_kernel == 0) {
-        k_forward<<<(S + TB - 1) / TB, TB, 0, s>>>(ctx->view(), a);
+        ctx->span_begin("k_forward", s); k_forward<<<(S + TB - 1) / TB, TB, 0, s>>>(ctx->view(), a); ctx->span_end(s);
     } else if (ctx->opt_forward_kernel == 3) {
         // wavefront: level-by-level work lists, per-ray hit bins, warp-per-ray compositing
         WfBufs w;
@@ -549,23 +549,23 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         }
         const BvhView bv = ctx->view();
         const int G = ctx->num_sms * 8;                                 // grid-stride kernels: 8 blocks of 256 threads per SM
-        k_wf_setup<<<(R + 255) / 256, 256, 0, s>>>(a, w);
+        ctx->span_begin("k_wf_setup", s); k_wf_setup<<<(R + 255) / 256, 256, 0, s>>>(a, w); ctx->span_end(s);
         const uint2* in = nullptr; const int* in_count = nullptr;
         uint2* bufs[2] = {w.list_a, w.list_b};
         int flip = 0;
         for (int level = bv.levels - 1; level >= 1; level--) {
-            k_wf_level<<<G, 256, 0, s>>>(bv, a, w, level, in, in_count, bufs[flip], w.counts + (level - 1));
+            ctx->span_begin("k_wf_level", s); k_wf_level<<<G, 256, 0, s>>>(bv, a, w, level, in, in_count, bufs[flip], w.counts + (level - 1)); ctx->span_end(s);
             in = bufs[flip]; in_count = w.counts + (level - 1); flip ^= 1;
         }
-        k_wf_leaf<<<G, 256, 0, s>>>(bv, a, w, in, in_count);
+        ctx->span_begin("k_wf_leaf", s); k_wf_leaf<<<G, 256, 0, s>>>(bv, a, w, in, in_count); ctx->span_end(s);
         if (ctx->opt_wavefront_shade == 0) {
-            k_wf_shade<<<min((S + 3) / 4, ctx->num_sms * 8), 128, 0, s>>>(bv, a, w);
+            ctx->span_begin("k_wf_shade", s); k_wf_shade<<<min((S + 3) / 4, ctx->num_sms * 8), 128, 0, s>>>(bv, a, w); ctx->span_end(s);
         } else {
-            k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w);
-            k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
+            ctx->span_begin("k_wf_sort", s); k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w); ctx->span_end(s);
+            ctx->span_begin("k_wf_composite", s); k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w); ctx->span_end(s);
             ctx->launches += 1;
         }
-        k_wf_fallback<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
+        ctx->span_begin("k_wf_fallback", s); k_wf_fallback<<<ctx->num_sms, 128, 0, s>>>(bv, a, w); ctx->span_end(s);
         ctx->launches += 3 + bv.levels;
     } else if (ctx->opt_forward_kernel == 2) {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 4));
@@ -578,7 +578,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             ctx->g8_blocks_per_sm = nb > 0 ? nb : 1; ctx->num_sms = sms > 0 ? sms : 148;
         }
         const int grid = min(ctx->num_sms * ctx->g8_blocks_per_sm, (S + 15) / 16);      // 16 rays in flight per 128-thread block
-        k_forward_g8<<<grid, TB, 0, s>>>(ctx->view(), a);
+        ctx->span_begin("k_forward_g8", s); k_forward_g8<<<grid, TB, 0, s>>>(ctx->view(), a); ctx->span_end(s);
     } else {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 4));
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 4, s));
@@ -590,7 +590,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             ctx->fwd_blocks_per_sm = nb > 0 ? nb : 1; ctx->num_sms = sms > 0 ? sms : 148;
         }
         const int grid = min(ctx->num_sms * ctx->fwd_blocks_per_sm, (S + TB - 1) / TB);   // one resident wave, sized to the SM count
-        k_forward_persistent<<<grid, TB, 0, s>>>(ctx->view(), a);
+        ctx->span_begin("k_forward_persistent", s); k_forward_persistent<<<grid, TB, 0, s>>>(ctx->view(), a); ctx->span_end(s);
     }
     ctx->launches += 1;
     LRT_CUDA_TRY(ctx, cudaGetLastError());

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("LIDAR_RT_B200_LIB") or os.path.join(os.path.dirname(_
 LRT_FLAG_FIX_BG_GRAD = 1
 NUM_CHANNELS = 9
 DEFAULT_HIT_CAP = 128          # contributing hits recorded per ray for the backward replay (rays beyond it are re-traced)
-OPT_FORWARD_KERNEL, OPT_RAY_GRID_WIDTH, OPT_VECTOR_ATOMICS, OPT_MORTON_BITS, OPT_BACKWARD_KERNEL, OPT_WAVEFRONT_SHADE = 1, 2, 3, 4, 5, 6
+OPT_FORWARD_KERNEL, OPT_RAY_GRID_WIDTH, OPT_VECTOR_ATOMICS, OPT_MORTON_BITS, OPT_BACKWARD_KERNEL, OPT_WAVEFRONT_SHADE, OPT_KERNEL_TIMING = 1, 2, 3, 4, 5, 6, 7
 
 
 class LrtError(RuntimeError):
@@ -58,6 +58,8 @@ def load_library() -> ctypes.CDLL:
     lib.lrt_backward.argtypes = [c_void_p, c_int, fp, c_int, fp, fp, c_int, fp, fp, fp, fp, fp, c_int, c_int, c_float,
                                  fp, fp, ip, fp, ip, c_int, fp, fp, fp, fp, fp, c_int, c_void_p]
     lib.lrt_set_option.argtypes = [c_void_p, c_int, c_int]
+    lib.lrt_get_kernel_times.argtypes = [c_void_p, c_char_p, POINTER(c_float), POINTER(c_int), c_int]
+    lib.lrt_get_kernel_times.restype = c_int
     lib.lrt_get_info.argtypes = [c_void_p, POINTER(LrtInfo)]
     lib.lrt_get_permutation.argtypes = [c_void_p, c_void_p, c_void_p]
     for f in (lib.lrt_set_option, lib.lrt_ctx_create, lib.lrt_ctx_destroy, lib.lrt_build, lib.lrt_refit, lib.lrt_forward, lib.lrt_backward,
@@ -138,6 +140,17 @@ class Context:
 
     def set_option(self, option: int, value: int):
         self._check(self.lib.lrt_set_option(self._h, int(option), int(value)))
+
+    def kernel_times(self) -> dict:
+        """{kernel name: (total ms, launches)} of the CUDA-event spans recorded since the previous call
+        (set_option(OPT_KERNEL_TIMING, 1) first). Synchronises on the recorded events."""
+        cap = 32
+        names = ctypes.create_string_buffer(32 * cap)
+        ms = (c_float * cap)(); cnt = (c_int * cap)()
+        n = self.lib.lrt_get_kernel_times(self._h, names, ms, cnt, cap)
+        if n < 0:
+            raise LrtError("lrt_get_kernel_times failed")
+        return {names.raw[32 * i:32 * (i + 1)].split(b"\0")[0].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
     def info(self) -> LrtInfo:
         i = LrtInfo()

@@ -45,5 +45,23 @@ for e in prof.key_averages():
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
 print(f"GPU time per step: {tot/1e3:.3f} ms over {len(rows)} kernel kinds")
-for ct, n, k in rows[:28]:
+for ct, n, k in rows[:14]:
     print(f"{ct/1e3:8.3f} ms x{n:3d}  {k}")
+cpu = sorted(((e.self_cpu_time_total / 3.0, e.count // 3, e.key[:80]) for e in prof.key_averages() if e.self_cpu_time_total > 0), reverse=True)
+print(f"CPU self time per step: {sum(c[0] for c in cpu)/1e3:.3f} ms")
+for ct, n, k in cpu[:22]:
+    print(f"{ct/1e3:8.3f} ms x{n:3d}  {k}")
+import time
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for rep in range(4):
+    for i in range(6):
+        step(i)
+torch.cuda.synchronize(); print(f"wall per step without profiler: {(time.perf_counter() - t0) / 24 * 1e3:.3f} ms")
+t0 = time.perf_counter()
+for rep in range(4):
+    for i in range(6):
+        centre, rd, dL = frames[i]
+        ro = centre[None, None].expand(H, W, 3)
+        with torch.no_grad():
+            pkg = gr.raytracing(i, [asset], (ro, rd, centre), bg, None)
+torch.cuda.synchronize(); print(f"wall per forward-only raytracing(): {(time.perf_counter() - t0) / 24 * 1e3:.3f} ms")
