@@ -375,26 +375,34 @@ def run_b200(args, rank, world, local_rank):
     bg_cpu = torch.tensor(BG, device=dev)            # train.py:104-106 creates the background on the device too
 
     copy_stream = torch.cuda.Stream(device=dev)
+    # double-buffered device staging (allocated once: per-step allocations on a side stream would make the caching
+    # allocator cudaMalloc, which synchronises)
+    stage_buf = [(torch.empty((H, W, 3), device=dev), torch.empty((1, 3), device=dev), torch.empty((H, W, 9), device=dev)) for _ in range(2)]
+    stage_free = [torch.cuda.Event(), torch.cuda.Event()]      # recorded on the compute stream when a buffer pair is no longer read
+    for e_ in stage_free:
+        e_.record(torch.cuda.current_stream(dev))
     staged = {}
 
     def stage(i):
         """H2D of step i's inputs from pinned memory on the copy stream (overlaps the previous step's kernels)."""
         if i >= n_frames:
             return
+        b = i & 1
         with torch.cuda.stream(copy_stream):
-            rd = d_pin[i].to(dev, non_blocking=True)
-            centre = o_pin[i].to(dev, non_blocking=True).reshape(3)
-            dL = dL_pin[i].to(dev, non_blocking=True)
+            copy_stream.wait_event(stage_free[b])
+            rd, centre, dL = stage_buf[b]
+            rd.copy_(d_pin[i], non_blocking=True)
+            centre.copy_(o_pin[i], non_blocking=True)
+            dL.copy_(dL_pin[i], non_blocking=True)
             ev = torch.cuda.Event(); ev.record(copy_stream)
-        staged[i] = (rd, centre, dL, ev)
+        staged[i] = (rd, centre.reshape(3), dL, ev)
 
     def step_e2e(i):
         if i not in staged:
             stage(i)
         rd, centre, dL, ev = staged.pop(i)
-        torch.cuda.current_stream(dev).wait_event(ev)
-        for t_ in (rd, centre, dL):
-            t_.record_stream(torch.cuda.current_stream(dev))
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev)
         stage(i + 1)                                              # next frame's copies run under this frame's kernels
         ro = centre[None, None].expand(H, W, 3)
         for p in asset.parameters():
@@ -405,6 +413,7 @@ def run_b200(args, rank, world, local_rank):
         loss.backward()
         out_host.copy_(rendered.detach(), non_blocking=True)
         loss_host.copy_(loss.detach(), non_blocking=True)
+        stage_free[i & 1].record(cur)
 
     for i in range(Wm):
         step_e2e(i)
