@@ -102,12 +102,15 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
  *                           neighbouring rays. 0 = no structure known (default).
  *   LRT_OPT_VECTOR_ATOMICS  backward: 128-bit vector reductions where alignment allows (default 1)
  *   LRT_OPT_BACKWARD_KERNEL 0 = one thread per ray replays its hit list (default), 1 = one warp per ray, one hit per lane
+ *   LRT_OPT_SORT_RAYS       1 = compositing and the backward replay take rays in order of descending list length, so the
+ *                           32 lanes of a warp run loops of equal length (default 1)
  *   LRT_OPT_KERNEL_TIMING   1 = record CUDA events around every kernel launch (read with lrt_get_kernel_times)
  *   LRT_OPT_WAVEFRONT_SHADE wavefront compositing: 0 = one warp per ray, 1 = warp sort + one thread per ray (default)
  *   LRT_OPT_MORTON_BITS     32 = 32-bit keys, bits dealt to the axes so cells stay cubic (default); 63 = 21 bits/axis on
  *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build) */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,
-                  LRT_OPT_BACKWARD_KERNEL = 5, LRT_OPT_WAVEFRONT_SHADE = 6, LRT_OPT_KERNEL_TIMING = 7 };
+                  LRT_OPT_BACKWARD_KERNEL = 5, LRT_OPT_WAVEFRONT_SHADE = 6, LRT_OPT_KERNEL_TIMING = 7,
+                  LRT_OPT_SORT_RAYS = 8 };
 int lrt_set_option(lrt_ctx* ctx, int option, int value);
 
 /* Introspection for tests / benchmarks (host pointers). */

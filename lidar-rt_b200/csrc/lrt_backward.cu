@@ -10,6 +10,7 @@
 //   k_backward_list  : replay the (id, depth) list the forward pass recorded — no traversal at all;
 //   k_backward_trace : re-trace through the LBVH exactly like the reference does (used for rays
 //                      whose list overflowed `cap`, or when the caller passes no lists).
+#include <cub/device/device_radix_sort.cuh>
 #include "lrt_ctx.cuh"
 #include "lrt_trace.cuh"
 
@@ -245,13 +246,21 @@ struct BwArgs {
     const float* means; const float* scales; const float* rots; const float* opac; const float* shs;
     int D, M; float mod; const float* fwd_out; const float* dL; int flags;
     const int32_t* hit_gidx; const float* hit_t; const int32_t* hit_cnt; int cap;
+    const int* order;                     // rays by descending hit count, or nullptr
     GradOut go;
 };
 
+__global__ void __launch_bounds__(128) k_iota(int n, int* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
 __global__ void __launch_bounds__(128) k_backward_list(BwArgs a)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.R) return;
+    const int s_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s_ >= a.R) return;
+    const int r = a.order ? a.order[s_] : s_;
     const int cnt = a.hit_cnt[r];
     if (cnt <= 0 || cnt > a.cap) return;                 // overflowed rays are handled by k_backward_trace
     const float o[3] = {a.ray_o[(size_t)r * a.ray_o_stride], a.ray_o[(size_t)r * a.ray_o_stride + 1], a.ray_o[(size_t)r * a.ray_o_stride + 2]};
@@ -424,7 +433,7 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
     a.R = R; a.ray_o = ray_o; a.ray_o_stride = ray_o_stride; a.ray_d = ray_d; a.bg = bg;
     a.means = means; a.scales = scales; a.rots = rots; a.opac = opac; a.shs = shs;
     a.D = D; a.M = M; a.mod = mod; a.fwd_out = fwd_out; a.dL = dL_dout; a.flags = flags;
-    a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_cnt = hit_cnt; a.cap = cap;
+    a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_cnt = hit_cnt; a.cap = cap; a.order = nullptr;
     a.go.d_means = dL_dmeans; a.go.d_shs = dL_dshs; a.go.d_opac = dL_dopac; a.go.d_scales = dL_dscales; a.go.d_rots = dL_drots;
     a.go.vec = ctx->opt_vector_atomics && (reinterpret_cast<uintptr_t>(dL_dshs) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(dL_drots) & 15) == 0 && (reinterpret_cast<uintptr_t>(dL_dscales) & 7) == 0;
@@ -439,6 +448,19 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
             }
             ctx->span_begin("k_backward_warp", s); k_backward_warp<<<min((R + 3) / 4, ctx->num_sms * 16), TB, 0, s>>>(a); ctx->span_end(s);
         } else {
+            if (ctx->opt_sort_rays) {                  // rays by descending contributing-hit count: equal loop lengths within a warp
+                LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_ids, sizeof(int) * (size_t)R * 2));
+                LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_keys, sizeof(int) * (size_t)R));
+                int* ids = (int*)ctx->bw_ids.p; int* order = ids + R;
+                k_iota<<<GB, TB, 0, s>>>(R, ids);
+                size_t tb = 0;
+                LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const int*)hit_cnt, (int*)ctx->bw_keys.p, (const int*)ids, order, R, 0, 12, s));
+                LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_sort_tmp, tb));
+                ctx->span_begin("ray_order_sort", s);
+                LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairsDescending(ctx->bw_sort_tmp.p, tb, (const int*)hit_cnt, (int*)ctx->bw_keys.p, (const int*)ids, order, R, 0, 12, s));
+                ctx->span_end(s);
+                a.order = order;
+            }
             ctx->span_begin("k_backward_list", s); k_backward_list<<<GB, TB, 0, s>>>(a); ctx->span_end(s);
         }
         ctx->launches += 1;

@@ -9,6 +9,7 @@
 //   last depth + 1e-5 when the buffer was full.
 // Additionally records, per ray, the ordered list of contributing surfels (id, depth) so the
 // backward pass can replay it instead of traversing again.
+#include <cub/device/device_radix_sort.cuh>
 #include "lrt_ctx.cuh"
 #include "lrt_trace.cuh"
 
@@ -537,11 +538,14 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_bins, sizeof(unsigned long long) * (size_t)R * hcap));
         w.hcap = hcap;
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_fb, sizeof(int) * (size_t)R));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_ids, sizeof(int) * (size_t)R * 2));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_keys, sizeof(int) * (size_t)R));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 16));
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 16, s));
         w.rs = (RaySetup*)ctx->wf_rs.p; w.list_a = (uint2*)ctx->wf_list_a.p; w.list_b = (uint2*)ctx->wf_list_b.p;
         w.cap_items = (int)cap_items; w.counts = (int*)ctx->counter.p; w.hit_count = (int*)ctx->wf_hit_count.p;
         w.bins = (unsigned long long*)ctx->wf_bins.p; w.fb_list = (int*)ctx->wf_fb.p;
+        w.ray_ids = (int*)ctx->wf_ids.p; w.order = nullptr;
         if (ctx->num_sms == 0) {
             int sms = 0;
             LRT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -561,6 +565,19 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         if (ctx->opt_wavefront_shade == 0) {
             ctx->span_begin("k_wf_shade", s); k_wf_shade<<<min((S + 3) / 4, ctx->num_sms * 8), 128, 0, s>>>(bv, a, w); ctx->span_end(s);
         } else {
+            if (ctx->opt_sort_rays) {
+                // rays by descending candidate count (11-bit keys: 2 radix passes over R pairs)
+                int* order = (int*)ctx->wf_ids.p + R;
+                size_t tb = 0;
+                LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const int*)w.hit_count, (int*)ctx->wf_keys.p,
+                                                                            (const int*)w.ray_ids, order, R, 0, 12, s));
+                LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_sort_tmp, tb));
+                ctx->span_begin("ray_order_sort", s);
+                LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairsDescending(ctx->wf_sort_tmp.p, tb, (const int*)w.hit_count, (int*)ctx->wf_keys.p,
+                                                                            (const int*)w.ray_ids, order, R, 0, 12, s));
+                ctx->span_end(s);
+                w.order = order;
+            }
             ctx->span_begin("k_wf_sort", s); k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w); ctx->span_end(s);
             ctx->span_begin("k_wf_composite", s); k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w); ctx->span_end(s);
             ctx->launches += 1;

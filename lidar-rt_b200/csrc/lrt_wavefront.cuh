@@ -34,6 +34,8 @@ struct WfBufs {
     unsigned long long* bins;       // (R, hcap)
     int hcap;                       // bin capacity (<= WF_HCAP_MAX)
     int* fb_list;                   // (R) fallback ray ids
+    int* ray_ids;                   // (R) identity, input of the by-length sort
+    const int* order;               // (R) rays sorted by descending candidate count, or nullptr (tile order)
 };
 
 __global__ void __launch_bounds__(256) k_wf_setup(FwdArgs a, WfBufs w)
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(256) k_wf_setup(FwdArgs a, WfBufs w)
     ray_setup(rs, o, d, 0.0f);
     w.rs[r] = rs;
     w.hit_count[r] = 0;
+    w.ray_ids[r] = r;
 }
 
 // One (ray, node) item per thread at `level` >= 1. in == nullptr: the implicit root list (every ray, node 0)
@@ -393,9 +396,10 @@ __global__ void __launch_bounds__(128) k_wf_sort(FwdArgs a, WfBufs w)
 
 __global__ void __launch_bounds__(128) k_wf_composite(BvhView bvh, FwdArgs a, WfBufs w)
 {
-    const int S = num_slots(a.R, a.grid_w);
+    // with `order`, a warp's 32 rays have (nearly) equal candidate counts: the per-ray loops below stay in step
+    const int S = w.order ? a.R : num_slots(a.R, a.grid_w);
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-        const int r = slot_to_ray(s, a.R, a.grid_w);
+        const int r = w.order ? w.order[s] : slot_to_ray(s, a.R, a.grid_w);
         if (r < 0) continue;
         const int hc = w.hit_count[r];
         if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }

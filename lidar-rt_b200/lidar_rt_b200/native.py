@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("LIDAR_RT_B200_LIB") or os.path.join(os.path.dirname(_
 LRT_FLAG_FIX_BG_GRAD = 1
 NUM_CHANNELS = 9
 DEFAULT_HIT_CAP = 256          # contributing hits recorded per ray for the backward replay (rays beyond it are re-traced)
-OPT_FORWARD_KERNEL, OPT_RAY_GRID_WIDTH, OPT_VECTOR_ATOMICS, OPT_MORTON_BITS, OPT_BACKWARD_KERNEL, OPT_WAVEFRONT_SHADE, OPT_KERNEL_TIMING = 1, 2, 3, 4, 5, 6, 7
+OPT_FORWARD_KERNEL, OPT_RAY_GRID_WIDTH, OPT_VECTOR_ATOMICS, OPT_MORTON_BITS, OPT_BACKWARD_KERNEL, OPT_WAVEFRONT_SHADE, OPT_KERNEL_TIMING, OPT_SORT_RAYS = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class LrtError(RuntimeError):
@@ -101,6 +101,10 @@ class Context:
             raise LrtError(self.lib.lrt_last_error(None).decode())
         self._h = h
         self.generation = 0          # bumps on every build / refit
+        # tuning knobs for A/B runs without code changes: LIDAR_RT_B200_OPTIONS="8=0,5=1" (LRT_OPT_* id = value)
+        for kv in filter(None, os.environ.get("LIDAR_RT_B200_OPTIONS", "").split(",")):
+            k, v = kv.split("=")
+            self.set_option(int(k), int(v))
 
     def close(self):
         if getattr(self, "_h", None):

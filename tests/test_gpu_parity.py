@@ -148,7 +148,10 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
         for kernel in (0, 1, 2, 3):
             for tiled in (True, False):
                 for morton in (32, 63, 30):
-                  for shade in ((0, 1) if kernel == 3 else (1,)):
+                  for shade in ((0, 1, 2) if kernel == 3 else (1,)):
+                    # shade 2 = default compositing kernel with the by-length ray ordering switched off
+                    ctx.set_option(native.OPT_SORT_RAYS, 0 if shade == 2 else 1)
+                    shade = min(shade, 1)
                     ctx.set_option(native.OPT_FORWARD_KERNEL, kernel)
                     ctx.set_option(native.OPT_MORTON_BITS, morton)
                     ctx.set_option(native.OPT_WAVEFRONT_SHADE, shade)
@@ -163,6 +166,7 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
                             assert np.array_equal(a_, b_), f"kernel={kernel} tiled={tiled} morton={morton} shade={shade} differs"
     finally:
         ctx.set_option(native.OPT_FORWARD_KERNEL, 3); ctx.set_option(native.OPT_MORTON_BITS, 32); ctx.set_option(native.OPT_WAVEFRONT_SHADE, 1)
+        ctx.set_option(native.OPT_SORT_RAYS, 1)
     assert_close(res["accum_w"], run_cuda(ctx, o, d, as_dict(sc), 3)["accum_w"], 1e-5, 1e-5, "accum (atomic order)")
 
 
@@ -176,10 +180,13 @@ def test_backward_kernels_agree(ctx):
     try:
         ctx.set_option(native.OPT_BACKWARD_KERNEL, 0); a = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
         ctx.set_option(native.OPT_BACKWARD_KERNEL, 1); b = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
+        ctx.set_option(native.OPT_BACKWARD_KERNEL, 0); ctx.set_option(native.OPT_SORT_RAYS, 0)
+        c = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
     finally:
-        ctx.set_option(native.OPT_BACKWARD_KERNEL, 0)
+        ctx.set_option(native.OPT_BACKWARD_KERNEL, 0); ctx.set_option(native.OPT_SORT_RAYS, 1)
     for k in ("means", "shs", "opac", "scales", "rots"):
         grad_close(b[f"g_{k}"], a[f"g_{k}"], 2e-4, f"d_{k}")
+        grad_close(c[f"g_{k}"], a[f"g_{k}"], 2e-4, f"unsorted rays d_{k}")
 
 
 def test_refit_matches_rebuild(ctx):
