@@ -96,7 +96,10 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
 
 /* Tuning knobs; none of them changes results.
  *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill, 2 = 8 lanes per ray,
- *                           3 = breadth-first wavefront + warp-per-ray compositing (default)
+ *                           3 = breadth-first wavefront through the hierarchy + per-ray sort + compositing,
+ *                           4 = shared-origin beam grid (default): when ray_o_stride == 0 the frame's rays are binned by
+ *                               direction and one pass over the surfel records fills the per-ray candidate bins; frames
+ *                               with per-ray origins take 3
  *   LRT_OPT_RAY_GRID_WIDTH  W > 0: the R rays of the next calls are a row-major (R / W, W) range image
  *                           (the (H, W, 3) tensors of the reference API); lets a warp take a 4 x 8 tile of
  *                           neighbouring rays. 0 = no structure known (default).
@@ -104,13 +107,14 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
  *   LRT_OPT_BACKWARD_KERNEL 0 = one thread per ray replays its hit list (default), 1 = one warp per ray, one hit per lane
  *   LRT_OPT_SORT_RAYS       1 = compositing and the backward replay take rays in order of descending list length, so the
  *                           32 lanes of a warp run loops of equal length (default 1)
+ *   LRT_OPT_BEAM_CELL_PCT   beam grid: cell edge in percent of the size that gives one ray per cell (default 100)
  *   LRT_OPT_KERNEL_TIMING   1 = record CUDA events around every kernel launch (read with lrt_get_kernel_times)
  *   LRT_OPT_WAVEFRONT_SHADE wavefront compositing: 0 = one warp per ray, 1 = warp sort + one thread per ray (default)
  *   LRT_OPT_MORTON_BITS     32 = 32-bit keys, bits dealt to the axes so cells stay cubic (default); 63 = 21 bits/axis on
  *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build) */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,
                   LRT_OPT_BACKWARD_KERNEL = 5, LRT_OPT_WAVEFRONT_SHADE = 6, LRT_OPT_KERNEL_TIMING = 7,
-                  LRT_OPT_SORT_RAYS = 8 };
+                  LRT_OPT_SORT_RAYS = 8, LRT_OPT_BEAM_CELL_PCT = 9 };
 int lrt_set_option(lrt_ctx* ctx, int option, int value);
 
 /* Introspection for tests / benchmarks (host pointers). */

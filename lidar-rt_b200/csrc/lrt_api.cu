@@ -40,7 +40,8 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     DevBuf* bufs[] = {&ctx->leafq, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
                       &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb,
-                      &ctx->wf_ids, &ctx->wf_keys, &ctx->wf_sort_tmp, &ctx->bw_ids, &ctx->bw_keys, &ctx->bw_sort_tmp};
+                      &ctx->wf_ids, &ctx->wf_keys, &ctx->wf_sort_tmp, &ctx->bw_ids, &ctx->bw_keys, &ctx->bw_sort_tmp,
+                      &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     delete ctx;
     return LRT_OK;
@@ -91,8 +92,9 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
 {
     if (!ctx) return LRT_ERR_INVALID;
     switch (option) {
-    case LRT_OPT_FORWARD_KERNEL: if (value < 0 || value > 3) break; ctx->opt_forward_kernel = value; return LRT_OK;
+    case LRT_OPT_FORWARD_KERNEL: if (value < 0 || value > 4) break; ctx->opt_forward_kernel = value; return LRT_OK;
     case LRT_OPT_RAY_GRID_WIDTH: if (value < 0) break; ctx->opt_ray_grid_w = value; return LRT_OK;
+    case LRT_OPT_BEAM_CELL_PCT: if (value < 10 || value > 1000) break; ctx->opt_beam_cell_pct = value; return LRT_OK;
     case LRT_OPT_SORT_RAYS: if (value != 0 && value != 1) break; ctx->opt_sort_rays = value; return LRT_OK;
     case LRT_OPT_KERNEL_TIMING: if (value != 0 && value != 1) break; ctx->opt_kernel_timing = value; return LRT_OK;
     case LRT_OPT_WAVEFRONT_SHADE: if (value != 0 && value != 1) break; ctx->opt_wavefront_shade = value; return LRT_OK;

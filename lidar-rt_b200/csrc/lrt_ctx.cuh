@@ -28,10 +28,13 @@ struct lrt_ctx {
     DevBuf leafq;
     DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, iperm, sort_tmp, bounds, counter;
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
+    DevBuf bg_ang, bg_cell_of, bg_cells, bg_sray, bg_wide, bg_plan;   // shared-origin beam grid (lrt_beamgrid.cuh)
     // options (lrt_set_option)
-    int opt_forward_kernel = 3;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray, 3: wavefront
+    int opt_forward_kernel = 4;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray, 3: wavefront,
+                                  // 4: shared-origin beam grid (frames with per-ray origins take 3)
     int opt_ray_grid_w = 0;       // > 0: rays are a row-major range image of this width (enables 4 x 8 warp tiles)
     int opt_wavefront_shade = 1;  // wavefront compositing: 0 = one warp per ray (k_wf_shade), 1 = warp-sort + one thread per ray
+    int opt_beam_cell_pct = 100;  // beam grid: cell edge in percent of the one-ray-per-cell size
     int opt_sort_rays = 1;        // composite / backward replay: process rays in order of descending list length (lanes stay in step)
     int opt_backward_kernel = 0;  // 0: one thread per ray replays its hit list (default, measured faster), 1: one warp per ray, one hit per lane (scans)
     int opt_vector_atomics = 1;   // backward: red.global.add.v4.f32 where alignment allows
@@ -85,7 +88,8 @@ struct lrt_ctx {
     size_t total_bytes() const
     {
         return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + iperm.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
-               wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap;
+               wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
+               bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap;
     }
     BvhView view() const
     {

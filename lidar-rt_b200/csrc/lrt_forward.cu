@@ -10,6 +10,7 @@
 // Additionally records, per ray, the ordered list of contributing surfels (id, depth) so the
 // backward pass can replay it instead of traversing again.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "lrt_ctx.cuh"
 #include "lrt_trace.cuh"
 
@@ -487,6 +488,7 @@ __global__ void __launch_bounds__(128, LRT_G8_MIN_BLOCKS) k_forward_g8(BvhView b
 }
 
 #include "lrt_wavefront.cuh"
+#include "lrt_beamgrid.cuh"
 
 } // namespace
 
@@ -523,14 +525,19 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
     const int S = num_slots(R, a.grid_w);
     if (ctx->opt_forward_kernel == 0) {
         ctx->span_begin("k_forward", s); k_forward<<<(S + TB - 1) / TB, TB, 0, s>>>(ctx->view(), a); ctx->span_end(s);
-    } else if (ctx->opt_forward_kernel == 3) {
-        // wavefront: level-by-level work lists, per-ray hit bins, warp-per-ray compositing
+    } else if (ctx->opt_forward_kernel >= 3) {
+        // candidate bins per ray, filled either by the shared-origin beam grid (kernel 4: one pass over the surfel
+        // records) or by the breadth-first wavefront through the hierarchy (kernel 3, and any frame with per-ray
+        // origins); then per-ray sort + compositing
+        const bool beam = ctx->opt_forward_kernel == 4 && ray_o_stride == 0;
         WfBufs w;
         const long long cap_items = (long long)R * 160 + 1024;
         if (cap_items > 0x3fffffffLL) { ctx->set_error("lrt_forward: too many rays for the wavefront work lists"); return LRT_ERR_INVALID; }
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_rs, sizeof(RaySetup) * (size_t)R));
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_a, sizeof(uint2) * (size_t)cap_items));
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_b, sizeof(uint2) * (size_t)cap_items));
+        if (!beam) {
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_rs, sizeof(RaySetup) * (size_t)R));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_a, sizeof(uint2) * (size_t)cap_items));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_b, sizeof(uint2) * (size_t)cap_items));
+        }
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_hit_count, sizeof(int) * (size_t)R));
         // bin capacity: 2048 candidates per ray while that stays under ~6 GB, never below what the shared-memory sort takes
         int hcap = WF_HCAP_MAX;
@@ -553,6 +560,37 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         }
         const BvhView bv = ctx->view();
         const int G = ctx->num_sms * 8;                                 // grid-stride kernels: 8 blocks of 256 threads per SM
+        if (beam) {
+            BgBufs b;
+            b.ncell_cap = 2 * R + 2 * BG_MAX_NA;
+            const size_t ncell = (size_t)b.ncell_cap + 1;
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bg_ang, sizeof(float2) * (size_t)R));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bg_cell_of, sizeof(int) * (size_t)R));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bg_cells, sizeof(int) * 2 * ncell));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bg_sray, sizeof(float4) * (size_t)R));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bg_wide, sizeof(int4) * (size_t)BG_ITEM_CAP));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bg_plan, 64));
+            size_t tb = 0;
+            LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)nullptr, (int*)nullptr, (int)ncell, s));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_sort_tmp, tb));
+            b.ang = (float2*)ctx->bg_ang.p; b.cell_of = (int*)ctx->bg_cell_of.p;
+            b.cell_cnt = (int*)ctx->bg_cells.p; b.cell_start = b.cell_cnt + ncell;
+            b.sray = (float4*)ctx->bg_sray.p; b.items = (int4*)ctx->bg_wide.p;
+            b.plan = (BgPlan*)ctx->bg_plan.p; b.el_bounds = (int*)((char*)ctx->bg_plan.p + 32); b.item_count = b.el_bounds + 2;
+            LRT_CUDA_TRY(ctx, cudaMemsetAsync(b.el_bounds, 0x80, sizeof(int) * 2, s));
+            LRT_CUDA_TRY(ctx, cudaMemsetAsync(b.item_count, 0, sizeof(int), s));
+            LRT_CUDA_TRY(ctx, cudaMemsetAsync(b.cell_cnt, 0, sizeof(int) * ncell, s));
+            ctx->span_begin("k_bg_grid", s);
+            k_bg_angles<<<(R + 255) / 256, 256, 0, s>>>(a, w, b);
+            k_bg_plan<<<1, 32, 0, s>>>(R, b, 0.01f * (float)ctx->opt_beam_cell_pct);
+            k_bg_count<<<(R + 255) / 256, 256, 0, s>>>(R, b);
+            LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->wf_sort_tmp.p, tb, (const int*)b.cell_cnt, b.cell_start, (int)ncell, s));
+            k_bg_fill<<<(R + 255) / 256, 256, 0, s>>>(a, b);
+            ctx->span_end(s);
+            ctx->span_begin("k_bg_bin", s); k_bg_bin<<<G, 256, 0, s>>>(bv, a, w, b, ctx->P_pad); ctx->span_end(s);
+            ctx->span_begin("k_bg_heavy", s); k_bg_heavy<<<G, 256, 0, s>>>(bv, a, w, b); ctx->span_end(s);
+            ctx->launches += 8;
+        } else {
         ctx->span_begin("k_wf_setup", s); k_wf_setup<<<(R + 255) / 256, 256, 0, s>>>(a, w); ctx->span_end(s);
         const uint2* in = nullptr; const int* in_count = nullptr;
         uint2* bufs[2] = {w.list_a, w.list_b};
@@ -562,6 +600,8 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             in = bufs[flip]; in_count = w.counts + (level - 1); flip ^= 1;
         }
         ctx->span_begin("k_wf_leaf", s); k_wf_leaf<<<G, 256, 0, s>>>(bv, a, w, in, in_count); ctx->span_end(s);
+        ctx->launches += 1 + bv.levels;
+        }
         if (ctx->opt_wavefront_shade == 0) {
             ctx->span_begin("k_wf_shade", s); k_wf_shade<<<min((S + 3) / 4, ctx->num_sms * 8), 128, 0, s>>>(bv, a, w); ctx->span_end(s);
         } else {
@@ -583,7 +623,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             ctx->launches += 1;
         }
         ctx->span_begin("k_wf_fallback", s); k_wf_fallback<<<ctx->num_sms, 128, 0, s>>>(bv, a, w); ctx->span_end(s);
-        ctx->launches += 3 + bv.levels;
+        ctx->launches += 2;
     } else if (ctx->opt_forward_kernel == 2) {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 4));
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 4, s));

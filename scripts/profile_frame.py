@@ -12,7 +12,7 @@ ap.add_argument("--gaussians", type=int, default=2_000_000)
 ap.add_argument("--frames", type=int, default=3)
 ap.add_argument("--stats", action="store_true")
 ap.add_argument("--ab", action="store_true", help="time every combination of the tuning options")
-ap.add_argument("--fwd-kernel", type=int, default=3)
+ap.add_argument("--fwd-kernel", type=int, default=4)
 ap.add_argument("--flat", action="store_true", help="pass rays as (R,3): no 4x8 tiles")
 ap.add_argument("--no-vec", action="store_true")
 ap.add_argument("--cap", type=int, default=native.DEFAULT_HIT_CAP)
@@ -56,7 +56,7 @@ def run(fwd_kernel, flat, vec, cap, label, verbose=True, morton=None):
     _c = (_ct.c_int * 16)(); ctx.lib.lrt_debug_counters(ctx._h, _c)
     sl = res["slot_cnt"].cpu().numpy().astype(np.int64); hc = res["hit_cnt"].cpu().numpy()
     print(f"{label:34s} build {np.mean(tb):6.2f} ms  fwd {np.mean(tf):6.2f} ms  bwd {np.mean(tw):6.2f} ms  | slots/ray {np.mean(sl & 0xffff):.1f} "
-          f"contrib/ray {hc.mean():.1f} max {hc.max()} overflow {(hc > cap).mean():.4f} fallback rays (last frame) {_c[8]}", flush=True)
+          f"contrib/ray {hc.mean():.1f} max {hc.max()} overflow {(hc > cap).mean():.4f} fallback rays (last frame) {_c[8]} heavy items {_c[9]}", flush=True)
     if a.stats:
         import ctypes
         st = (ctypes.c_ulonglong * 16)(); ctx.lib.lrt_debug_stats(st, 1); st = np.array(list(st), np.float64) / (a.frames * hc.shape[0])

@@ -139,16 +139,16 @@ def test_backward_list_replay_equals_retrace_and_overflow(ctx):
 
 
 def test_all_forward_kernels_and_options_agree_bitwise(ctx):
-    """LRT_OPT_FORWARD_KERNEL 0/1/2/3, ray tiles on/off, Morton 30/63: tuning knobs must not change a single bit."""
+    """LRT_OPT_FORWARD_KERNEL 0/1/2/3/4, ray tiles on/off, Morton 30/63: tuning knobs must not change a single bit."""
     from lidar_rt_b200 import native
     sc = syn.make_street_scene(60000, seed=12)
     o, d = syn.ray_patch(32, 96, frame=1)
     ref = None
     try:
-        for kernel in (0, 1, 2, 3):
+        for kernel in (0, 1, 2, 3, 4):
             for tiled in (True, False):
                 for morton in (32, 63, 30):
-                  for shade in ((0, 1, 2) if kernel == 3 else (1,)):
+                  for shade in ((0, 1, 2) if kernel >= 3 else (1,)):
                     # shade 2 = default compositing kernel with the by-length ray ordering switched off
                     ctx.set_option(native.OPT_SORT_RAYS, 0 if shade == 2 else 1)
                     shade = min(shade, 1)
@@ -165,9 +165,56 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
                         for a_, b_ in zip(ref, key):
                             assert np.array_equal(a_, b_), f"kernel={kernel} tiled={tiled} morton={morton} shade={shade} differs"
     finally:
-        ctx.set_option(native.OPT_FORWARD_KERNEL, 3); ctx.set_option(native.OPT_MORTON_BITS, 32); ctx.set_option(native.OPT_WAVEFRONT_SHADE, 1)
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 4); ctx.set_option(native.OPT_MORTON_BITS, 32); ctx.set_option(native.OPT_WAVEFRONT_SHADE, 1)
         ctx.set_option(native.OPT_SORT_RAYS, 1)
     assert_close(res["accum_w"], run_cuda(ctx, o, d, as_dict(sc), 3)["accum_w"], 1e-5, 1e-5, "accum (atomic order)")
+
+
+def _same_forward(a, b, what):
+    valid = np.arange(a["hit_gidx"].shape[0])[:, None] < np.minimum(a["hit_cnt"], a["hit_gidx"].shape[0])[None, :]
+    assert np.array_equal(a["out"], b["out"], equal_nan=True), f"{what}: outputs differ"
+    assert np.array_equal(a["hit_cnt"], b["hit_cnt"]) and np.array_equal(a["slot_cnt"], b["slot_cnt"]), f"{what}: counts differ"
+    assert np.array_equal(np.where(valid, a["hit_gidx"], -1), np.where(valid, b["hit_gidx"], -1)), f"{what}: hit lists differ"
+
+
+def test_beam_grid_edge_cases_equal_per_ray_traversal(ctx, oracle32):
+    """The shared-origin beam grid (kernel 4) against one-thread-per-ray traversal (kernel 0), bit for bit, on the inputs
+    that stress its (azimuth, elevation) windows: a tilted sensor, zenith / nadir / duplicate / degenerate directions,
+    un-normalised directions, the +-pi azimuth seam, surfels around, above and below the sensor, 1- and 7-ray frames."""
+    from lidar_rt_b200 import native
+    rng = np.random.default_rng(21)
+    sc = syn.make_street_scene(40000, seed=21, scale_mult=2.0)
+    o, d = syn.ray_patch(32, 128, frame=2)
+    th = 0.6; c, s = np.cos(th), np.sin(th)
+    tilt = np.array([[1, 0, 0], [0, c, -s], [0, s, c]], np.float32)
+    # big surfels enclosing / next to / right above and below the sensor; one straddling the azimuth seam behind it
+    extra = dict(means=np.array([[0.05, 0.02, 0.1], [0.0, 0.0, 1.5], [0.3, -0.2, -1.2], [-6.0, 0.01, 0.0], [2.0, 0.0, 0.0]], np.float32) + o.reshape(1, 3),
+                 scales=np.array([[0.4, 0.3], [0.8, 0.8], [0.5, 0.9], [0.7, 0.7], [0.05, 3.0]], np.float32),
+                 rots=np.array([[1, 0, 0, 0], [1, 0.02, 0, 0], [1, 0, 0.03, 0], [1, 0, 1, 0], [1, 0.5, 0.5, 0.1]], np.float32),
+                 opac=np.full((5, 1), 0.3, np.float32), shs=(0.2 * rng.standard_normal((5, 16, 3))).astype(np.float32))
+    scd = {k: np.concatenate([as_dict(sc)[k], extra[k]], 0) for k in extra}
+    special = np.array([[0, 0, 1], [0, 0, -1], [0, 0, 1], [1e-9, 0, 1], [-1, 1e-8, 0], [-1, -1e-8, 0], [-1, 0, 0], [0, 0, 0],
+                        [3, 0, 0.1], [0, -250.0, 5.0], [1e-4, 1e-4, 1e-5]], np.float32)
+    cases = {"upright": d.reshape(-1, 3), "tilted": d.reshape(-1, 3) @ tilt.T,
+             "special": np.concatenate([special, d.reshape(-1, 3)[::37] * rng.uniform(0.1, 30, (len(d.reshape(-1, 3)[::37]), 1)).astype(np.float32)], 0),
+             "one_ray": d.reshape(-1, 3)[:1], "seven_rays": d.reshape(-1, 3)[100:107]}
+    try:
+        for name, dd in cases.items():
+            dd = np.ascontiguousarray(dd, np.float32)
+            ctx.set_option(native.OPT_FORWARD_KERNEL, 0); a = run_cuda(ctx, o, dd, scd, 3, cap=160)
+            ctx.set_option(native.OPT_FORWARD_KERNEL, 4); b = run_cuda(ctx, o, dd, scd, 3, cap=160)
+            _same_forward(a, b, name)
+        # the oracle agrees on the stress scene too (hit indices bit-exact)
+        dd = np.ascontiguousarray(cases["tilted"][::5])
+        b = run_cuda(ctx, o, dd, scd, 3, cap=160)
+        f = oracle32.forward(o, dd, BG, scd["means"], scd["scales"], scd["rots"], scd["opac"], scd["shs"], 3, flags=ORC_BVH, cap=160)
+        assert hit_lists(b) == oracle_lists(f) and np.array_equal(b["slot_cnt"], f["slot_cnt"])
+        # per-ray origins cannot use the grid: kernel 4 must route them through the hierarchy, same answer
+        oo = np.ascontiguousarray(np.broadcast_to(o.reshape(1, 3), (dd.shape[0], 3)) + 0.0)
+        c_ = run_cuda(ctx, oo, dd, scd, 3, cap=160)
+        _same_forward(b, c_, "per-ray origins")
+    finally:
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 4)
 
 
 def test_backward_kernels_agree(ctx):
