@@ -343,7 +343,7 @@ def run_b200(args, rank, world, local_rank):
     kernels = {k: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K} for k, v in kt.items()}
     # algorithmic bytes of the kernels that own a SURVEY §8d term (per step): the backward replay owns B_bwd; the
     # forward bytes are split: candidate geometry (K x 40 B) to the leaf kernel, rays + SH + outputs to the composite
-    kalg = {"k_backward_list": B_bwd, "k_wf_leaf": Ksum * 40, "k_bg_bin": Ksum * 40, "k_wf_composite": R * (12 + 36) + Kcsum * (nsh + 8),
+    kalg = {"k_backward_list": B_bwd, "k_bw_hits": B_bwd, "k_wf_leaf": Ksum * 40, "k_bg_bin": Ksum * 40, "k_wf_composite": R * (12 + 36) + Kcsum * (nsh + 8),
             "k_records": P * (40 + 64 + 24 + 4 + 10), "radix_sort": 2 * P * 8 * 4}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else "forward"
     dom_ms = kernels[dom]["ms_per_step"] if kernels else t_fwd

@@ -71,18 +71,22 @@ int lrt_refit(lrt_ctx* ctx, int P, const float* means, const float* scales, cons
  *   accum_w (P)         sum of blending weights per Gaussian (forward.cu:272)
  *   hit_gidx, hit_t     optional, (cap,R) each: contributing Gaussian ids (caller's indexing) and
  *                       depths in compositing order, slot k of ray r at [k*R + r]
+ *   hit_aux             optional (needs the lists), (cap,R,4) 16-byte aligned: per recorded hit (alpha, c0, c1, c2) — the
+ *                       blending opacity and SH colour the forward composited (c0 = -0.0 where channel 0 was clamped).
+ *                       With it the backward needs neither a serial re-evaluation of the ray nor the SH coefficients.
  *   hit_cnt (R)         optional: number of contributing hits (may exceed cap; list is truncated)
  *   slot_cnt (R)        optional: k-buffer slots consumed (evaluated proxy hits)
  */
 int lrt_forward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
                 const float* bg, int P, const float* means, const float* scales, const float* rots,
                 const float* opac, const float* shs, int D, int M, float scale_modifier,
-                float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, int32_t* hit_cnt,
+                float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, float* hit_aux, int32_t* hit_cnt,
                 int cap, int32_t* slot_cnt, void* stream);
 
 /* Replaces _C.trace_surfels_backward (trace_surfels.cpp:268-386; backward.cu:434-691).
  * fwd_out / dL_dout (R,9). If hit lists from the forward are given, rays with hit_cnt <= cap are
- * replayed from the list (no traversal); the others — or all rays when the lists are NULL — are
+ * replayed from the list (no traversal; with hit_aux as two passes: a per-ray prefix pass over the recorded
+ * (alpha, colour) and a pass with one thread per hit that scatters the gradients); the others — or all rays when the lists are NULL — are
  * re-traced through the current acceleration structure like the reference does.
  * Gradients (written entirely by the call, accumulated with float atomics):
  *   dL_dmeans (P,3)  dL_dshs (P,M,3)  dL_dopac (P)  dL_dscales (P,2)  dL_drots (P,4) */
@@ -90,7 +94,7 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
                  const float* bg, int P, const float* means, const float* scales, const float* rots,
                  const float* opac, const float* shs, int D, int M, float scale_modifier,
                  const float* fwd_out, const float* dL_dout,
-                 const int32_t* hit_gidx, const float* hit_t, const int32_t* hit_cnt, int cap,
+                 const int32_t* hit_gidx, const float* hit_t, const float* hit_aux, const int32_t* hit_cnt, int cap,
                  float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
                  float* dL_drots, int flags, void* stream);
 
@@ -104,7 +108,8 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
  *                           (the (H, W, 3) tensors of the reference API); lets a warp take a 4 x 8 tile of
  *                           neighbouring rays. 0 = no structure known (default).
  *   LRT_OPT_VECTOR_ATOMICS  backward: 128-bit vector reductions where alignment allows (default 1)
- *   LRT_OPT_BACKWARD_KERNEL 0 = one thread per ray replays its hit list (default), 1 = one warp per ray, one hit per lane
+ *   LRT_OPT_BACKWARD_KERNEL 0 = one thread per ray replays its hit list, 1 = one warp per ray, one hit per lane,
+ *                           2 = per-ray prefix pass + one thread per hit (default; used when hit_aux is given, else 0)
  *   LRT_OPT_SORT_RAYS       1 = compositing and the backward replay take rays in order of descending list length, so the
  *                           32 lanes of a warp run loops of equal length (default 1)
  *   LRT_OPT_BEAM_CELL_PCT   beam grid: cell edge in percent of the size that gives one ray per cell (default 100)

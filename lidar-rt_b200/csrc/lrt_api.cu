@@ -41,7 +41,7 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
     DevBuf* bufs[] = {&ctx->leafq, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->iperm, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
                       &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb,
                       &ctx->wf_ids, &ctx->wf_keys, &ctx->wf_sort_tmp, &ctx->bw_ids, &ctx->bw_keys, &ctx->bw_sort_tmp,
-                      &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan};
+                      &ctx->bw_off, &ctx->bw_rec_a, &ctx->bw_rec_b, &ctx->bw_legacy, &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     delete ctx;
     return LRT_OK;
@@ -66,25 +66,25 @@ int lrt_refit(lrt_ctx* ctx, int P, const float* means, const float* scales, cons
 int lrt_forward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
                 const float* bg, int P, const float* means, const float* scales, const float* rots,
                 const float* opac, const float* shs, int D, int M, float scale_modifier,
-                float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, int32_t* hit_cnt,
+                float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, float* hit_aux, int32_t* hit_cnt,
                 int cap, int32_t* slot_cnt, void* stream)
 {
     if (!ctx) return LRT_ERR_INVALID;
     return lrt_forward_impl(ctx, R, ray_o, ray_o_stride, ray_d, bg, P, means, scales, rots, opac, shs, D, M,
-                            scale_modifier, out, accum_w, hit_gidx, hit_t, hit_cnt, cap, slot_cnt, (cudaStream_t)stream);
+                            scale_modifier, out, accum_w, hit_gidx, hit_t, hit_aux, hit_cnt, cap, slot_cnt, (cudaStream_t)stream);
 }
 
 int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
                  const float* bg, int P, const float* means, const float* scales, const float* rots,
                  const float* opac, const float* shs, int D, int M, float scale_modifier,
                  const float* fwd_out, const float* dL_dout,
-                 const int32_t* hit_gidx, const float* hit_t, const int32_t* hit_cnt, int cap,
+                 const int32_t* hit_gidx, const float* hit_t, const float* hit_aux, const int32_t* hit_cnt, int cap,
                  float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
                  float* dL_drots, int flags, void* stream)
 {
     if (!ctx) return LRT_ERR_INVALID;
     return lrt_backward_impl(ctx, R, ray_o, ray_o_stride, ray_d, bg, P, means, scales, rots, opac, shs, D, M,
-                             scale_modifier, fwd_out, dL_dout, hit_gidx, hit_t, hit_cnt, cap,
+                             scale_modifier, fwd_out, dL_dout, hit_gidx, hit_t, hit_aux, hit_cnt, cap,
                              dL_dmeans, dL_dshs, dL_dopac, dL_dscales, dL_drots, flags, (cudaStream_t)stream);
 }
 
@@ -98,7 +98,7 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
     case LRT_OPT_SORT_RAYS: if (value != 0 && value != 1) break; ctx->opt_sort_rays = value; return LRT_OK;
     case LRT_OPT_KERNEL_TIMING: if (value != 0 && value != 1) break; ctx->opt_kernel_timing = value; return LRT_OK;
     case LRT_OPT_WAVEFRONT_SHADE: if (value != 0 && value != 1) break; ctx->opt_wavefront_shade = value; return LRT_OK;
-    case LRT_OPT_BACKWARD_KERNEL: if (value != 0 && value != 1) break; ctx->opt_backward_kernel = value; return LRT_OK;
+    case LRT_OPT_BACKWARD_KERNEL: if (value < 0 || value > 2) break; ctx->opt_backward_kernel = value; return LRT_OK;
     case LRT_OPT_MORTON_BITS: if (value != 30 && value != 32 && value != 63) break; ctx->opt_morton_bits = value; return LRT_OK;
     case LRT_OPT_VECTOR_ATOMICS: if (value != 0 && value != 1) break; ctx->opt_vector_atomics = value; return LRT_OK;
     default: break;

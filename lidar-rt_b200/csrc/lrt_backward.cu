@@ -11,6 +11,7 @@
 //   k_backward_trace : re-trace through the LBVH exactly like the reference does (used for rays
 //                      whose list overflowed `cap`, or when the caller passes no lists).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "lrt_ctx.cuh"
 #include "lrt_trace.cuh"
 
@@ -58,76 +59,81 @@ __device__ __forceinline__ void load_sh_bw(const float* __restrict__ shs, int g,
     }
 }
 
-// One proxy hit of ray (o, d) at depth dpt on Gaussian g.
-// FILTER = true replays the forward's skip / termination rules (re-trace path);
-// returns 0 = not contributing, 1 = composited (gradients scattered), 2 = ray terminated.
-template <bool FILTER>
-__device__ __forceinline__ int hit_backward(int g, float dpt, const float* o, const float* d, const float* dirn,
-                                            const float* __restrict__ means, const float* __restrict__ scales,
-                                            const float* __restrict__ rots, const float* __restrict__ opac,
-                                            const float* __restrict__ shs, int D, int M, float mod,
-                                            const float* __restrict__ bg, int flags, RayState& st, const GradOut& go)
+// Geometry of one proxy hit of ray (o, d) at depth dpt on Gaussian g (forward.cu:116-141, :228-251 recomputed
+// from the raw parameters, same arithmetic as the forward's record).
+struct HitGeo { Derived s; float rr[3], u, v, cosv, power, G, alpha; };
+
+__device__ __forceinline__ void hit_geo(int g, float dpt, const float* o, const float* d,
+                                        const float* __restrict__ means, const float* __restrict__ scales,
+                                        const float* __restrict__ rots, const float* __restrict__ opac, float mod, HitGeo& h)
 {
-    if (FILTER && dpt < LRT_MIN_T) return 0;                                          // backward.cu:528
     const float mu_[3] = {ld_f(means + 3 * (size_t)g), ld_f(means + 3 * (size_t)g + 1), ld_f(means + 3 * (size_t)g + 2)};
     const float2 sc2 = __ldg(reinterpret_cast<const float2*>(scales + 2 * (size_t)g));
     const float4 q4 = __ldg(reinterpret_cast<const float4*>(rots + 4 * (size_t)g));
     const float sc_[2] = {sc2.x, sc2.y};
     const float q_[4] = {q4.x, q4.y, q4.z, q4.w};
-    Derived s;
-    derive_surfel(mu_, sc_, q_, ld_f(opac + g), mod, s);
-
+    derive_surfel(mu_, sc_, q_, ld_f(opac + g), mod, h.s);
     const float xyz[3] = {o[0] + dpt * d[0], o[1] + dpt * d[1], o[2] + dpt * d[2]};
-    const float rr[3] = {xyz[0] - s.mu[0], xyz[1] - s.mu[1], xyz[2] - s.mu[2]};
-    const float u = s.Lu[0] * rr[0] + s.Lu[1] * rr[1] + s.Lu[2] * rr[2];
-    const float v = s.Lv[0] * rr[0] + s.Lv[1] * rr[1] + s.Lv[2] * rr[2];
-    const float cosv = -((s.mu[0] - o[0]) * s.n[0] + (s.mu[1] - o[1]) * s.n[1] + (s.mu[2] - o[2]) * s.n[2]);
-    const float rho = u * u + v * v;
-    const float power = -0.5f * rho;
-    if (FILTER && power > 0.0f) return 0;
-    const float G = expf(power);
-    const float alpha = fminf(LRT_ALPHA_MAX, s.op * G);
-    if (FILTER && alpha < 1.0f / 255.0f) return 0;
-    const float testT = st.T * (1.0f - alpha);
-    if (FILTER && testT < LRT_T_MIN) return 2;
+#pragma unroll
+    for (int k = 0; k < 3; k++) h.rr[k] = xyz[k] - h.s.mu[k];
+    h.u = h.s.Lu[0] * h.rr[0] + h.s.Lu[1] * h.rr[1] + h.s.Lu[2] * h.rr[2];
+    h.v = h.s.Lv[0] * h.rr[0] + h.s.Lv[1] * h.rr[1] + h.s.Lv[2] * h.rr[2];
+    h.cosv = -((h.s.mu[0] - o[0]) * h.s.n[0] + (h.s.mu[1] - o[1]) * h.s.n[1] + (h.s.mu[2] - o[2]) * h.s.n[2]);
+    const float rho = h.u * h.u + h.v * h.v;
+    h.power = -0.5f * rho;
+    h.G = expf(h.power);
+    h.alpha = fminf(LRT_ALPHA_MAX, h.s.op * h.G);
+}
+
+// What a hit takes from (and adds to) its ray's running state: blending weight w = alpha T, the prefix sums
+// including this hit, and dL/dalpha (backward.cu:577-604). Advances st.T.
+__device__ __forceinline__ float hit_state(RayState& st, float alpha, const float* c, const float* n, float dpt,
+                                           const float* bg, int flags, float& w_out)
+{
     const float T = st.T;
     const float w = alpha * T;
-
-    const int nb = (D + 1) * (D + 1);
-    float sh[48], c[3], basis[16]; bool clamped0;
-    load_sh_bw(shs, g, M, nb, sh);
-    sh_colour<true>(D, dirn, sh, c, clamped0, basis);
-
 #pragma unroll
-    for (int k = 0; k < 3; k++) { st.C[k] += w * c[k]; st.N[k] += w * s.n[k]; }       // :577-578
+    for (int k = 0; k < 3; k++) { st.C[k] += w * c[k]; st.N[k] += w * n[k]; }        // :577-578
     st.Dp += w * dpt;
-
     const float inv1a = 1.0f / (1.0f - alpha);
-    float dalpha = 0.0f, dcol[3];
+    float dalpha = 0.0f;
 #pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        dcol[ch] = st.g_rgb[ch] * w;
-        dalpha += st.g_rgb[ch] * (T * c[ch] - (st.F_c[ch] - st.C[ch]) * inv1a);      // :590
-    }
+    for (int ch = 0; ch < 3; ch++) dalpha += st.g_rgb[ch] * (T * c[ch] - (st.F_c[ch] - st.C[ch]) * inv1a);      // :590
     if (!(flags & LRT_FLAG_FIX_BG_GRAD)) {
         float dbg = 0.0f;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) dbg += st.g_rgb[ch] * bg[ch];
         dalpha += dbg * (-st.F_T * inv1a);                                            // :595-598 (duplicate term)
     }
-    const float dD_gs = st.g_d * w;
     dalpha += st.g_d * (T * dpt - (st.F_d - st.Dp) * inv1a);                          // :601
-    float dN_gs[3];
     {
         float acc = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 3; k++) { dN_gs[k] = st.g_n[k] * w; acc += st.g_n[k] * (T * s.n[k] - (st.F_n[k] - st.N[k]) * inv1a); }
+        for (int k = 0; k < 3; k++) acc += st.g_n[k] * (T * n[k] - (st.F_n[k] - st.N[k]) * inv1a);
         dalpha += acc;                                                                // :604
     }
+    st.T = T * (1.0f - alpha);
+    w_out = w;
+    return dalpha;
+}
+
+// Everything downstream of dL/dalpha for one hit: VJPs onto opacity, scale, rotation, mean (incl. the gradient
+// through the hit depth) and SH, scattered with float reductions (backward.cu:607-675).
+__device__ __forceinline__ void hit_scatter(int g, const float* o, const float* d, const HitGeo& h, float w, float dalpha,
+                                            float g_d, const float* g_n, float* dcol, bool clamped0, const float* basis, int nb, int M,
+                                            const GradOut& go)
+{
+    const Derived& s = h.s;
+    const float G = h.G, u = h.u, v = h.v;
+    const float* rr = h.rr;
+    const float dD_gs = g_d * w;
+    float dN_gs[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) dN_gs[k] = g_n[k] * w;
     if (s.op * G > LRT_ALPHA_MAX) dalpha = 0.0f;                                      // :607-608
     const float dG = s.op * dalpha;
     atomicAdd(go.d_opac + g, G * dalpha);                                             // :615
-    const float nsign = cosv > 0.0f ? 1.0f : -1.0f;                                   // :649-650
+    const float nsign = h.cosv > 0.0f ? 1.0f : -1.0f;                                 // :649-650
 
     // compute_transmat_uv_backward (:339-431)
     const float du = dG * -G * u, dv = dG * -G * v;
@@ -205,16 +211,16 @@ __device__ __forceinline__ int hit_backward(int g, float dpt, const float* o, co
     float* dsh = go.d_shs + (size_t)g * M * 3;
     if (go.vec && (M & 3) == 0) {
         // (j, ch) pairs are contiguous: 3 nb floats = groups of 4 (nb = 1 -> 3 floats: scalar tail)
-        float vals[48];
-#pragma unroll
-        for (int j = 0; j < 16; j++) { vals[3 * j] = basis[j] * dcol[0]; vals[3 * j + 1] = basis[j] * dcol[1]; vals[3 * j + 2] = basis[j] * dcol[2]; }
         const int nf = 3 * nb;
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-            if (4 * i + 3 < nf) red_add_v4(dsh + 4 * i, vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+            float vals[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const int idx = 4 * i + e; vals[e] = basis[idx / 3] * dcol[idx % 3]; }
+            if (4 * i + 3 < nf) red_add_v4(dsh + 4 * i, vals[0], vals[1], vals[2], vals[3]);
             else {
 #pragma unroll
-                for (int e = 0; e < 4; e++) if (4 * i + e < nf) atomicAdd(dsh + 4 * i + e, vals[4 * i + e]);
+                for (int e = 0; e < 4; e++) if (4 * i + e < nf) atomicAdd(dsh + 4 * i + e, vals[e]);
             }
         }
     } else {
@@ -227,7 +233,32 @@ __device__ __forceinline__ int hit_backward(int g, float dpt, const float* o, co
             }
         }
     }
-    st.T = testT;
+}
+
+// One proxy hit of ray (o, d) at depth dpt on Gaussian g, start to finish (serial replay / re-trace paths).
+// FILTER = true replays the forward's skip / termination rules (re-trace path);
+// returns 0 = not contributing, 1 = composited (gradients scattered), 2 = ray terminated.
+template <bool FILTER>
+__device__ __forceinline__ int hit_backward(int g, float dpt, const float* o, const float* d, const float* dirn,
+                                            const float* __restrict__ means, const float* __restrict__ scales,
+                                            const float* __restrict__ rots, const float* __restrict__ opac,
+                                            const float* __restrict__ shs, int D, int M, float mod,
+                                            const float* __restrict__ bg, int flags, RayState& st, const GradOut& go)
+{
+    if (FILTER && dpt < LRT_MIN_T) return 0;                                          // backward.cu:528
+    HitGeo h;
+    hit_geo(g, dpt, o, d, means, scales, rots, opac, mod, h);
+    if (FILTER && h.power > 0.0f) return 0;
+    if (FILTER && h.alpha < 1.0f / 255.0f) return 0;
+    if (FILTER && st.T * (1.0f - h.alpha) < LRT_T_MIN) return 2;
+    const int nb = (D + 1) * (D + 1);
+    float sh[48], c[3], basis[16]; bool clamped0;
+    load_sh_bw(shs, g, M, nb, sh);
+    sh_colour<true>(D, dirn, sh, c, clamped0, basis);
+    float w;
+    const float dalpha = hit_state(st, h.alpha, c, h.s.n, dpt, bg, flags, w);
+    float dcol[3] = {st.g_rgb[0] * w, st.g_rgb[1] * w, st.g_rgb[2] * w};
+    hit_scatter(g, o, d, h, w, dalpha, st.g_d, st.g_n, dcol, clamped0, basis, nb, M, go);
     return 1;
 }
 
@@ -245,8 +276,9 @@ struct BwArgs {
     int R; const float* ray_o; int ray_o_stride; const float* ray_d; const float* bg;
     const float* means; const float* scales; const float* rots; const float* opac; const float* shs;
     int D, M; float mod; const float* fwd_out; const float* dL; int flags;
-    const int32_t* hit_gidx; const float* hit_t; const int32_t* hit_cnt; int cap;
+    const int32_t* hit_gidx; const float* hit_t; const float4* hit_aux; const int32_t* hit_cnt; int cap;
     const int* order;                     // rays by descending hit count, or nullptr
+    const unsigned char* only;            // k_backward_list: if set, replay only the rays flagged here
     GradOut go;
 };
 
@@ -263,6 +295,7 @@ __global__ void __launch_bounds__(128) k_backward_list(BwArgs a)
     const int r = a.order ? a.order[s_] : s_;
     const int cnt = a.hit_cnt[r];
     if (cnt <= 0 || cnt > a.cap) return;                 // overflowed rays are handled by k_backward_trace
+    if (a.only && !a.only[r]) return;
     const float o[3] = {a.ray_o[(size_t)r * a.ray_o_stride], a.ray_o[(size_t)r * a.ray_o_stride + 1], a.ray_o[(size_t)r * a.ray_o_stride + 2]};
     const float d[3] = {a.ray_d[3 * (size_t)r], a.ray_d[3 * (size_t)r + 1], a.ray_d[3 * (size_t)r + 2]};
     const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -274,6 +307,89 @@ __global__ void __launch_bounds__(128) k_backward_list(BwArgs a)
         const int g = a.hit_gidx[(size_t)k * a.R + r];
         const float dpt = a.hit_t[(size_t)k * a.R + r];
         hit_backward<false>(g, dpt, o, d, dirn, a.means, a.scales, a.rots, a.opac, a.shs, a.D, a.M, a.mod, bg, a.flags, st, a.go);
+    }
+}
+
+// ---- two-pass replay (default when the forward recorded hit_aux) ----------------------------------------------
+// The serial part of a ray's backward is tiny: transmittance and the running sums of w c, w depth (w n) in front
+// of each hit. With (alpha, colour) of every contributing hit recorded by the forward, that part needs no Gaussian
+// parameter at all. So:
+//   k_bw_offsets + scan : flat position of every ray's hits
+//   k_bw_prefix         : one thread per ray walks its recorded (depth, alpha, colour) and writes, per hit, the flat
+//                         record (g, ray, depth, w, dL/dalpha). ~30 flops and 24 B per hit, coalesced reads.
+//   k_bw_hits           : one thread per HIT, all independent: recompute the surfel frame, VJPs, reductions. Full
+//                         occupancy instead of 8 warps/SM each waiting on its own chain of gathers; the SH
+//                         coefficients are never read (their gradient only needs the basis and dL/dcolour).
+struct BwFlat { int2* a; float4* b; const int* off; int capacity; unsigned char* legacy; };
+
+__global__ void __launch_bounds__(256) k_bw_offsets(int R, const int32_t* __restrict__ hit_cnt, int cap, int* __restrict__ cnt_eff)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > R) return;
+    int c = 0;
+    if (r < R) { c = hit_cnt[r]; if (c <= 0 || c > cap) c = 0; }
+    cnt_eff[r] = c;                                       // entry R stays 0: the scan's last output is the total
+}
+
+__global__ void __launch_bounds__(128) k_bw_prefix(BwArgs a, BwFlat f)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    f.legacy[r] = 0;
+    const int cnt = a.hit_cnt[r];
+    if (cnt <= 0 || cnt > a.cap) return;                  // overflowed rays are handled by k_backward_trace
+    const int off = f.off[r];
+    if (off + cnt > f.capacity) { f.legacy[r] = 1; return; }     // flat buffers full: this ray is replayed serially
+    const float bg[3] = {a.bg[0], a.bg[1], a.bg[2]};
+    RayState st;
+    ray_state_init(st, r, a.fwd_out, a.dL);
+    const bool need_n = st.g_n[0] != 0.0f || st.g_n[1] != 0.0f || st.g_n[2] != 0.0f;    // dL/dnormal is zero in practice (train.py never feeds it)
+    for (int k = 0; k < cnt; k++) {
+        const size_t at = (size_t)k * a.R + r;
+        const int g = a.hit_gidx[at];
+        const float dpt = a.hit_t[at];
+        const float4 ax = a.hit_aux[at];
+        const float c[3] = {ax.y, ax.z, ax.w};
+        float n[3] = {0.f, 0.f, 0.f};
+        if (need_n) {                                      // the normal prefix only matters then; same arithmetic as derive_surfel
+            const float4 q4 = __ldg(reinterpret_cast<const float4*>(a.rots + 4 * (size_t)g));
+            const float nrm = q4.x * q4.x + q4.y * q4.y + q4.z * q4.z + q4.w * q4.w;
+            const float inv = 1.0f / sqrtf(nrm);
+            const float w_ = q4.x * inv, x = q4.y * inv, y = q4.z * inv, z = q4.w * inv;
+            n[0] = 2.0f * (x * z + w_ * y); n[1] = 2.0f * (y * z - w_ * x); n[2] = 1.0f - 2.0f * (x * x + y * y);
+        }
+        float w;
+        const float dalpha = hit_state(st, ax.x, c, n, dpt, bg, a.flags, w);
+        const unsigned clamp = __float_as_uint(ax.y) & 0x80000000u;        // c0 == -0.0: channel 0 was clamped
+        f.a[off + k] = make_int2(g, (int)((unsigned)r | clamp));
+        f.b[off + k] = make_float4(dpt, w, dalpha, 0.0f);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bw_hits(BwArgs a, BwFlat f)
+{
+    const int n = min(f.off[a.R], f.capacity);
+    const int nb = (a.D + 1) * (a.D + 1);
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x) {
+        const int2 ra = f.a[h];
+        const float4 rb = f.b[h];
+        const int g = ra.x, r = ra.y & 0x7fffffff;
+        const bool clamped0 = ra.y < 0;
+        const float o[3] = {a.ray_o[(size_t)r * a.ray_o_stride], a.ray_o[(size_t)r * a.ray_o_stride + 1], a.ray_o[(size_t)r * a.ray_o_stride + 2]};
+        const float d[3] = {a.ray_d[3 * (size_t)r], a.ray_d[3 * (size_t)r + 1], a.ray_d[3 * (size_t)r + 2]};
+        const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        const float dirn[3] = {d[0] / dl, d[1] / dl, d[2] / dl};
+        const float* gl = a.dL + (size_t)LRT_NCH * r;
+        const float g_n[3] = {gl[5], gl[6], gl[7]};
+        const float w = rb.y;
+        float dcol[3] = {gl[0] * w, gl[1] * w, gl[2] * w};
+        HitGeo hg;
+        hit_geo(g, rb.x, o, d, a.means, a.scales, a.rots, a.opac, a.mod, hg);
+        float basis[16];
+        sh_basis(a.D, dirn, basis);
+#pragma unroll
+        for (int j = 0; j < 16; j++) if (j >= nb) basis[j] = 0.0f;
+        hit_scatter(g, o, d, hg, w, rb.z, gl[3], g_n, dcol, clamped0, basis, nb, a.M, a.go);
     }
 }
 
@@ -412,7 +528,7 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
                       const float* bg, int P, const float* means, const float* scales, const float* rots,
                       const float* opac, const float* shs, int D, int M, float mod,
                       const float* fwd_out, const float* dL_dout,
-                      const int32_t* hit_gidx, const float* hit_t, const int32_t* hit_cnt, int cap,
+                      const int32_t* hit_gidx, const float* hit_t, const float* hit_aux, const int32_t* hit_cnt, int cap,
                       float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
                       float* dL_drots, int flags, cudaStream_t s)
 {
@@ -433,14 +549,45 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
     a.R = R; a.ray_o = ray_o; a.ray_o_stride = ray_o_stride; a.ray_d = ray_d; a.bg = bg;
     a.means = means; a.scales = scales; a.rots = rots; a.opac = opac; a.shs = shs;
     a.D = D; a.M = M; a.mod = mod; a.fwd_out = fwd_out; a.dL = dL_dout; a.flags = flags;
-    a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_cnt = hit_cnt; a.cap = cap; a.order = nullptr;
+    a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_aux = reinterpret_cast<const float4*>(hit_aux); a.hit_cnt = hit_cnt; a.cap = cap;
+    a.order = nullptr; a.only = nullptr;
     a.go.d_means = dL_dmeans; a.go.d_shs = dL_dshs; a.go.d_opac = dL_dopac; a.go.d_scales = dL_dscales; a.go.d_rots = dL_drots;
     a.go.vec = ctx->opt_vector_atomics && (reinterpret_cast<uintptr_t>(dL_dshs) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(dL_drots) & 15) == 0 && (reinterpret_cast<uintptr_t>(dL_dscales) & 7) == 0;
     const int TB = 128, GB = (R + TB - 1) / TB;
     const bool can_trace = ctx->built && ctx->P == P && ctx->scale_modifier == mod;
     if (have_lists) {
-        if (ctx->opt_backward_kernel == 1) {
+        if (ctx->num_sms == 0) {
+            int sms = 0;
+            LRT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+            ctx->num_sms = sms > 0 ? sms : 148;
+        }
+        if (ctx->opt_backward_kernel == 2 && hit_aux && (reinterpret_cast<uintptr_t>(hit_aux) & 15) == 0) {
+            // two passes: per-ray prefix over the recorded (alpha, colour), then one thread per hit
+            const long long worst = (long long)R * cap;
+            const long long capacity_ll = worst < ((long long)R * 64 > (1LL << 20) ? (long long)R * 64 : (1LL << 20)) ? worst
+                                          : ((long long)R * 64 > (1LL << 20) ? (long long)R * 64 : (1LL << 20));
+            const int capacity = (int)(capacity_ll > 0x7fffff00LL ? 0x7fffff00LL : capacity_ll);
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_off, sizeof(int) * 2 * ((size_t)R + 1)));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_rec_a, sizeof(int2) * (size_t)capacity));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_rec_b, sizeof(float4) * (size_t)capacity));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_legacy, (size_t)R));
+            int* cnt_eff = (int*)ctx->bw_off.p; int* off = cnt_eff + (R + 1);
+            size_t tb = 0;
+            LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)cnt_eff, off, R + 1, s));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_sort_tmp, tb));
+            BwFlat f;
+            f.a = (int2*)ctx->bw_rec_a.p; f.b = (float4*)ctx->bw_rec_b.p; f.off = off; f.capacity = capacity; f.legacy = (unsigned char*)ctx->bw_legacy.p;
+            ctx->span_begin("k_bw_prefix", s);
+            k_bw_offsets<<<(R + 256) / 256, 256, 0, s>>>(R, hit_cnt, cap, cnt_eff);
+            LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->bw_sort_tmp.p, tb, (const int*)cnt_eff, off, R + 1, s));
+            k_bw_prefix<<<GB, TB, 0, s>>>(a, f);
+            ctx->span_end(s);
+            ctx->span_begin("k_bw_hits", s); k_bw_hits<<<ctx->num_sms * 8, 256, 0, s>>>(a, f); ctx->span_end(s);
+            a.only = f.legacy;                        // rays that did not fit the flat buffers (normally none)
+            ctx->span_begin("k_backward_list", s); k_backward_list<<<GB, TB, 0, s>>>(a); ctx->span_end(s);
+            ctx->launches += 5;
+        } else if (ctx->opt_backward_kernel == 1) {
             if (ctx->num_sms == 0) {
                 int sms = 0;
                 LRT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));

@@ -126,7 +126,7 @@ __device__ __forceinline__ void sh_colour(int deg, const float* dirn, const floa
     }
     c[0] = r0 + 0.5f; c[1] = r1 + 0.5f; c[2] = r2 + 0.5f;
     clamped0 = c[0] < 0.0f;
-    if (clamped0) c[0] = 0.0f;
+    if (clamped0) c[0] = -0.0f;        // clamped to zero; the sign bit carries "was clamped" to the recorded hit list (x + -0 == x)
     if (WITH_BASIS) {
 #pragma unroll
         for (int j = 0; j < 16; j++) basis[j] = j < nb ? b[j] : 0.0f;
@@ -185,7 +185,7 @@ __device__ __forceinline__ void sh_colour_stream(int deg, const float* dirn, con
         }
     }
     c[0] = r[0] + 0.5f; c[1] = r[1] + 0.5f; c[2] = r[2] + 0.5f;
-    if (c[0] < 0.0f) c[0] = 0.0f;
+    if (c[0] < 0.0f) c[0] = -0.0f;     // see sh_colour
 }
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return __ldg(p); }
 

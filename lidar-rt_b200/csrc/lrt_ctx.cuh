@@ -28,6 +28,7 @@ struct lrt_ctx {
     DevBuf leafq;
     DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, iperm, sort_tmp, bounds, counter;
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
+    DevBuf bw_off, bw_rec_a, bw_rec_b, bw_legacy;   // hit-parallel backward (lrt_backward.cu)
     DevBuf bg_ang, bg_cell_of, bg_cells, bg_sray, bg_wide, bg_plan;   // shared-origin beam grid (lrt_beamgrid.cuh)
     // options (lrt_set_option)
     int opt_forward_kernel = 4;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray, 3: wavefront,
@@ -36,7 +37,8 @@ struct lrt_ctx {
     int opt_wavefront_shade = 1;  // wavefront compositing: 0 = one warp per ray (k_wf_shade), 1 = warp-sort + one thread per ray
     int opt_beam_cell_pct = 100;  // beam grid: cell edge in percent of the one-ray-per-cell size
     int opt_sort_rays = 1;        // composite / backward replay: process rays in order of descending list length (lanes stay in step)
-    int opt_backward_kernel = 0;  // 0: one thread per ray replays its hit list (default, measured faster), 1: one warp per ray, one hit per lane (scans)
+    int opt_backward_kernel = 2;  // 0: one thread per ray replays its hit list, 1: one warp per ray, one hit per lane (scans),
+                                  // 2: two passes (default; needs hit_aux): per-ray prefix pass, then one thread per hit
     int opt_vector_atomics = 1;   // backward: red.global.add.v4.f32 where alignment allows
     int opt_morton_bits = 32;     // 32: 32-bit cubic-cell keys (default); 63: 21 bits/axis on cubic cells; 30: 10 bits/axis, per-axis extent
     int fwd_blocks_per_sm = 0, g8_blocks_per_sm = 0, num_sms = 0;
@@ -89,7 +91,8 @@ struct lrt_ctx {
     {
         return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + iperm.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
-               bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap;
+               bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
+               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + bw_legacy.cap;
     }
     BvhView view() const
     {
@@ -111,12 +114,12 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
 int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
                      const float* bg, int P, const float* means, const float* scales, const float* rots,
                      const float* opac, const float* shs, int D, int M, float mod,
-                     float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, int32_t* hit_cnt,
+                     float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, float* hit_aux, int32_t* hit_cnt,
                      int cap, int32_t* slot_cnt, cudaStream_t s);
 int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
                       const float* bg, int P, const float* means, const float* scales, const float* rots,
                       const float* opac, const float* shs, int D, int M, float mod,
                       const float* fwd_out, const float* dL_dout,
-                      const int32_t* hit_gidx, const float* hit_t, const int32_t* hit_cnt, int cap,
+                      const int32_t* hit_gidx, const float* hit_t, const float* hit_aux, const int32_t* hit_cnt, int cap,
                       float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
                       float* dL_drots, int flags, cudaStream_t s);

@@ -34,7 +34,7 @@ __device__ __forceinline__ void load_sh(const float* __restrict__ shs, int g, in
 
 struct FwdArgs {
     int R; const float* ray_o; int ray_o_stride; const float* ray_d; const float* bg; const float* shs; int D, M;
-    float* out; float* accum_w; int32_t* hit_gidx; float* hit_t; int32_t* hit_cnt; int cap; int32_t* slot_cnt;
+    float* out; float* accum_w; int32_t* hit_gidx; float* hit_t; float4* hit_aux; int32_t* hit_cnt; int cap; int32_t* slot_cnt;
     int grid_w;                  // > 0: rays form a row-major (R / grid_w, grid_w) range image -> 4 x 8 warp tiles
     int* work_counter;           // persistent kernel: next work slot
 };
@@ -100,6 +100,7 @@ __device__ __forceinline__ bool fwd_shade_round(FwdRay& q, const unsigned long l
         if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
             a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g;
             a.hit_t[(size_t)q.ncontrib * a.R + q.r] = q.dpt;
+            if (a.hit_aux) a.hit_aux[(size_t)q.ncontrib * a.R + q.r] = make_float4(alpha, c[0], c[1], c[2]);
         }
         q.ncontrib++;
         q.T = q.testT;
@@ -467,6 +468,7 @@ __global__ void __launch_bounds__(128, LRT_G8_MIN_BLOCKS) k_forward_g8(BvhView b
                     if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
                         a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g_i;
                         a.hit_t[(size_t)q.ncontrib * a.R + q.r] = dpt_i;
+                        if (a.hit_aux) a.hit_aux[(size_t)q.ncontrib * a.R + q.r] = make_float4(alpha, c0, c1, c2);
                     }
                 }
                 q.ncontrib++;
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(128, LRT_G8_MIN_BLOCKS) k_forward_g8(BvhView b
 int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, const float* ray_d,
                      const float* bg, int P, const float* means, const float* scales, const float* rots,
                      const float* opac, const float* shs, int D, int M, float mod,
-                     float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, int32_t* hit_cnt,
+                     float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, float* hit_aux, int32_t* hit_cnt,
                      int cap, int32_t* slot_cnt, cudaStream_t s)
 {
     (void)means; (void)scales; (void)rots; (void)opac;
@@ -513,12 +515,13 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
     if ((hit_gidx == nullptr) != (hit_t == nullptr) || (hit_gidx && (cap <= 0 || !hit_cnt))) {
         ctx->set_error("lrt_forward: hit_gidx, hit_t and hit_cnt go together and need cap > 0"); return LRT_ERR_INVALID;
     }
+    if (hit_aux && (!hit_gidx || (reinterpret_cast<uintptr_t>(hit_aux) & 15))) { ctx->set_error("lrt_forward: hit_aux needs the hit lists and 16-byte alignment"); return LRT_ERR_INVALID; }
     LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     LRT_CUDA_TRY(ctx, cudaMemsetAsync(accum_w, 0, sizeof(float) * (size_t)P, s));
     if (R == 0) return LRT_OK;
     FwdArgs a;
     a.R = R; a.ray_o = ray_o; a.ray_o_stride = ray_o_stride; a.ray_d = ray_d; a.bg = bg; a.shs = shs; a.D = D; a.M = M;
-    a.out = out; a.accum_w = accum_w; a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_cnt = hit_cnt; a.cap = cap; a.slot_cnt = slot_cnt;
+    a.out = out; a.accum_w = accum_w; a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_aux = reinterpret_cast<float4*>(hit_aux); a.hit_cnt = hit_cnt; a.cap = cap; a.slot_cnt = slot_cnt;
     a.grid_w = (ctx->opt_ray_grid_w > 0 && R % ctx->opt_ray_grid_w == 0) ? ctx->opt_ray_grid_w : 0;
     a.work_counter = nullptr;
     const int TB = 128;

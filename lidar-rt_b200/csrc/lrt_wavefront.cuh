@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
                     if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
                         a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g_i;
                         a.hit_t[(size_t)q.ncontrib * a.R + q.r] = dpt_i;
+                        if (a.hit_aux) a.hit_aux[(size_t)q.ncontrib * a.R + q.r] = make_float4(alpha, c0, c1, c2);
                     }
                 }
                 q.ncontrib++;

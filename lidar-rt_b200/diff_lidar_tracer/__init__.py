@@ -98,7 +98,7 @@ class _Tracer(torch.autograd.Function):
         ctx.have_hits = res["hit_gidx"] is not None
         saved = [ray_o, ray_d, means3D, shs, opacities, scales, rotations, out]
         if ctx.have_hits:
-            saved += [res["hit_gidx"], res["hit_t"], res["hit_cnt"]]
+            saved += [res["hit_gidx"], res["hit_t"], res["hit_cnt"], res["hit_aux"]]
         ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(accum)
         return out, accum
@@ -110,7 +110,7 @@ class _Tracer(torch.autograd.Function):
         ray_o, ray_d, means3D, shs, opacities, scales, rotations, out = saved[:8]
         hits = None
         if ctx.have_hits:
-            hits = dict(hit_gidx=saved[8], hit_t=saved[9], hit_cnt=saved[10], cap=ctx.cap)
+            hits = dict(hit_gidx=saved[8], hit_t=saved[9], hit_cnt=saved[10], hit_aux=saved[11], cap=ctx.cap)
         nctx = handle.ctx
         stale = nctx.generation != ctx.generation
         if stale and (hits is None or bool((hits["hit_cnt"] > ctx.cap).any())):

@@ -54,9 +54,9 @@ def load_library() -> ctypes.CDLL:
     lib.lrt_build.argtypes = build_args
     lib.lrt_refit.argtypes = build_args
     lib.lrt_forward.argtypes = [c_void_p, c_int, fp, c_int, fp, fp, c_int, fp, fp, fp, fp, fp, c_int, c_int, c_float,
-                                fp, fp, ip, fp, ip, c_int, ip, c_void_p]
+                                fp, fp, ip, fp, fp, ip, c_int, ip, c_void_p]
     lib.lrt_backward.argtypes = [c_void_p, c_int, fp, c_int, fp, fp, c_int, fp, fp, fp, fp, fp, c_int, c_int, c_float,
-                                 fp, fp, ip, fp, ip, c_int, fp, fp, fp, fp, fp, c_int, c_void_p]
+                                 fp, fp, ip, fp, fp, ip, c_int, fp, fp, fp, fp, fp, c_int, c_void_p]
     lib.lrt_set_option.argtypes = [c_void_p, c_int, c_int]
     lib.lrt_get_kernel_times.argtypes = [c_void_p, c_char_p, POINTER(c_float), POINTER(c_int), c_int]
     lib.lrt_get_kernel_times.restype = c_int
@@ -185,7 +185,7 @@ class Context:
         return R, lead, ray_o.contiguous(), 3, ray_d
 
     def forward(self, ray_o, ray_d, bg, means, scales, rots, opac, shs, sh_degree: int, scale_modifier: float = 1.0,
-                record_hits: bool = True, cap: int = DEFAULT_HIT_CAP, want_slots: bool = False):
+                record_hits: bool = True, cap: int = DEFAULT_HIT_CAP, want_slots: bool = False, record_aux: bool = True):
         P, means, scales, rots, opac = self._gauss(means, scales, rots, opac)
         R, lead, o, stride, d = self._rays(ray_o, ray_d)
         shs = _f32(shs, "shs", (3,))
@@ -198,18 +198,20 @@ class Context:
         with torch.cuda.device(dev):
             out = torch.empty(lead + (NUM_CHANNELS,), dtype=torch.float32, device=dev)
             accum = torch.empty(P, dtype=torch.float32, device=dev)
-            hit_g = hit_t = hit_c = slots = None
+            hit_g = hit_t = hit_a = hit_c = slots = None
             if record_hits:
                 hit_g = torch.empty((cap, R), dtype=torch.int32, device=dev)
                 hit_t = torch.empty((cap, R), dtype=torch.float32, device=dev)
                 hit_c = torch.empty(R, dtype=torch.int32, device=dev)
+                if record_aux:
+                    hit_a = torch.empty((cap, R, 4), dtype=torch.float32, device=dev)    # (alpha, c0, c1, c2) per recorded hit
             if want_slots:
                 slots = torch.empty(R, dtype=torch.int32, device=dev)
             self._check(self.lib.lrt_forward(self._h, R, _ptr(o), stride, _ptr(d), _ptr(bg), P, _ptr(means), _ptr(scales),
                                              _ptr(rots), _ptr(opac), _ptr(shs), int(sh_degree), M, c_float(scale_modifier),
-                                             _ptr(out), _ptr(accum), _ptr(hit_g), _ptr(hit_t), _ptr(hit_c), cap, _ptr(slots),
+                                             _ptr(out), _ptr(accum), _ptr(hit_g), _ptr(hit_t), _ptr(hit_a), _ptr(hit_c), cap, _ptr(slots),
                                              _stream(dev)))
-        return dict(out=out, accum_w=accum, hit_gidx=hit_g, hit_t=hit_t, hit_cnt=hit_c, slot_cnt=slots, cap=cap)
+        return dict(out=out, accum_w=accum, hit_gidx=hit_g, hit_t=hit_t, hit_aux=hit_a, hit_cnt=hit_c, slot_cnt=slots, cap=cap)
 
     def backward(self, ray_o, ray_d, bg, means, scales, rots, opac, shs, sh_degree: int, fwd_out, dL_dout,
                  hits: dict | None = None, scale_modifier: float = 1.0, flags: int = 0):
@@ -228,12 +230,13 @@ class Context:
             g_opac = torch.empty((P, 1), dtype=torch.float32, device=dev)
             g_scales = torch.empty((P, 2), dtype=torch.float32, device=dev)
             g_rots = torch.empty((P, 4), dtype=torch.float32, device=dev)
-            hg = ht = hc = None; cap = 0
+            hg = ht = ha = hc = None; cap = 0
             if hits is not None and hits.get("hit_gidx") is not None:
                 hg, ht, hc, cap = hits["hit_gidx"], hits["hit_t"], hits["hit_cnt"], int(hits["cap"])
+                ha = hits.get("hit_aux")
             self._check(self.lib.lrt_backward(self._h, R, _ptr(o), stride, _ptr(d), _ptr(bg), P, _ptr(means), _ptr(scales),
                                               _ptr(rots), _ptr(opac), _ptr(shs), int(sh_degree), M, c_float(scale_modifier),
-                                              _ptr(fwd_out), _ptr(dL), _ptr(hg), _ptr(ht), _ptr(hc), cap,
+                                              _ptr(fwd_out), _ptr(dL), _ptr(hg), _ptr(ht), _ptr(ha), _ptr(hc), cap,
                                               _ptr(g_means), _ptr(g_shs), _ptr(g_opac), _ptr(g_scales), _ptr(g_rots),
                                               int(flags), _stream(dev)))
         return dict(means=g_means, shs=g_shs, opac=g_opac, scales=g_scales, rots=g_rots)

@@ -17,7 +17,7 @@ ap.add_argument("--flat", action="store_true", help="pass rays as (R,3): no 4x8 
 ap.add_argument("--no-vec", action="store_true")
 ap.add_argument("--cap", type=int, default=native.DEFAULT_HIT_CAP)
 ap.add_argument("--morton", type=int, default=32)
-ap.add_argument("--bwd-kernel", type=int, default=0)
+ap.add_argument("--bwd-kernel", type=int, default=2)
 ap.add_argument("--shade", type=int, default=1)
 a = ap.parse_args()
 BG = np.array([0, 0, 1], np.float32)

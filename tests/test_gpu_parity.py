@@ -217,8 +217,9 @@ def test_beam_grid_edge_cases_equal_per_ray_traversal(ctx, oracle32):
         ctx.set_option(native.OPT_FORWARD_KERNEL, 4)
 
 
-def test_backward_kernels_agree(ctx):
-    """thread-per-ray list replay vs warp-per-ray scans: same gradients up to summation order."""
+def test_backward_kernels_agree(ctx, oracle32):
+    """thread-per-ray list replay (0), warp-per-ray scans (1), two-pass prefix + thread-per-hit (2, default): same
+    gradients up to summation order; the two-pass kernel also with dL/dnormal fed and against the oracle."""
     from lidar_rt_b200 import native
     sc = syn.make_street_scene(60000, seed=13)
     o, d = syn.ray_patch(32, 96, frame=3)
@@ -229,11 +230,24 @@ def test_backward_kernels_agree(ctx):
         ctx.set_option(native.OPT_BACKWARD_KERNEL, 1); b = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
         ctx.set_option(native.OPT_BACKWARD_KERNEL, 0); ctx.set_option(native.OPT_SORT_RAYS, 0)
         c = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
+        ctx.set_option(native.OPT_BACKWARD_KERNEL, 2); ctx.set_option(native.OPT_SORT_RAYS, 1)
+        e = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128)
+        e1 = run_cuda(ctx, o, d, as_dict(sc), 1, dL, cap=128)                      # SH degree 1: 12-float rows, scalar tail
+        e_fix = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128, flags=1)
+        ctx.set_option(native.OPT_BACKWARD_KERNEL, 0)
+        a1 = run_cuda(ctx, o, d, as_dict(sc), 1, dL, cap=128)
+        a_fix = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=128, flags=1)
     finally:
-        ctx.set_option(native.OPT_BACKWARD_KERNEL, 0); ctx.set_option(native.OPT_SORT_RAYS, 1)
+        ctx.set_option(native.OPT_BACKWARD_KERNEL, 2); ctx.set_option(native.OPT_SORT_RAYS, 1)
     for k in ("means", "shs", "opac", "scales", "rots"):
         grad_close(b[f"g_{k}"], a[f"g_{k}"], 2e-4, f"d_{k}")
         grad_close(c[f"g_{k}"], a[f"g_{k}"], 2e-4, f"unsorted rays d_{k}")
+        grad_close(e[f"g_{k}"], a[f"g_{k}"], 2e-4, f"two-pass d_{k}")
+        grad_close(e1[f"g_{k}"], a1[f"g_{k}"], 2e-4, f"two-pass degree 1 d_{k}")
+        grad_close(e_fix[f"g_{k}"], a_fix[f"g_{k}"], 2e-4, f"two-pass FIX_BG_GRAD d_{k}")
+    ob = oracle32.backward(o, d, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, 3, e["out"], dL, flags=ORC_BVH)
+    for k in ("means", "shs", "opac", "scales", "rots"):
+        grad_close(e[f"g_{k}"], ob[k], GRAD_REL, f"two-pass vs oracle d_{k}")
 
 
 def test_refit_matches_rebuild(ctx):
