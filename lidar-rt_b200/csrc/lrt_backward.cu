@@ -119,9 +119,10 @@ __device__ __forceinline__ float hit_state(RayState& st, float alpha, const floa
 
 // Everything downstream of dL/dalpha for one hit: VJPs onto opacity, scale, rotation, mean (incl. the gradient
 // through the hit depth) and SH, scattered with float reductions (backward.cu:607-675).
-__device__ __forceinline__ void hit_scatter(int g, const float* o, const float* d, const HitGeo& h, float w, float dalpha,
-                                            float g_d, const float* g_n, float* dcol, bool clamped0, const float* basis, int nb, int M,
-                                            const GradOut& go)
+struct HitGrads { float d_opac, dmu[3], dsc[2], dq[4]; };
+
+__device__ __forceinline__ void hit_vjp(const float* o, const float* d, const HitGeo& h, float w, float dalpha,
+                                        float g_d, const float* g_n, HitGrads& out)
 {
     const Derived& s = h.s;
     const float G = h.G, u = h.u, v = h.v;
@@ -132,7 +133,7 @@ __device__ __forceinline__ void hit_scatter(int g, const float* o, const float* 
     for (int k = 0; k < 3; k++) dN_gs[k] = g_n[k] * w;
     if (s.op * G > LRT_ALPHA_MAX) dalpha = 0.0f;                                      // :607-608
     const float dG = s.op * dalpha;
-    atomicAdd(go.d_opac + g, G * dalpha);                                             // :615
+    out.d_opac = G * dalpha;                                                          // :615
     const float nsign = h.cosv > 0.0f ? 1.0f : -1.0f;                                 // :649-650
 
     // compute_transmat_uv_backward (:339-431)
@@ -195,17 +196,30 @@ __device__ __forceinline__ void hit_scatter(int g, const float* o, const float* 
         const float dq2 = 2.0f * (qx * (GM(1, 0) + GM(0, 1)) - 2.0f * qy * (GM(0, 0) + GM(2, 2)) + qz * (GM(2, 1) + GM(1, 2)) + qw * (GM(0, 2) - GM(2, 0)));
         const float dq3 = 2.0f * (qx * (GM(2, 0) + GM(0, 2)) + qy * (GM(2, 1) + GM(1, 2)) - 2.0f * qz * (GM(0, 0) + GM(1, 1)) + qw * (GM(1, 0) - GM(0, 1)));
 #undef GM
-        if (go.vec) {                                                                                             // :659-669
-            red_add_v2(go.d_scales + 2 * (size_t)g, dsc[0], dsc[1]);
-            red_add_v4(go.d_rots + 4 * (size_t)g, dq0, dq1, dq2, dq3);
-        } else {
-            atomicAdd(go.d_scales + 2 * (size_t)g, dsc[0]); atomicAdd(go.d_scales + 2 * (size_t)g + 1, dsc[1]);
-            atomicAdd(go.d_rots + 4 * (size_t)g, dq0); atomicAdd(go.d_rots + 4 * (size_t)g + 1, dq1);
-            atomicAdd(go.d_rots + 4 * (size_t)g + 2, dq2); atomicAdd(go.d_rots + 4 * (size_t)g + 3, dq3);
-        }
-        atomicAdd(go.d_means + 3 * (size_t)g, dmu[0]); atomicAdd(go.d_means + 3 * (size_t)g + 1, dmu[1]);
-        atomicAdd(go.d_means + 3 * (size_t)g + 2, dmu[2]);
+        out.dq[0] = dq0; out.dq[1] = dq1; out.dq[2] = dq2; out.dq[3] = dq3;
     }
+    out.dsc[0] = dsc[0]; out.dsc[1] = dsc[1];
+    out.dmu[0] = dmu[0]; out.dmu[1] = dmu[1]; out.dmu[2] = dmu[2];
+}
+
+// scatter one hit's gradients with float reductions (backward.cu:659-675)
+__device__ __forceinline__ void hit_scatter(int g, const float* o, const float* d, const HitGeo& h, float w, float dalpha,
+                                            float g_d, const float* g_n, float* dcol, bool clamped0, const float* basis, int nb, int M,
+                                            const GradOut& go)
+{
+    HitGrads hv;
+    hit_vjp(o, d, h, w, dalpha, g_d, g_n, hv);
+    atomicAdd(go.d_opac + g, hv.d_opac);
+    if (go.vec) {
+        red_add_v2(go.d_scales + 2 * (size_t)g, hv.dsc[0], hv.dsc[1]);
+        red_add_v4(go.d_rots + 4 * (size_t)g, hv.dq[0], hv.dq[1], hv.dq[2], hv.dq[3]);
+    } else {
+        atomicAdd(go.d_scales + 2 * (size_t)g, hv.dsc[0]); atomicAdd(go.d_scales + 2 * (size_t)g + 1, hv.dsc[1]);
+        atomicAdd(go.d_rots + 4 * (size_t)g, hv.dq[0]); atomicAdd(go.d_rots + 4 * (size_t)g + 1, hv.dq[1]);
+        atomicAdd(go.d_rots + 4 * (size_t)g + 2, hv.dq[2]); atomicAdd(go.d_rots + 4 * (size_t)g + 3, hv.dq[3]);
+    }
+    atomicAdd(go.d_means + 3 * (size_t)g, hv.dmu[0]); atomicAdd(go.d_means + 3 * (size_t)g + 1, hv.dmu[1]);
+    atomicAdd(go.d_means + 3 * (size_t)g + 2, hv.dmu[2]);
     // computeColorFromSHBackward (:123-247): dL_dsh[j] = basis_j * dL_dcolour, channel 0 zero if clamped
     if (clamped0) dcol[0] = 0.0f;
     float* dsh = go.d_shs + (size_t)g * M * 3;
@@ -278,7 +292,7 @@ struct BwArgs {
     int D, M; float mod; const float* fwd_out; const float* dL; int flags;
     const int32_t* hit_gidx; const float* hit_t; const float4* hit_aux; const int32_t* hit_cnt; int cap;
     const int* order;                     // rays by descending hit count, or nullptr
-    const unsigned char* only;            // k_backward_list: if set, replay only the rays flagged here
+    const int* only_flag;                 // k_backward_list: if set, run only when the device flag is non-zero
     GradOut go;
 };
 
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(128) k_backward_list(BwArgs a)
     const int r = a.order ? a.order[s_] : s_;
     const int cnt = a.hit_cnt[r];
     if (cnt <= 0 || cnt > a.cap) return;                 // overflowed rays are handled by k_backward_trace
-    if (a.only && !a.only[r]) return;
+    if (a.only_flag && *a.only_flag == 0) return;
     const float o[3] = {a.ray_o[(size_t)r * a.ray_o_stride], a.ray_o[(size_t)r * a.ray_o_stride + 1], a.ray_o[(size_t)r * a.ray_o_stride + 2]};
     const float d[3] = {a.ray_d[3 * (size_t)r], a.ray_d[3 * (size_t)r + 1], a.ray_d[3 * (size_t)r + 2]};
     const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -310,36 +324,37 @@ __global__ void __launch_bounds__(128) k_backward_list(BwArgs a)
     }
 }
 
-// ---- two-pass replay (default when the forward recorded hit_aux) ----------------------------------------------
+// ---- grouped replay (default when the forward recorded hit_aux) -------------------------------------------------
 // The serial part of a ray's backward is tiny: transmittance and the running sums of w c, w depth (w n) in front
 // of each hit. With (alpha, colour) of every contributing hit recorded by the forward, that part needs no Gaussian
-// parameter at all. So:
-//   k_bw_offsets + scan : flat position of every ray's hits
-//   k_bw_prefix         : one thread per ray walks its recorded (depth, alpha, colour) and writes, per hit, the flat
-//                         record (g, ray, depth, w, dL/dalpha). ~30 flops and 24 B per hit, coalesced reads.
-//   k_bw_hits           : one thread per HIT, all independent: recompute the surfel frame, VJPs, reductions. Full
-//                         occupancy instead of 8 warps/SM each waiting on its own chain of gathers; the SH
-//                         coefficients are never read (their gradient only needs the basis and dL/dcolour).
-struct BwFlat { int2* a; float4* b; const int* off; int capacity; unsigned char* legacy; };
+// parameter at all. And the expensive part — VJPs and the scatter of 58 floats per hit — is bound by the L2's
+// reduction rate (18 x 16-byte red operations per hit, ~100 G/s measured), while every Gaussian is hit by several
+// neighbouring rays. So the hits are regrouped BY GAUSSIAN before they are scattered:
+//   k_bw_gcount + scan : hits per Gaussian -> first flat position of every Gaussian's group
+//   k_bw_prefix        : one thread per ray walks its recorded (depth, alpha, colour) and drops, per hit, the record
+//                        (g, ray, depth, w, dL/dalpha) into the Gaussian's group. ~30 flops and 24 B per hit.
+//   k_bw_hits          : one thread per record, all independent: recompute the surfel frame, VJPs; lanes holding the
+//                        same Gaussian are neighbours, so a segmented warp reduction leaves ONE set of reductions per
+//                        (Gaussian, warp). Parameter loads coalesce for the same reason, and the SH coefficients are
+//                        never read (their gradient only needs the basis and dL/dcolour).
+struct BwFlat { int2* a; float4* b; int* gcnt; const int* goff; int P; int capacity; int* legacy_flag; };
 
-__global__ void __launch_bounds__(256) k_bw_offsets(int R, const int32_t* __restrict__ hit_cnt, int cap, int* __restrict__ cnt_eff)
+__global__ void __launch_bounds__(128) k_bw_gcount(BwArgs a, int* __restrict__ gcnt)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > R) return;
-    int c = 0;
-    if (r < R) { c = hit_cnt[r]; if (c <= 0 || c > cap) c = 0; }
-    cnt_eff[r] = c;                                       // entry R stays 0: the scan's last output is the total
+    if (r >= a.R) return;
+    const int cnt = a.hit_cnt[r];
+    if (cnt <= 0 || cnt > a.cap) return;                  // overflowed rays are handled by k_backward_trace
+    for (int k = 0; k < cnt; k++) atomicAdd(gcnt + a.hit_gidx[(size_t)k * a.R + r], 1);
 }
 
 __global__ void __launch_bounds__(128) k_bw_prefix(BwArgs a, BwFlat f)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.R) return;
-    f.legacy[r] = 0;
+    if (f.goff[f.P] > f.capacity) { if (r == 0) *f.legacy_flag = 1; return; }      // records do not fit: serial replay of everything
     const int cnt = a.hit_cnt[r];
-    if (cnt <= 0 || cnt > a.cap) return;                  // overflowed rays are handled by k_backward_trace
-    const int off = f.off[r];
-    if (off + cnt > f.capacity) { f.legacy[r] = 1; return; }     // flat buffers full: this ray is replayed serially
+    if (cnt <= 0 || cnt > a.cap) return;
     const float bg[3] = {a.bg[0], a.bg[1], a.bg[2]};
     RayState st;
     ray_state_init(st, r, a.fwd_out, a.dL);
@@ -349,6 +364,7 @@ __global__ void __launch_bounds__(128) k_bw_prefix(BwArgs a, BwFlat f)
         const int g = a.hit_gidx[at];
         const float dpt = a.hit_t[at];
         const float4 ax = a.hit_aux[at];
+        const int pos = f.goff[g] + atomicSub(f.gcnt + g, 1) - 1;          // a free slot of g's group (order within a group is irrelevant)
         const float c[3] = {ax.y, ax.z, ax.w};
         float n[3] = {0.f, 0.f, 0.f};
         if (need_n) {                                      // the normal prefix only matters then; same arithmetic as derive_surfel
@@ -361,35 +377,96 @@ __global__ void __launch_bounds__(128) k_bw_prefix(BwArgs a, BwFlat f)
         float w;
         const float dalpha = hit_state(st, ax.x, c, n, dpt, bg, a.flags, w);
         const unsigned clamp = __float_as_uint(ax.y) & 0x80000000u;        // c0 == -0.0: channel 0 was clamped
-        f.a[off + k] = make_int2(g, (int)((unsigned)r | clamp));
-        f.b[off + k] = make_float4(dpt, w, dalpha, 0.0f);
+        f.a[pos] = make_int2(g, (int)((unsigned)r | clamp));
+        f.b[pos] = make_float4(dpt, w, dalpha, 0.0f);
     }
+}
+
+// sum of v over the lanes to the right that hold the same Gaussian (equal ids are contiguous): lane i ends up with the
+// total of [i, end of its segment]; `same` bit s = lane + 2^s is in range and holds the same id
+__device__ __forceinline__ float seg_sum(float v, unsigned same)
+{
+#pragma unroll
+    for (int s = 0; s < 5; s++) { const float o = __shfl_down_sync(0xffffffffu, v, 1 << s); if (same & (1u << s)) v += o; }
+    return v;
 }
 
 __global__ void __launch_bounds__(256) k_bw_hits(BwArgs a, BwFlat f)
 {
-    const int n = min(f.off[a.R], f.capacity);
+    const unsigned FULL = 0xffffffffu;
+    const int n = f.goff[f.P];
+    if (n > f.capacity) return;
     const int nb = (a.D + 1) * (a.D + 1);
-    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x) {
-        const int2 ra = f.a[h];
-        const float4 rb = f.b[h];
-        const int g = ra.x, r = ra.y & 0x7fffffff;
-        const bool clamped0 = ra.y < 0;
-        const float o[3] = {a.ray_o[(size_t)r * a.ray_o_stride], a.ray_o[(size_t)r * a.ray_o_stride + 1], a.ray_o[(size_t)r * a.ray_o_stride + 2]};
-        const float d[3] = {a.ray_d[3 * (size_t)r], a.ray_d[3 * (size_t)r + 1], a.ray_d[3 * (size_t)r + 2]};
-        const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        const float dirn[3] = {d[0] / dl, d[1] / dl, d[2] / dl};
-        const float* gl = a.dL + (size_t)LRT_NCH * r;
-        const float g_n[3] = {gl[5], gl[6], gl[7]};
-        const float w = rb.y;
-        float dcol[3] = {gl[0] * w, gl[1] * w, gl[2] * w};
-        HitGeo hg;
-        hit_geo(g, rb.x, o, d, a.means, a.scales, a.rots, a.opac, a.mod, hg);
-        float basis[16];
-        sh_basis(a.D, dirn, basis);
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
+        const int h = base + lane;
+        int g = -1 - lane;                                 // inactive lanes: distinct ids, never equal to a neighbour
+        HitGrads hv; hv.d_opac = 0.f; hv.dmu[0] = hv.dmu[1] = hv.dmu[2] = 0.f; hv.dsc[0] = hv.dsc[1] = 0.f; hv.dq[0] = hv.dq[1] = hv.dq[2] = hv.dq[3] = 0.f;
+        float dcol[3] = {0.f, 0.f, 0.f}, basis[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) if (j >= nb) basis[j] = 0.0f;
-        hit_scatter(g, o, d, hg, w, rb.z, gl[3], g_n, dcol, clamped0, basis, nb, a.M, a.go);
+        for (int j = 0; j < 16; j++) basis[j] = 0.0f;
+        if (h < n) {
+            const int2 ra = f.a[h];
+            const float4 rb = f.b[h];
+            g = ra.x;
+            const int r = ra.y & 0x7fffffff;
+            const float o[3] = {a.ray_o[(size_t)r * a.ray_o_stride], a.ray_o[(size_t)r * a.ray_o_stride + 1], a.ray_o[(size_t)r * a.ray_o_stride + 2]};
+            const float d[3] = {a.ray_d[3 * (size_t)r], a.ray_d[3 * (size_t)r + 1], a.ray_d[3 * (size_t)r + 2]};
+            const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            const float dirn[3] = {d[0] / dl, d[1] / dl, d[2] / dl};
+            const float* gl = a.dL + (size_t)LRT_NCH * r;
+            const float g_n[3] = {gl[5], gl[6], gl[7]};
+            const float w = rb.y;
+            dcol[0] = (ra.y < 0) ? 0.0f : gl[0] * w; dcol[1] = gl[1] * w; dcol[2] = gl[2] * w;     // channel 0 clamped: no SH gradient (:134)
+            HitGeo hg;
+            hit_geo(g, rb.x, o, d, a.means, a.scales, a.rots, a.opac, a.mod, hg);
+            sh_basis(a.D, dirn, basis);
+#pragma unroll
+            for (int j = 0; j < 16; j++) if (j >= nb) basis[j] = 0.0f;
+            hit_vjp(o, d, hg, w, rb.z, gl[3], g_n, hv);
+        }
+        // segment structure of this warp's 32 records
+        unsigned same = 0;
+#pragma unroll
+        for (int s = 0; s < 5; s++) { const int og = __shfl_down_sync(FULL, g, 1 << s); if (lane + (1 << s) < 32 && og == g) same |= 1u << s; }
+        const int pg = __shfl_up_sync(FULL, g, 1);
+        const bool head = (h < n) && (lane == 0 || pg != g);
+        const GradOut& go = a.go;
+        {
+            const float t0 = seg_sum(hv.d_opac, same);
+            const float m0 = seg_sum(hv.dmu[0], same), m1 = seg_sum(hv.dmu[1], same), m2 = seg_sum(hv.dmu[2], same);
+            const float s0 = seg_sum(hv.dsc[0], same), s1 = seg_sum(hv.dsc[1], same);
+            const float q0 = seg_sum(hv.dq[0], same), q1 = seg_sum(hv.dq[1], same), q2 = seg_sum(hv.dq[2], same), q3 = seg_sum(hv.dq[3], same);
+            if (head) {
+                atomicAdd(go.d_opac + g, t0);
+                atomicAdd(go.d_means + 3 * (size_t)g, m0); atomicAdd(go.d_means + 3 * (size_t)g + 1, m1); atomicAdd(go.d_means + 3 * (size_t)g + 2, m2);
+                if (go.vec) { red_add_v2(go.d_scales + 2 * (size_t)g, s0, s1); red_add_v4(go.d_rots + 4 * (size_t)g, q0, q1, q2, q3); }
+                else {
+                    atomicAdd(go.d_scales + 2 * (size_t)g, s0); atomicAdd(go.d_scales + 2 * (size_t)g + 1, s1);
+                    atomicAdd(go.d_rots + 4 * (size_t)g, q0); atomicAdd(go.d_rots + 4 * (size_t)g + 1, q1);
+                    atomicAdd(go.d_rots + 4 * (size_t)g + 2, q2); atomicAdd(go.d_rots + 4 * (size_t)g + 3, q3);
+                }
+            }
+        }
+        // SH: dL_dsh[j][ch] = basis_j dL_dcolour[ch], four contiguous floats at a time
+        float* dsh = go.d_shs + (size_t)(g < 0 ? 0 : g) * a.M * 3;
+        const int nf = 3 * nb;
+        const bool vec = go.vec && (a.M & 3) == 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            if (4 * i < nf) {                              // warp-uniform
+                float vals[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) { const int idx = 4 * i + e; vals[e] = seg_sum(basis[idx / 3] * dcol[idx % 3], same); }
+                if (head) {
+                    if (vec && 4 * i + 3 < nf) red_add_v4(dsh + 4 * i, vals[0], vals[1], vals[2], vals[3]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) if (4 * i + e < nf) atomicAdd(dsh + 4 * i + e, vals[e]);
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -550,7 +627,7 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
     a.means = means; a.scales = scales; a.rots = rots; a.opac = opac; a.shs = shs;
     a.D = D; a.M = M; a.mod = mod; a.fwd_out = fwd_out; a.dL = dL_dout; a.flags = flags;
     a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_aux = reinterpret_cast<const float4*>(hit_aux); a.hit_cnt = hit_cnt; a.cap = cap;
-    a.order = nullptr; a.only = nullptr;
+    a.order = nullptr; a.only_flag = nullptr;
     a.go.d_means = dL_dmeans; a.go.d_shs = dL_dshs; a.go.d_opac = dL_dopac; a.go.d_scales = dL_dscales; a.go.d_rots = dL_drots;
     a.go.vec = ctx->opt_vector_atomics && (reinterpret_cast<uintptr_t>(dL_dshs) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(dL_drots) & 15) == 0 && (reinterpret_cast<uintptr_t>(dL_dscales) & 7) == 0;
@@ -563,30 +640,31 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
             ctx->num_sms = sms > 0 ? sms : 148;
         }
         if (ctx->opt_backward_kernel == 2 && hit_aux && (reinterpret_cast<uintptr_t>(hit_aux) & 15) == 0) {
-            // two passes: per-ray prefix over the recorded (alpha, colour), then one thread per hit
+            // grouped replay: hits regrouped by Gaussian, per-ray prefix pass, one thread per hit + segmented reduction
+            long long want = (long long)R * 64; if (want < (1LL << 20)) want = 1LL << 20;
             const long long worst = (long long)R * cap;
-            const long long capacity_ll = worst < ((long long)R * 64 > (1LL << 20) ? (long long)R * 64 : (1LL << 20)) ? worst
-                                          : ((long long)R * 64 > (1LL << 20) ? (long long)R * 64 : (1LL << 20));
-            const int capacity = (int)(capacity_ll > 0x7fffff00LL ? 0x7fffff00LL : capacity_ll);
-            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_off, sizeof(int) * 2 * ((size_t)R + 1)));
+            if (want > worst) want = worst;
+            const int capacity = (int)(want > 0x7fffff00LL ? 0x7fffff00LL : want);
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_off, sizeof(int) * 2 * ((size_t)P + 1) + 64));
             LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_rec_a, sizeof(int2) * (size_t)capacity));
             LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_rec_b, sizeof(float4) * (size_t)capacity));
-            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_legacy, (size_t)R));
-            int* cnt_eff = (int*)ctx->bw_off.p; int* off = cnt_eff + (R + 1);
+            int* gcnt = (int*)ctx->bw_off.p; int* goff = gcnt + (P + 1); int* legacy_flag = goff + (P + 1);
             size_t tb = 0;
-            LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)cnt_eff, off, R + 1, s));
+            LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)gcnt, goff, P + 1, s));
             LRT_CUDA_TRY(ctx, ctx->reserve(ctx->bw_sort_tmp, tb));
+            LRT_CUDA_TRY(ctx, cudaMemsetAsync(gcnt, 0, sizeof(int) * ((size_t)P + 1), s));
+            LRT_CUDA_TRY(ctx, cudaMemsetAsync(legacy_flag, 0, sizeof(int), s));
             BwFlat f;
-            f.a = (int2*)ctx->bw_rec_a.p; f.b = (float4*)ctx->bw_rec_b.p; f.off = off; f.capacity = capacity; f.legacy = (unsigned char*)ctx->bw_legacy.p;
-            ctx->span_begin("k_bw_prefix", s);
-            k_bw_offsets<<<(R + 256) / 256, 256, 0, s>>>(R, hit_cnt, cap, cnt_eff);
-            LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->bw_sort_tmp.p, tb, (const int*)cnt_eff, off, R + 1, s));
-            k_bw_prefix<<<GB, TB, 0, s>>>(a, f);
+            f.a = (int2*)ctx->bw_rec_a.p; f.b = (float4*)ctx->bw_rec_b.p; f.gcnt = gcnt; f.goff = goff; f.P = P; f.capacity = capacity; f.legacy_flag = legacy_flag;
+            ctx->span_begin("k_bw_gcount", s);
+            k_bw_gcount<<<GB, TB, 0, s>>>(a, gcnt);
+            LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->bw_sort_tmp.p, tb, (const int*)gcnt, goff, P + 1, s));
             ctx->span_end(s);
+            ctx->span_begin("k_bw_prefix", s); k_bw_prefix<<<GB, TB, 0, s>>>(a, f); ctx->span_end(s);
             ctx->span_begin("k_bw_hits", s); k_bw_hits<<<ctx->num_sms * 8, 256, 0, s>>>(a, f); ctx->span_end(s);
-            a.only = f.legacy;                        // rays that did not fit the flat buffers (normally none)
+            a.only_flag = legacy_flag;                // set on the device if the records did not fit (normally not)
             ctx->span_begin("k_backward_list", s); k_backward_list<<<GB, TB, 0, s>>>(a); ctx->span_end(s);
-            ctx->launches += 5;
+            ctx->launches += 6;
         } else if (ctx->opt_backward_kernel == 1) {
             if (ctx->num_sms == 0) {
                 int sms = 0;

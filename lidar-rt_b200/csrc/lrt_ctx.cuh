@@ -28,7 +28,7 @@ struct lrt_ctx {
     DevBuf leafq;
     DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, iperm, sort_tmp, bounds, counter;
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
-    DevBuf bw_off, bw_rec_a, bw_rec_b, bw_legacy;   // hit-parallel backward (lrt_backward.cu)
+    DevBuf bw_off, bw_rec_a, bw_rec_b;   // hit-parallel backward (lrt_backward.cu)
     DevBuf bg_ang, bg_cell_of, bg_cells, bg_sray, bg_wide, bg_plan;   // shared-origin beam grid (lrt_beamgrid.cuh)
     // options (lrt_set_option)
     int opt_forward_kernel = 4;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray, 3: wavefront,
@@ -92,7 +92,7 @@ struct lrt_ctx {
         return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + iperm.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
                bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
-               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + bw_legacy.cap;
+               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap;
     }
     BvhView view() const
     {
