@@ -359,11 +359,15 @@ __global__ void __launch_bounds__(128) k_bw_prefix(BwArgs a, BwFlat f)
     RayState st;
     ray_state_init(st, r, a.fwd_out, a.dL);
     const bool need_n = st.g_n[0] != 0.0f || st.g_n[1] != 0.0f || st.g_n[2] != 0.0f;    // dL/dnormal is zero in practice (train.py never feeds it)
+    int g_nx = a.hit_gidx[r]; float t_nx = a.hit_t[r]; float4 ax_nx = a.hit_aux[r];
     for (int k = 0; k < cnt; k++) {
-        const size_t at = (size_t)k * a.R + r;
-        const int g = a.hit_gidx[at];
-        const float dpt = a.hit_t[at];
-        const float4 ax = a.hit_aux[at];
+        const int g = g_nx;
+        const float dpt = t_nx;
+        const float4 ax = ax_nx;
+        if (k + 1 < cnt) {                                 // next hit's record: in flight while this one is folded
+            const size_t at = (size_t)(k + 1) * a.R + r;
+            g_nx = a.hit_gidx[at]; t_nx = a.hit_t[at]; ax_nx = a.hit_aux[at];
+        }
         const int pos = f.goff[g] + atomicSub(f.gcnt + g, 1) - 1;          // a free slot of g's group (order within a group is irrelevant)
         const float c[3] = {ax.y, ax.z, ax.w};
         float n[3] = {0.f, 0.f, 0.f};

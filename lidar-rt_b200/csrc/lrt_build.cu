@@ -10,8 +10,8 @@
 //                (32-bit cubic-cell keys by default; 30-bit and 63-bit Morton selectable)
 //   cub radix  : sort (key, index) pairs, 8 bits per pass
 //   k_records  : gather raw parameters through the permutation, derive the surfel frame,
-//                write the 64 B record in Morton order and the padded quad AABB into its
-//                level-0 node slot                              read 40 B, write 64 + 24 B
+//                write the 64 B record in Morton order (and once more by caller id) and the padded
+//                quad AABB into its level-0 node slot           read 40 B, write 2 x 64 + 24 B
 //   k_fit      : one launch per upper level: child box = union of the child's 8 boxes
 // The hierarchy is IMPLICIT: level l node j has children 8j..8j+7 of level l-1 (level 0: surfels),
 // so there are no child pointers, a refit is k_records + k_fit with the stored permutation, and
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
                                                  const float* __restrict__ means, const float* __restrict__ scales,
                                                  const float* __restrict__ rots, const float* __restrict__ opac,
                                                  float mod, SurfelRec* __restrict__ rec, Node8* __restrict__ leaf,
-                                                 int* __restrict__ iperm, LeafQ* __restrict__ leafq)
+                                                 SurfelRec* __restrict__ rec_g, LeafQ* __restrict__ leafq)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P_pad) return;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
         r.r2 = make_float4(d.Lv[0], d.Lv[1], d.Lv[2], __int_as_float(g));
         r.r3 = make_float4(d.n[0], d.n[1], d.n[2], 0.0f);
         rec[i] = r;
-        iperm[g] = i;
+        rec_g[g] = r;
         const bool valid = (d.f == d.f) && d.f >= 0.0f && d.f < 1e30f;
         if (valid) {
             const float ax = mod * d.sx * d.f, ay = mod * d.sy * d.f;
@@ -294,7 +294,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->rec, sizeof(SurfelRec) * (size_t)P_pad));
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->nodes, sizeof(Node8) * (size_t)total));
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->perm_a, sizeof(unsigned) * (size_t)P));
-    LRT_CUDA_TRY(ctx, ctx->reserve(ctx->iperm, sizeof(int) * (size_t)P));
+    LRT_CUDA_TRY(ctx, ctx->reserve(ctx->rec_g, sizeof(SurfelRec) * (size_t)P));
     LRT_CUDA_TRY(ctx, ctx->reserve(ctx->leafq, sizeof(LeafQ) * (size_t)(P_pad / 8)));
     const int TB = 256;
     if (!refit) {
@@ -340,7 +340,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
     }
     Node8* nodes = (Node8*)ctx->nodes.p;
     ctx->span_begin("k_records", s); k_records<<<(P_pad + TB - 1) / TB, TB, 0, s>>>(P, P_pad, (const unsigned*)ctx->perm_a.p, means, scales, rots, opac,
-                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0], (int*)ctx->iperm.p, (LeafQ*)ctx->leafq.p); ctx->span_end(s);
+                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0], (SurfelRec*)ctx->rec_g.p, (LeafQ*)ctx->leafq.p); ctx->span_end(s);
     for (int l = 1; l < L; l++) {
         ctx->span_begin("k_fit", s);
         k_fit<<<(cnt[l] * 8 + TB - 1) / TB, TB, 0, s>>>(cnt[l], cnt[l - 1], nodes + off[l - 1], nodes + off[l]);

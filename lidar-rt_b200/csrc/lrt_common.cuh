@@ -58,7 +58,8 @@ struct __align__(16) LeafQ {
 struct BvhView {
     const SurfelRec* rec;         // (P_pad)
     const Node8* nodes;           // all levels, level 0 (children = surfels) first
-    const int* iperm;             // (P) caller's Gaussian index -> position in Morton order
+    const SurfelRec* rec_g;       // (P) the same records indexed by the caller's Gaussian id (compositing gathers by id: no
+                                  // id -> Morton position lookup in front of every record fetch)
     const LeafQ* leafq;           // (P_pad / 8) compact level-0 nodes
     int level_off[LRT_MAX_LEVELS];
     int levels;

@@ -26,7 +26,7 @@ struct lrt_ctx {
     bool built = false;
     float scale_modifier = 1.0f;
     DevBuf leafq;
-    DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, iperm, sort_tmp, bounds, counter;
+    DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, rec_g, sort_tmp, bounds, counter;
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
     DevBuf bw_off, bw_rec_a, bw_rec_b;   // hit-parallel backward (lrt_backward.cu)
     DevBuf bg_ang, bg_cell_of, bg_cells, bg_sray, bg_wide, bg_plan;   // shared-origin beam grid (lrt_beamgrid.cuh)
@@ -89,7 +89,7 @@ struct lrt_ctx {
     }
     size_t total_bytes() const
     {
-        return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + iperm.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
+        return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
                bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
                bw_off.cap + bw_rec_a.cap + bw_rec_b.cap;
@@ -99,7 +99,7 @@ struct lrt_ctx {
         BvhView v;
         v.rec = (const SurfelRec*)rec.p;
         v.nodes = (const Node8*)nodes.p;
-        v.iperm = (const int*)iperm.p;
+        v.rec_g = (const SurfelRec*)rec_g.p;
         v.leafq = (const LeafQ*)leafq.p;
         for (int i = 0; i < LRT_MAX_LEVELS; i++) v.level_off[i] = level_off[i];
         v.levels = levels;

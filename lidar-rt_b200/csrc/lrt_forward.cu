@@ -74,9 +74,8 @@ __device__ __forceinline__ bool fwd_shade_round(FwdRay& q, const unsigned long l
         // (the 1e-5 step is below one ulp of the depth beyond 128 m): it must not composite twice
         if (g == q.last) continue;
         q.last = g;
-        const int prim = __ldg(bvh.iperm + g);
-        const float4 a0 = ld_f4(&bvh.rec[prim].r0), a1 = ld_f4(&bvh.rec[prim].r1);
-        const float4 a2 = ld_f4(&bvh.rec[prim].r2), a3 = ld_f4(&bvh.rec[prim].r3);
+        const float4 a0 = ld_f4(&bvh.rec_g[g].r0), a1 = ld_f4(&bvh.rec_g[g].r1);
+        const float4 a2 = ld_f4(&bvh.rec_g[g].r2), a3 = ld_f4(&bvh.rec_g[g].r3);
         const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
         const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;                        // :139
         const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
@@ -91,9 +90,14 @@ __device__ __forceinline__ bool fwd_shade_round(FwdRay& q, const unsigned long l
         q.testT = q.T * (1.0f - alpha);
         if (q.testT < LRT_T_MIN) { terminated = true; break; }                    // :253-257
         const float w = alpha * q.T;
-        float sh[48], c[3]; bool cl;
-        load_sh(a.shs, g, a.M, nb, sh);
-        sh_colour<false>(a.D, q.dirn, sh, c, cl, nullptr);
+        float c[3];
+        if ((a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)) {
+            sh_colour_stream(a.D, q.dirn, a.shs + (size_t)g * a.M * 3, c);        // same sums in the same order, no 48-float staging
+        } else {
+            float sh[48]; bool cl;
+            load_sh(a.shs, g, a.M, nb, sh);
+            sh_colour<false>(a.D, q.dirn, sh, c, cl, nullptr);
+        }
         q.C0 += w * c[0]; q.C1 += w * c[1]; q.C2 += w * c[2];
         q.Dp += w * q.dpt; q.W += w;
         atomicAdd(a.accum_w + g, w);                                              // :272
@@ -308,9 +312,8 @@ __device__ __forceinline__ void g8_shade_slot(unsigned long long key, bool valid
     if (o.dpt < LRT_MIN_T) return;                                                // :214
     o.flags |= G8_F_DPT_OK;
     const float x0 = q.o[0] + o.dpt * q.d[0], x1 = q.o[1] + o.dpt * q.d[1], x2 = q.o[2] + o.dpt * q.d[2];
-    const int prim = __ldg(bvh.iperm + g);
-    const float4 a0 = ld_f4(&bvh.rec[prim].r0), a1 = ld_f4(&bvh.rec[prim].r1);
-    const float4 a2 = ld_f4(&bvh.rec[prim].r2), a3 = ld_f4(&bvh.rec[prim].r3);
+    const float4 a0 = ld_f4(&bvh.rec_g[g].r0), a1 = ld_f4(&bvh.rec_g[g].r1);
+    const float4 a2 = ld_f4(&bvh.rec_g[g].r2), a3 = ld_f4(&bvh.rec_g[g].r3);
     const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
     const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;                            // :139
     const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;

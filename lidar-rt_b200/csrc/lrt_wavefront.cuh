@@ -181,6 +181,27 @@ __device__ __forceinline__ unsigned long long warp_sort32(unsigned long long k, 
     return k;
 }
 
+// warp-wide bitonic sort of 64 keys, two per lane: k0 = element `lane`, k1 = element `lane + 32` (ascending)
+__device__ __forceinline__ void warp_sort64(unsigned long long& k0, unsigned long long& k1, int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride == 32) {                            // partner is the lane's own second key; elements 0..63 all sort upwards here
+                const unsigned long long lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
+                k0 = lo; k1 = hi;
+            } else {
+                const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, stride), o1 = __shfl_xor_sync(0xffffffffu, k1, stride);
+                const bool lower = ((lane & stride) == 0);
+                const bool up0 = ((lane & size) == 0), up1 = (((lane + 32) & size) == 0);
+                k0 = (lower == up0) ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
+                k1 = (lower == up1) ? (k1 < o1 ? k1 : o1) : (k1 < o1 ? o1 : k1);
+            }
+        }
+    }
+}
+
 // One warp per ray. smem: 4 warps x WF_HCAP keys (16 KB).
 #ifndef LRT_SHADE_MIN_BLOCKS
 #define LRT_SHADE_MIN_BLOCKS 4
@@ -249,7 +270,7 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
                     if (idx < n) {
                         const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
                         float t; int g2;
-                        if (quad_hit(bvh.rec, __ldg(bvh.iperm + g), rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                        if (quad_hit(bvh.rec_g, g, rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
                     }
                     const unsigned vm = __ballot_sync(FULL, nk != LRT_KEY_EMPTY);
                     const int want = lane - have;                                   // lane takes the want-th valid key of this window
@@ -292,7 +313,7 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
                     if (idx < n) {
                         const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
                         float t; int g2;
-                        if (quad_hit(bvh.rec, __ldg(bvh.iperm + g), rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                        if (quad_hit(bvh.rec_g, g, rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
                     }
                     nk = warp_sort32(nk, lane);
                     const unsigned long long rev = __shfl_sync(FULL, nk, 31 - lane);      // bitonic merge: 32 smallest of best U nk
@@ -372,7 +393,14 @@ __global__ void __launch_bounds__(128) k_wf_sort(FwdArgs a, WfBufs w)
             if (lane < n) bin[lane] = k;
             continue;
         }
-        int m = 64; while (m < n) m <<= 1;
+        if (n <= 64) {                                             // two keys per lane: still registers only
+            unsigned long long k0 = bin[lane], k1 = lane + 32 < n ? bin[lane + 32] : LRT_KEY_EMPTY;
+            warp_sort64(k0, k1, lane);
+            bin[lane] = k0;
+            if (lane + 32 < n) bin[lane + 32] = k1;
+            continue;
+        }
+        int m = 128; while (m < n) m <<= 1;
         // shared memory for the common sizes; the few bins beyond WF_HCAP are sorted in place in global memory
         // (padding entries up to m live in the bin itself: m <= hcap because hcap is a power of two)
         unsigned long long* buf = (m <= WF_HCAP) ? keys : bin;
@@ -395,7 +423,10 @@ __global__ void __launch_bounds__(128) k_wf_sort(FwdArgs a, WfBufs w)
     }
 }
 
-__global__ void __launch_bounds__(128) k_wf_composite(BvhView bvh, FwdArgs a, WfBufs w)
+#ifndef LRT_COMPOSITE_MIN_BLOCKS
+#define LRT_COMPOSITE_MIN_BLOCKS 3      // 156 registers, no spills; 4-6 blocks were measured slower (spills in the round loop)
+#endif
+__global__ void __launch_bounds__(128, LRT_COMPOSITE_MIN_BLOCKS) k_wf_composite(BvhView bvh, FwdArgs a, WfBufs w)
 {
     // with `order`, a warp's 32 rays have (nearly) equal candidate counts: the per-ray loops below stay in step
     const int S = w.order ? a.R : num_slots(a.R, a.grid_w);
@@ -418,15 +449,22 @@ __global__ void __launch_bounds__(128) k_wf_composite(BvhView bvh, FwdArgs a, Wf
             while (pos < n && __uint_as_float((unsigned)(bin[pos] >> 32)) < thr) pos++;
             unsigned long long kb[LRT_KBUF];
             int cnt = 0;
+            unsigned long long ck_next = pos < n ? bin[pos] : 0ull;
             for (int i = pos; i < n; i++) {
-                const unsigned long long ck = bin[i];
+                const unsigned long long ck = ck_next;
+                if (i + 1 < n) ck_next = bin[i + 1];                                       // one ahead: its latency hides behind this test
                 if (cnt == LRT_KBUF) {
                     const float t16 = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32)) + q.base;
                     if (__uint_as_float((unsigned)(ck >> 32)) - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) break;
                 }
                 const int g = (int)(unsigned)(ck & 0xffffffffull);
                 float t; int g2;
-                if (!quad_hit(bvh.rec, __ldg(bvh.iperm + g), rs, t, g2)) continue;
+                if (!quad_hit(bvh.rec_g, g, rs, t, g2)) continue;
+                {   // a slot of this round: most slots composite, so start pulling its SH row (two 128 B lines at D = 3) into L2 now
+                    const char* row = reinterpret_cast<const char*>(a.shs + (size_t)g * a.M * 3);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                    if (a.D >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+                }
                 const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
                 if (cnt == LRT_KBUF) { if (key >= kb[LRT_KBUF - 1]) continue; cnt--; }      // replaces the current 16th
                 int j = cnt;
