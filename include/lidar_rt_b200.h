@@ -98,6 +98,37 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
                  float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
                  float* dL_drots, int flags, void* stream);
 
+/* ---- the step above the tracer: parameter activation + world transform + concatenation, fused ----
+ * Replaces, in lib/gaussian_renderer/__init__.py:76-134, the per-asset accessor calls of the reference's GaussianModel
+ * (lib/scene/gaussian_model.py:112-148: exp / sigmoid / normalize, xyz @ R^T + T, cat(features_dc, features_rest)),
+ * the quaternion composition of dynamic scenes (general_utils.py:156-174) and the torch.cat over assets.
+ * One lrt_asset per GaussianModel, in concatenation order (background first). All pointers are device pointers. */
+#define LRT_MAX_ASSETS 128
+typedef struct lrt_asset {
+    int32_t P;                    /* Gaussians of this asset */
+    int32_t compose_rotation;     /* 0: rotations = normalize(rotation)                       (:117-118, static scene / background)
+                                     1: rotations = pose_quat (x) normalize(normalize(rotation))  (:119-130, actors of a dynamic scene) */
+    const float* xyz;             /* (P,3)   _xyz            local frame */
+    const float* scaling;         /* (P,2)   _scaling        log-scale, 8-byte aligned */
+    const float* rotation;        /* (P,4)   _rotation       raw quaternion (w first), 16-byte aligned */
+    const float* opacity;         /* (P,1)   _opacity        logit */
+    const float* features_dc;     /* (P,1,3) _features_dc */
+    const float* features_rest;   /* (P,M-1,3) _features_rest */
+    const float* pose_T;          /* (3) translation of BoundingBox.frame[t], or NULL: world xyz = xyz (gaussian_model.py:133-138) */
+    const float* pose_quat;       /* (4) quaternion of BoundingBox.frame[t] (R = build_rotation(q)), or NULL */
+    /* lrt_prepare_backward only: where the leaf gradients go (each may be NULL = not wanted); written, not accumulated */
+    float* d_xyz; float* d_scaling; float* d_rotation; float* d_opacity; float* d_features_dc; float* d_features_rest;
+} lrt_asset;
+
+/* assets: HOST array of n_assets descriptors. Outputs (device, Ptot = sum of P): means (Ptot,3), scales (Ptot,2) 8-byte aligned,
+ * rots (Ptot,4) 16-byte aligned, opac (Ptot), shs (Ptot,M,3) — exactly what lrt_build / lrt_forward take. */
+int lrt_prepare(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, float* means, float* scales, float* rots,
+                float* opac, float* shs, void* stream);
+/* VJP of lrt_prepare: gradients w.r.t. its five outputs in, leaf gradients out through the d_* pointers of the assets.
+ * No gradient flows to the poses (plain tensors in the reference). */
+int lrt_prepare_backward(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, const float* dL_dmeans,
+                         const float* dL_dscales, const float* dL_drots, const float* dL_dopac, const float* dL_dshs, void* stream);
+
 /* Tuning knobs; none of them changes results.
  *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill, 2 = 8 lanes per ray,
  *                           3 = breadth-first wavefront through the hierarchy + per-ray sort + compositing,

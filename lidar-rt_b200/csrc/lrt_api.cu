@@ -88,6 +88,20 @@ int lrt_backward(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, cons
                              dL_dmeans, dL_dshs, dL_dopac, dL_dscales, dL_drots, flags, (cudaStream_t)stream);
 }
 
+int lrt_prepare(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, float* means, float* scales, float* rots,
+                float* opac, float* shs, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_prepare_impl(ctx, n_assets, assets, M, means, scales, rots, opac, shs, (cudaStream_t)stream);
+}
+
+int lrt_prepare_backward(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, const float* dL_dmeans,
+                         const float* dL_dscales, const float* dL_drots, const float* dL_dopac, const float* dL_dshs, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_prepare_backward_impl(ctx, n_assets, assets, M, dL_dmeans, dL_dscales, dL_drots, dL_dopac, dL_dshs, (cudaStream_t)stream);
+}
+
 int lrt_set_option(lrt_ctx* ctx, int option, int value)
 {
     if (!ctx) return LRT_ERR_INVALID;

@@ -123,3 +123,7 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
                       const int32_t* hit_gidx, const float* hit_t, const float* hit_aux, const int32_t* hit_cnt, int cap,
                       float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
                       float* dL_drots, int flags, cudaStream_t s);
+int lrt_prepare_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, float* means, float* scales, float* rots,
+                     float* opac, float* shs, cudaStream_t s);
+int lrt_prepare_backward_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, const float* g_means, const float* g_scales,
+                              const float* g_rots, const float* g_opac, const float* g_shs, cudaStream_t s);

@@ -16,6 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from diff_lidar_tracer import Tracer, TracingSettings
+from lidar_rt_b200.prepare import fused_prepare
 
 tracer_2dgs = Tracer()              # module-global, constructed at import like the reference (:11)
 
@@ -33,6 +34,34 @@ def quaternion_raw_multiply(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 def _arg(args, group, name, default):
     g = getattr(args, group, None) if args is not None else None
     return getattr(g, name, default) if g is not None else default
+
+
+def _assemble(frame, gaussian_assets, dynamic, decomp):
+    """The reference's accessor loop and concatenations (:76-134), op for op."""
+    all_means, all_opac, all_scales, all_shs, obj_rot, rot_local = [], [], [], [], [], []
+    for pc in gaussian_assets:
+        all_means.append(pc.get_world_xyz(frame))
+        all_opac.append(pc.get_opacity)
+        all_scales.append(pc.get_scaling)
+        r1, r2 = pc.get_rotation(frame)
+        obj_rot.append(r1.expand(r2.shape[0], -1))
+        rot_local.append(r2)
+        all_shs.append(pc.get_features)
+    _cat = lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs, 0)      # one asset: no 232 B/Gaussian copy (+ its backward)
+    means3D = _cat(all_means)
+    opacity = _cat(all_opac)
+    scales = _cat(all_scales)
+    shs = _cat(all_shs)
+    if decomp == "background" or not dynamic:                      # reference :117-130
+        rotations = rot_local[0] if len(rot_local) == 1 else torch.cat(rot_local, 0)
+    elif decomp == "object":
+        rotations = quaternion_raw_multiply(torch.cat(obj_rot, 0), F.normalize(torch.cat(rot_local, 0), dim=1))
+    else:
+        rot_act = quaternion_raw_multiply(torch.cat(obj_rot[1:], 0), F.normalize(torch.cat(rot_local[1:], 0), dim=1)) \
+            if len(rot_local) > 1 else rot_local[0][:0]
+        rotations = torch.cat([rot_local[0], rot_act], 0)
+
+    return means3D, opacity, scales, rotations, shs
 
 
 def raytracing(frame, gaussian_assets, sensor, background, args, scaling_modifier=1.0, override_color=None,
@@ -63,29 +92,16 @@ def raytracing(frame, gaussian_assets, sensor, background, args, scaling_modifie
         sh_degree=gaussian_assets[0].active_sh_degree, campos=sensor_center.to(dev),
         prefiltered=False, debug=False)
 
-    all_means, all_opac, all_scales, all_shs, obj_rot, rot_local = [], [], [], [], [], []
-    for pc in gaussian_assets:
-        all_means.append(pc.get_world_xyz(frame))
-        all_opac.append(pc.get_opacity)
-        all_scales.append(pc.get_scaling)
-        r1, r2 = pc.get_rotation(frame)
-        obj_rot.append(r1.expand(r2.shape[0], -1))
-        rot_local.append(r2)
-        all_shs.append(pc.get_features)
-    _cat = lambda xs: xs[0] if len(xs) == 1 else torch.cat(xs, 0)      # one asset: no 232 B/Gaussian copy (+ its backward)
-    means3D = _cat(all_means)
-    opacity = _cat(all_opac)
-    scales = _cat(all_scales)
-    shs = _cat(all_shs)
     dynamic = bool(getattr(args, "dynamic", False)) if args is not None else False
-    if decomp == "background" or not dynamic:                      # reference :117-130
-        rotations = rot_local[0] if len(rot_local) == 1 else torch.cat(rot_local, 0)
-    elif decomp == "object":
-        rotations = quaternion_raw_multiply(torch.cat(obj_rot, 0), F.normalize(torch.cat(rot_local, 0), dim=1))
+    fused = None
+    if _arg(args, "pipe", "fused_prepare", True):
+        # one native call instead of the accessor loop + torch.cat below (same values, same gradients); applies when
+        # the assets expose the GaussianModel leaves
+        fused = fused_prepare(gaussian_assets, frame, dynamic, decomp, tracer_2dgs.optix_context.ctx)
+    if fused is not None:
+        means3D, opacity, scales, rotations, shs = fused
     else:
-        rot_act = quaternion_raw_multiply(torch.cat(obj_rot[1:], 0), F.normalize(torch.cat(rot_local[1:], 0), dim=1)) \
-            if len(rot_local) > 1 else rot_local[0][:0]
-        rotations = torch.cat([rot_local[0], rot_act], 0)
+        means3D, opacity, scales, rotations, shs = _assemble(frame, gaussian_assets, dynamic, decomp)
 
     grads3D = torch.zeros_like(means3D, requires_grad=True)
     try:

@@ -33,6 +33,16 @@ class LrtInfo(ctypes.Structure):
                 ("kernel_launches", c_int32)]
 
 
+class LrtAsset(ctypes.Structure):
+    """lrt_asset of include/lidar_rt_b200.h: one GaussianModel's leaf tensors (+ optional pose, + gradient targets)."""
+    _fields_ = [("P", c_int32), ("compose_rotation", c_int32),
+                ("xyz", c_void_p), ("scaling", c_void_p), ("rotation", c_void_p), ("opacity", c_void_p),
+                ("features_dc", c_void_p), ("features_rest", c_void_p), ("pose_T", c_void_p), ("pose_quat", c_void_p),
+                ("d_xyz", c_void_p), ("d_scaling", c_void_p), ("d_rotation", c_void_p), ("d_opacity", c_void_p),
+                ("d_features_dc", c_void_p), ("d_features_rest", c_void_p)]
+
+
+MAX_ASSETS = 128
 _lib = None
 
 
@@ -57,6 +67,9 @@ def load_library() -> ctypes.CDLL:
                                 fp, fp, ip, fp, fp, ip, c_int, ip, c_void_p]
     lib.lrt_backward.argtypes = [c_void_p, c_int, fp, c_int, fp, fp, c_int, fp, fp, fp, fp, fp, c_int, c_int, c_float,
                                  fp, fp, ip, fp, fp, ip, c_int, fp, fp, fp, fp, fp, c_int, c_void_p]
+    lib.lrt_prepare.argtypes = [c_void_p, c_int, POINTER(LrtAsset), c_int, fp, fp, fp, fp, fp, c_void_p]
+    lib.lrt_prepare_backward.argtypes = [c_void_p, c_int, POINTER(LrtAsset), c_int, fp, fp, fp, fp, fp, c_void_p]
+    lib.lrt_prepare.restype = c_int; lib.lrt_prepare_backward.restype = c_int
     lib.lrt_set_option.argtypes = [c_void_p, c_int, c_int]
     lib.lrt_get_kernel_times.argtypes = [c_void_p, c_char_p, POINTER(c_float), POINTER(c_int), c_int]
     lib.lrt_get_kernel_times.restype = c_int
@@ -166,6 +179,73 @@ class Context:
         out = torch.empty(P, dtype=torch.int32, device=self.device)
         self._check(self.lib.lrt_get_permutation(self._h, _ptr(out), _stream(self.device)))
         return out
+
+    # ---- fused activation + world transform + concatenation
+    @staticmethod
+    def _asset_table(assets, grads=None):
+        """assets: list of dicts with the leaf tensors xyz, scaling, rotation, opacity, features_dc, features_rest (float32 CUDA,
+        contiguous), optional pose_T (3,), pose_quat (4,), compose_rotation. grads: matching list of dicts of output tensors."""
+        n = len(assets)
+        if not 1 <= n <= MAX_ASSETS:
+            raise LrtError(f"need 1..{MAX_ASSETS} assets, got {n}")
+        tab = (LrtAsset * n)()
+        M = None
+        for k, a in enumerate(assets):
+            leaves = {}
+            for name in ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest"):
+                t = a[name]
+                if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise LrtError(f"asset {k}: {name} must be a contiguous float32 CUDA tensor")
+                leaves[name] = t
+            P = leaves["xyz"].shape[0]
+            if (tuple(leaves["xyz"].shape) != (P, 3) or tuple(leaves["scaling"].shape) != (P, 2) or tuple(leaves["rotation"].shape) != (P, 4)
+                    or leaves["opacity"].numel() != P or tuple(leaves["features_dc"].shape) != (P, 1, 3)
+                    or leaves["features_rest"].shape[0] != P or leaves["features_rest"].shape[2:] != (3,)):
+                raise LrtError(f"asset {k}: leaf tensors disagree on shapes")
+            m_k = 1 + leaves["features_rest"].shape[1]
+            if M is None:
+                M = m_k
+            elif M != m_k:
+                raise LrtError("assets disagree on the number of SH coefficients")
+            e = tab[k]
+            e.P = P; e.compose_rotation = int(bool(a.get("compose_rotation", False)))
+            for name in leaves:
+                setattr(e, name, leaves[name].data_ptr())
+            for name in ("pose_T", "pose_quat"):
+                t = a.get(name)
+                if t is not None:
+                    if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                        raise LrtError(f"asset {k}: {name} must be a contiguous float32 CUDA tensor")
+                    setattr(e, name, t.data_ptr())
+            if grads is not None:
+                for name, t in grads[k].items():
+                    if t is not None:
+                        setattr(e, "d_" + name, t.data_ptr())
+        return tab, n, M
+
+    def prepare(self, assets):
+        """lrt_prepare: -> (means (P,3), scales (P,2), rots (P,4), opac (P,1), shs (P,M,3)) for the concatenated assets."""
+        tab, n, M = self._asset_table(assets)
+        P = sum(int(tab[k].P) for k in range(n))
+        dev = self.device
+        with torch.cuda.device(dev):
+            means = torch.empty((P, 3), dtype=torch.float32, device=dev); scales = torch.empty((P, 2), dtype=torch.float32, device=dev)
+            rots = torch.empty((P, 4), dtype=torch.float32, device=dev); opac = torch.empty((P, 1), dtype=torch.float32, device=dev)
+            shs = torch.empty((P, M, 3), dtype=torch.float32, device=dev)
+            self._check(self.lib.lrt_prepare(self._h, n, tab, M, _ptr(means), _ptr(scales), _ptr(rots), _ptr(opac), _ptr(shs), _stream(dev)))
+        return means, scales, rots, opac, shs
+
+    def prepare_backward(self, assets, g_means, g_scales, g_rots, g_opac, g_shs, want=None):
+        """lrt_prepare_backward: leaf gradients, one dict per asset (keys like the leaves)."""
+        names = ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest")
+        dev = self.device
+        with torch.cuda.device(dev):
+            grads = [{nm: (torch.empty_like(a[nm]) if (want is None or want[k].get(nm, True)) else None) for nm in names}
+                     for k, a in enumerate(assets)]
+            tab, n, M = self._asset_table(assets, grads)
+            args = [_f32(g, nm) for g, nm in ((g_means, "dL_dmeans"), (g_scales, "dL_dscales"), (g_rots, "dL_drots"), (g_opac, "dL_dopac"), (g_shs, "dL_dshs"))]
+            self._check(self.lib.lrt_prepare_backward(self._h, n, tab, M, *(_ptr(t) for t in args), _stream(dev)))
+        return grads
 
     # ---- forward / backward
     @staticmethod
