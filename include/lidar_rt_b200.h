@@ -129,6 +129,17 @@ int lrt_prepare(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, floa
 int lrt_prepare_backward(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, const float* dL_dmeans,
                          const float* dL_dscales, const float* dL_drots, const float* dL_dopac, const float* dL_dshs, void* stream);
 
+/* ---- ray generation / back-projection of a LiDAR range image ----
+ * lrt_range_rays replaces LiDARSensor.get_range_rays (lib/scene/lidar_sensor.py:395-434): unit ray directions (H,W,3) in the
+ * world frame and the shared origin (3) — pass it to lrt_forward with ray_o_stride = 0.
+ * lrt_range_points replaces LiDARSensor.range2point (:325-393): world points (H,W,3) of a range map (H,W).
+ *   inc_table: device (H) beam inclinations in ascending order (the reference's list form), or NULL to use the two bounds
+ *   [inc_lo, inc_hi] (its 2-element form); sensor2world: device (4,4) row-major. */
+int lrt_range_rays(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc_lo, float inc_hi, float pixel_offset,
+                   float angle_offset, const float* sensor2world, float* ray_d, float* centre, void* stream);
+int lrt_range_points(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc_lo, float inc_hi, float pixel_offset,
+                     float angle_offset, const float* sensor2world, const float* range_map, float* points, void* stream);
+
 /* Tuning knobs; none of them changes results.
  *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill, 2 = 8 lanes per ray,
  *                           3 = breadth-first wavefront through the hierarchy + per-ray sort + compositing,

@@ -9,6 +9,6 @@ HOSTCXX="/usr/bin/g++"; [ -x "$HOSTCXX" ] || HOSTCXX="g++"
 OUT="${LRT_OUT:-$HERE/liblidar_rt_b200.so}"
 "$NVCC" -ccbin "$HOSTCXX" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
     -Xcompiler -fPIC -shared ${LRT_NVCC_EXTRA:-} \
-    "$HERE/lrt_api.cu" "$HERE/lrt_build.cu" "$HERE/lrt_forward.cu" "$HERE/lrt_backward.cu" "$HERE/lrt_prepare.cu" \
+    "$HERE/lrt_api.cu" "$HERE/lrt_build.cu" "$HERE/lrt_forward.cu" "$HERE/lrt_backward.cu" "$HERE/lrt_prepare.cu" "$HERE/lrt_rays.cu" \
     -o "$OUT" -lcudart
 echo "built $OUT"

@@ -102,6 +102,21 @@ int lrt_prepare_backward(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, in
     return lrt_prepare_backward_impl(ctx, n_assets, assets, M, dL_dmeans, dL_dscales, dL_drots, dL_dopac, dL_dshs, (cudaStream_t)stream);
 }
 
+int lrt_range_rays(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc_lo, float inc_hi, float pixel_offset,
+                   float angle_offset, const float* sensor2world, float* ray_d, float* centre, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_range_rays_impl(ctx, H, W, inc_table, inc_lo, inc_hi, pixel_offset, angle_offset, sensor2world, nullptr, ray_d, centre, (cudaStream_t)stream);
+}
+
+int lrt_range_points(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc_lo, float inc_hi, float pixel_offset,
+                     float angle_offset, const float* sensor2world, const float* range_map, float* points, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    if (!range_map) { ctx->set_error("lrt_range_points: range_map is null"); return LRT_ERR_INVALID; }
+    return lrt_range_rays_impl(ctx, H, W, inc_table, inc_lo, inc_hi, pixel_offset, angle_offset, sensor2world, range_map, points, nullptr, (cudaStream_t)stream);
+}
+
 int lrt_set_option(lrt_ctx* ctx, int option, int value)
 {
     if (!ctx) return LRT_ERR_INVALID;

@@ -127,3 +127,5 @@ int lrt_prepare_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M,
                      float* opac, float* shs, cudaStream_t s);
 int lrt_prepare_backward_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, const float* g_means, const float* g_scales,
                               const float* g_rots, const float* g_opac, const float* g_shs, cudaStream_t s);
+int lrt_range_rays_impl(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc_lo, float inc_hi, float pixel_offset,
+                        float angle_offset, const float* sensor2world, const float* range_map, float* out, float* centre, cudaStream_t s);

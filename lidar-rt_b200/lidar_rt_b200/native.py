@@ -70,6 +70,9 @@ def load_library() -> ctypes.CDLL:
     lib.lrt_prepare.argtypes = [c_void_p, c_int, POINTER(LrtAsset), c_int, fp, fp, fp, fp, fp, c_void_p]
     lib.lrt_prepare_backward.argtypes = [c_void_p, c_int, POINTER(LrtAsset), c_int, fp, fp, fp, fp, fp, c_void_p]
     lib.lrt_prepare.restype = c_int; lib.lrt_prepare_backward.restype = c_int
+    lib.lrt_range_rays.argtypes = [c_void_p, c_int, c_int, fp, c_float, c_float, c_float, c_float, fp, fp, fp, c_void_p]
+    lib.lrt_range_points.argtypes = [c_void_p, c_int, c_int, fp, c_float, c_float, c_float, c_float, fp, fp, fp, c_void_p]
+    lib.lrt_range_rays.restype = c_int; lib.lrt_range_points.restype = c_int
     lib.lrt_set_option.argtypes = [c_void_p, c_int, c_int]
     lib.lrt_get_kernel_times.argtypes = [c_void_p, c_char_p, POINTER(c_float), POINTER(c_int), c_int]
     lib.lrt_get_kernel_times.restype = c_int
@@ -246,6 +249,43 @@ class Context:
             args = [_f32(g, nm) for g, nm in ((g_means, "dL_dmeans"), (g_scales, "dL_dscales"), (g_rots, "dL_drots"), (g_opac, "dL_dopac"), (g_shs, "dL_dshs"))]
             self._check(self.lib.lrt_prepare_backward(self._h, n, tab, M, *(_ptr(t) for t in args), _stream(dev)))
         return grads
+
+    # ---- range-image ray generation / back-projection
+    def _grid(self, H, W, inclinations, sensor2world):
+        dev = self.device
+        s2w = torch.as_tensor(sensor2world, dtype=torch.float32, device=dev).reshape(4, 4).contiguous()
+        table, lo, hi = None, 0.0, 0.0
+        if isinstance(inclinations, torch.Tensor) or len(inclinations) != 2:
+            table = torch.as_tensor(inclinations, dtype=torch.float32, device=dev).reshape(-1).contiguous()
+            if table.numel() != H:
+                raise LrtError(f"need H = {H} inclinations, got {table.numel()}")
+        else:
+            lo, hi = float(inclinations[0]), float(inclinations[1])
+        return s2w, table, lo, hi
+
+    def range_rays(self, H, W, inclinations, sensor2world, pixel_offset=0.5, angle_offset=0.0):
+        """-> (rays_o (H,W,3) stride-0 view of the sensor centre, rays_d (H,W,3)): LiDARSensor.get_range_rays."""
+        s2w, table, lo, hi = self._grid(H, W, inclinations, sensor2world)
+        dev = self.device
+        with torch.cuda.device(dev):
+            d = torch.empty((H, W, 3), dtype=torch.float32, device=dev); c = torch.empty(3, dtype=torch.float32, device=dev)
+            self._check(self.lib.lrt_range_rays(self._h, H, W, _ptr(table), c_float(lo), c_float(hi), c_float(pixel_offset),
+                                                c_float(angle_offset), _ptr(s2w), _ptr(d), _ptr(c), _stream(dev)))
+        return c[None, None].expand(H, W, 3), d
+
+    def range_points(self, range_map, inclinations, sensor2world, pixel_offset=0.5, angle_offset=0.0):
+        """-> world points (H,W,3) of a range map (H,W): LiDARSensor.range2point."""
+        rm = _f32(range_map, "range_map")
+        if rm.dim() != 2:
+            raise LrtError("range_map must be (H, W)")
+        H, W = rm.shape
+        s2w, table, lo, hi = self._grid(H, W, inclinations, sensor2world)
+        dev = self.device
+        with torch.cuda.device(dev):
+            p = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+            self._check(self.lib.lrt_range_points(self._h, H, W, _ptr(table), c_float(lo), c_float(hi), c_float(pixel_offset),
+                                                  c_float(angle_offset), _ptr(s2w), _ptr(rm), _ptr(p), _stream(dev)))
+        return p
 
     # ---- forward / backward
     @staticmethod

@@ -80,7 +80,8 @@ class LidarSensor:
         self.sensor_center[frame] = torch.tensor(sensor2world[:3, 3], device=self.device, dtype=torch.float32)
 
     def get_range_rays(self, frame):
-        o, d = syn.lidar_rays(self.H, self.W, self.inclinations, self.sensor2world[frame], self.pixel_offset)
-        rays_d = torch.as_tensor(d, device=self.device)
-        rays_o = self.sensor_center[frame][None, None].expand(self.H, self.W, 3)      # stride-0 view, as the reference
-        return rays_o, rays_d
+        """One kernel (lrt_range_rays) instead of the reference's ~15 torch ops; same (rays_o stride-0 view, rays_d)."""
+        from . import native
+        if getattr(self, "_nctx", None) is None:
+            self._nctx = native.Context(self.device)
+        return self._nctx.range_rays(self.H, self.W, self.inclinations, self.sensor2world[frame], self.pixel_offset)
