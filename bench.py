@@ -429,7 +429,7 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_e2e = float(t.item())
     e2e = {"value": world * K * R / t_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": 1e3 * t_e2e / K, "api": "lib.gaussian_renderer.raytracing() + loss.backward(); next frame's H2D prefetched on a copy stream"}
+           "ms_per_step": 1e3 * t_e2e / K, "api": "lib.gaussian_renderer.raytracing() (fused prepare + rebuild + forward) + loss.backward(); next frame's H2D prefetched on a copy stream"}
 
     # ---- 4. CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -439,6 +439,16 @@ def run_b200(args, rank, world, local_rank):
         except Exception as ex:      # the checker must never take the bench line down
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
 
+    ref_gpu = None
+    rpath = os.path.join(ROOT, "profiles", "r1_e_reference_optix_b200.json")
+    if os.path.exists(rpath):
+        try:
+            rj = json.load(open(rpath))
+            ref_gpu = {"value": rj["mrays_per_s_fwd_bwd"], "unit": UNIT, "ms_per_step": rj["ms"]["step"], "ms": rj["ms"],
+                       "what": "the unmodified reference (diff-lidar-tracer on OptiX, build2DRectangle + accel rebuild + forward + backward) on one B200 of this "
+                               "pool, same workload; measured by oracle/run_ref_optix.py bench, recorded in profiles/ (not re-measured by this run)"}
+        except Exception:
+            ref_gpu = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -447,7 +457,8 @@ def run_b200(args, rank, world, local_rank):
                            "rays_per_frame": R, "sh_degree": D, "step": "lbvh rebuild + forward + backward per frame",
                            "l2": "inputs larger than L2 (Gaussian parameters 464 MB + SH gradients 384 MB per step vs 126 MB L2)",
                            "frames_per_rank": K, "sharding": "frame-parallel, replicated Gaussians, one gather of rendered buffers per sweep"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "reference_on_gpu": ref_gpu}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

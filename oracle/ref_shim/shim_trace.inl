@@ -92,7 +92,7 @@ static void build(const float3* verts, int ntri)
     const char* ce = getenv("ORC_REF_CACHE_BVH");
     if (ce && ce[0] == '1') {
         double sum = 0.0;
-        for (long long i = 0; i < 3LL * ntri; i++) { const float3& v = verts[i]; sum += (double)v.x + 2.0 * (double)v.y + 3.0 * (double)v.z; }
+        for (long long i = 0; i < 2LL * ntri; i++) { /* 4 vertices per quad = 2 per triangle */ const float3& v = verts[i]; sum += (double)v.x + 2.0 * (double)v.y + 3.0 * (double)v.z; }
         if (ntri == g_cache_ntri && sum == g_cache_sum && (!g_nodes.empty() || g_brute)) { g_verts = verts; return; }
         g_cache_sum = sum; g_cache_ntri = ntri;
     } else { g_cache_ntri = -1; }

@@ -1,0 +1,71 @@
+"""BASELINE config #5: the shape of the reference's train.py iteration (train.py:120-290) on a synthetic Waymo-dynamic scene:
+random frame -> raytracing() -> depth / intensity / ray-drop losses -> backward -> Adam step on every Gaussian parameter.
+Reports iterations/s on one GPU. Data loading, densification and logging are out of scope.
+   python scripts/train_loop.py [--gaussians 2000000] [--actors 40] [--iters 60] [--frames 16]"""
+import argparse, os, sys, time, types
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "lidar-rt_b200"))
+import numpy as np, torch
+from lidar_rt_b200 import synthetic as syn
+from lidar_rt_b200.scene import GaussianAsset, LidarSensor
+import lib.gaussian_renderer as gr
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--gaussians", type=int, default=2_000_000)
+ap.add_argument("--actors", type=int, default=40)
+ap.add_argument("--iters", type=int, default=60)
+ap.add_argument("--warmup", type=int, default=8)
+ap.add_argument("--frames", type=int, default=16)
+ap.add_argument("--no-fused-prepare", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+P = a.gaussians + a.actors * 10000
+sc = syn.make_street_scene(P, seed=1, n_actors=a.actors, per_actor=10000)
+assets = []
+for k in [-1] + list(range(a.actors)):
+    m = sc.actor_id == k
+    sub = syn.Scene(sc.means[m], sc.scales[m], sc.rots[m], sc.opac[m], sc.shs[m], sc.actor_id[m], 3)
+    poses = None
+    if k >= 0:          # actor Gaussians live in the actor's frame-0 pose; later frames = rigid translation (synthetic.actor_transform)
+        poses = {f: (torch.tensor(syn.actor_transform(k, f)[1], device=dev), torch.tensor([[1.0, 0, 0, 0]], device=dev)) for f in range(a.frames)}
+    assets.append(GaussianAsset(sub, device=dev, actor_poses=poses))
+sensor = LidarSensor(device=dev)
+for f in range(a.frames):
+    sensor.add_frame(f, syn.sensor_pose(f))
+H, W = sensor.H, sensor.W
+bg = torch.tensor([0.0, 0.0, 1.0], device=dev)
+args = types.SimpleNamespace(dynamic=True, pipe=types.SimpleNamespace(fused_prepare=not a.no_fused_prepare, compute_cov3D_python=False, convert_SHs_python=False),
+                             opt=types.SimpleNamespace(use_rayhit=True))
+# "ground truth": the initial render of every frame, perturbed
+gt = {}
+with torch.no_grad():
+    for f in range(a.frames):
+        pkg = gr.raytracing(f, assets, sensor, bg, args)
+        gt[f] = (pkg["depth"] * (1 + 0.02 * torch.randn_like(pkg["depth"])), (pkg["intensity"] + 0.05 * torch.randn_like(pkg["intensity"])).clamp(0, 1),
+                 (pkg["raydrop"] > 0.5).float())
+groups = []
+lrs = dict(_xyz=1.6e-4, _features_dc=2.5e-3, _features_rest=1.25e-4, _opacity=0.05, _scaling=5e-3, _rotation=1e-3)     # configs/exp.yaml
+for name, lr in lrs.items():
+    groups.append({"params": [getattr(x, name) for x in assets], "lr": lr})
+opt = torch.optim.Adam(groups, eps=1e-15, fused=True)
+rng = np.random.default_rng(0)
+
+def iteration():
+    f = int(rng.integers(0, a.frames))
+    pkg = gr.raytracing(f, assets, sensor, bg, args)
+    d_gt, i_gt, r_gt = gt[f]
+    loss = (pkg["depth"] - d_gt).abs().mean() * 0.1 + (pkg["intensity"] - i_gt).abs().mean() + \
+        torch.nn.functional.binary_cross_entropy(pkg["raydrop"].clamp(1e-6, 1 - 1e-6), r_gt) * 0.1
+    loss.backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    return loss
+
+for _ in range(a.warmup):
+    iteration()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(a.iters):
+    loss = iteration()
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print(f"config #5 (synthetic): P = {P} Gaussians ({a.actors} actors), {H} x {W} rays, SH degree 3, fused_prepare={not a.no_fused_prepare}: "
+      f"{a.iters / dt:.1f} it/s ({1e3 * dt / a.iters:.2f} ms/it, {H * W * a.iters / dt / 1e6:.1f} Mrays/s), final loss {float(loss):.4f}")
