@@ -140,6 +140,21 @@ int lrt_range_rays(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc
 int lrt_range_points(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc_lo, float inc_hi, float pixel_offset,
                      float angle_offset, const float* sensor2world, const float* range_map, float* points, void* stream);
 
+/* ---- Chamfer distance between two point clouds ----
+ * lrt_chamfer_forward replaces chamfer_3D.forward (lib/utils/chamfer3D/chamfer_cuda.cpp:17-19 -> chamfer3D.cu:135-155, kernel :11-133):
+ *   xyz1 (b,n,3), xyz2 (b,m,3); for every point of xyz1 the squared distance to its nearest point of xyz2 and that point's index
+ *   (the lowest index among exact ties, as the reference's strict comparisons give), and the same for xyz2 against xyz1.
+ *   dist1 (b,n), idx1 (b,n) int32, dist2 (b,m), idx2 (b,m); written entirely by the call. An empty opposite cloud leaves zeros,
+ *   like the reference's zero-initialised outputs. Inputs must be finite.
+ * lrt_chamfer_backward replaces chamfer_3D.backward (chamfer_cuda.cpp:22-26 -> chamfer3D.cu:157-196): grad_xyz1 (b,n,3) and
+ *   grad_xyz2 (b,m,3) from grad_dist1 (b,n), grad_dist2 (b,m) and the indices of the forward; written entirely by the call
+ *   (the reference accumulates into zero-filled tensors), neighbour terms accumulated with float atomics. */
+int lrt_chamfer_forward(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, const float* xyz2,
+                        float* dist1, int32_t* idx1, float* dist2, int32_t* idx2, void* stream);
+int lrt_chamfer_backward(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, const float* xyz2,
+                         const float* grad_dist1, const float* grad_dist2, const int32_t* idx1, const int32_t* idx2,
+                         float* grad_xyz1, float* grad_xyz2, void* stream);
+
 /* Tuning knobs; none of them changes results.
  *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill, 2 = 8 lanes per ray,
  *                           3 = breadth-first wavefront through the hierarchy + per-ray sort + compositing,

@@ -41,7 +41,10 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
     DevBuf* bufs[] = {&ctx->leafq, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->rec_g, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
                       &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb,
                       &ctx->wf_ids, &ctx->wf_keys, &ctx->wf_sort_tmp, &ctx->bw_ids, &ctx->bw_keys, &ctx->bw_sort_tmp,
-                      &ctx->bw_off, &ctx->bw_rec_a, &ctx->bw_rec_b, &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan};
+                      &ctx->bw_off, &ctx->bw_rec_a, &ctx->bw_rec_b, &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan,
+                      &ctx->ch_tmp, &ctx->ch_bounds,
+                      &ctx->ch[0].keys_a, &ctx->ch[0].keys_b, &ctx->ch[0].idx_a, &ctx->ch[0].idx_b, &ctx->ch[0].pts, &ctx->ch[0].boxes,
+                      &ctx->ch[1].keys_a, &ctx->ch[1].keys_b, &ctx->ch[1].idx_a, &ctx->ch[1].idx_b, &ctx->ch[1].pts, &ctx->ch[1].boxes};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     delete ctx;
     return LRT_OK;
@@ -115,6 +118,21 @@ int lrt_range_points(lrt_ctx* ctx, int H, int W, const float* inc_table, float i
     if (!ctx) return LRT_ERR_INVALID;
     if (!range_map) { ctx->set_error("lrt_range_points: range_map is null"); return LRT_ERR_INVALID; }
     return lrt_range_rays_impl(ctx, H, W, inc_table, inc_lo, inc_hi, pixel_offset, angle_offset, sensor2world, range_map, points, nullptr, (cudaStream_t)stream);
+}
+
+int lrt_chamfer_forward(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, const float* xyz2,
+                        float* dist1, int32_t* idx1, float* dist2, int32_t* idx2, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_chamfer_forward_impl(ctx, b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, (cudaStream_t)stream);
+}
+
+int lrt_chamfer_backward(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, const float* xyz2,
+                         const float* grad_dist1, const float* grad_dist2, const int32_t* idx1, const int32_t* idx2,
+                         float* grad_xyz1, float* grad_xyz2, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_chamfer_backward_impl(ctx, b, n, xyz1, m, xyz2, grad_dist1, grad_dist2, idx1, idx2, grad_xyz1, grad_xyz2, (cudaStream_t)stream);
 }
 
 int lrt_set_option(lrt_ctx* ctx, int option, int value)

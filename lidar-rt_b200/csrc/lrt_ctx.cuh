@@ -15,6 +15,8 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+#define LRT_CH_MAX_LEVELS 10      // chamfer point hierarchy, 8-wide: 8^10 points
+
 struct lrt_ctx {
     int device = 0;
     std::string err;
@@ -30,6 +32,15 @@ struct lrt_ctx {
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
     DevBuf bw_off, bw_rec_a, bw_rec_b;   // hit-parallel backward (lrt_backward.cu)
     DevBuf bg_ang, bg_cell_of, bg_cells, bg_sray, bg_wide, bg_plan;   // shared-origin beam grid (lrt_beamgrid.cuh)
+    // chamfer distance (lrt_chamfer.cu): one Morton-sorted point hierarchy per cloud, rebuilt every call
+    struct ChTree {
+        DevBuf keys_a, keys_b, idx_a, idx_b, pts, boxes;
+        int n = 0, n_pad = 0, levels = 0;
+        int level_off[LRT_CH_MAX_LEVELS] = {0}, level_cnt[LRT_CH_MAX_LEVELS] = {0};
+        size_t bytes() const { return keys_a.cap + keys_b.cap + idx_a.cap + idx_b.cap + pts.cap + boxes.cap; }
+    };
+    ChTree ch[2];
+    DevBuf ch_tmp, ch_bounds;
     // options (lrt_set_option)
     int opt_forward_kernel = 4;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray, 3: wavefront,
                                   // 4: shared-origin beam grid (frames with per-ray origins take 3)
@@ -92,7 +103,7 @@ struct lrt_ctx {
         return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
                bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
-               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap;
+               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap;
     }
     BvhView view() const
     {
@@ -127,5 +138,10 @@ int lrt_prepare_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M,
                      float* opac, float* shs, cudaStream_t s);
 int lrt_prepare_backward_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, const float* g_means, const float* g_scales,
                               const float* g_rots, const float* g_opac, const float* g_shs, cudaStream_t s);
+int lrt_chamfer_forward_impl(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, const float* xyz2,
+                             float* dist1, int32_t* idx1, float* dist2, int32_t* idx2, cudaStream_t s);
+int lrt_chamfer_backward_impl(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, const float* xyz2,
+                              const float* grad_dist1, const float* grad_dist2, const int32_t* idx1, const int32_t* idx2,
+                              float* grad_xyz1, float* grad_xyz2, cudaStream_t s);
 int lrt_range_rays_impl(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc_lo, float inc_hi, float pixel_offset,
                         float angle_offset, const float* sensor2world, const float* range_map, float* out, float* centre, cudaStream_t s);

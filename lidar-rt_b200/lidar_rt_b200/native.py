@@ -73,6 +73,9 @@ def load_library() -> ctypes.CDLL:
     lib.lrt_range_rays.argtypes = [c_void_p, c_int, c_int, fp, c_float, c_float, c_float, c_float, fp, fp, fp, c_void_p]
     lib.lrt_range_points.argtypes = [c_void_p, c_int, c_int, fp, c_float, c_float, c_float, c_float, fp, fp, fp, c_void_p]
     lib.lrt_range_rays.restype = c_int; lib.lrt_range_points.restype = c_int
+    lib.lrt_chamfer_forward.argtypes = [c_void_p, c_int, c_int, fp, c_int, fp, fp, ip, fp, ip, c_void_p]
+    lib.lrt_chamfer_backward.argtypes = [c_void_p, c_int, c_int, fp, c_int, fp, fp, fp, ip, ip, fp, fp, c_void_p]
+    lib.lrt_chamfer_forward.restype = c_int; lib.lrt_chamfer_backward.restype = c_int
     lib.lrt_set_option.argtypes = [c_void_p, c_int, c_int]
     lib.lrt_get_kernel_times.argtypes = [c_void_p, c_char_p, POINTER(c_float), POINTER(c_int), c_int]
     lib.lrt_get_kernel_times.restype = c_int
@@ -286,6 +289,39 @@ class Context:
             self._check(self.lib.lrt_range_points(self._h, H, W, _ptr(table), c_float(lo), c_float(hi), c_float(pixel_offset),
                                                   c_float(angle_offset), _ptr(s2w), _ptr(rm), _ptr(p), _stream(dev)))
         return p
+
+    # ---- Chamfer distance
+    @staticmethod
+    def _clouds(xyz1, xyz2):
+        a = _f32(xyz1, "xyz1", (3,)); c = _f32(xyz2, "xyz2", (3,))
+        if a.dim() != 3 or c.dim() != 3 or a.shape[0] != c.shape[0]:
+            raise LrtError("xyz1 / xyz2 must be (batch, n, 3) and (batch, m, 3)")
+        return a, c, a.shape[0], a.shape[1], c.shape[1]
+
+    def chamfer_forward(self, xyz1, xyz2):
+        """lrt_chamfer_forward: -> (dist1 (b,n), dist2 (b,m), idx1 (b,n) int32, idx2 (b,m) int32), chamfer_3D.forward's outputs."""
+        a, c, b, n, m = self._clouds(xyz1, xyz2)
+        dev = self.device
+        with torch.cuda.device(dev):
+            d1 = torch.empty((b, n), dtype=torch.float32, device=dev); d2 = torch.empty((b, m), dtype=torch.float32, device=dev)
+            i1 = torch.empty((b, n), dtype=torch.int32, device=dev); i2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+            self._check(self.lib.lrt_chamfer_forward(self._h, b, n, _ptr(a), m, _ptr(c), _ptr(d1), _ptr(i1), _ptr(d2), _ptr(i2), _stream(dev)))
+        return d1, d2, i1, i2
+
+    def chamfer_backward(self, xyz1, xyz2, grad_dist1, grad_dist2, idx1, idx2):
+        """lrt_chamfer_backward: -> (grad_xyz1 (b,n,3), grad_xyz2 (b,m,3))."""
+        a, c, b, n, m = self._clouds(xyz1, xyz2)
+        g1 = _f32(grad_dist1, "grad_dist1"); g2 = _f32(grad_dist2, "grad_dist2")
+        if tuple(g1.shape) != (b, n) or tuple(g2.shape) != (b, m) or tuple(idx1.shape) != (b, n) or tuple(idx2.shape) != (b, m):
+            raise LrtError("grad_dist / idx shapes must be (batch, n) and (batch, m)")
+        if idx1.dtype != torch.int32 or idx2.dtype != torch.int32 or not idx1.is_cuda or not idx2.is_cuda:
+            raise LrtError("idx1 / idx2 must be int32 CUDA tensors")
+        dev = self.device
+        with torch.cuda.device(dev):
+            ga = torch.empty_like(a); gc = torch.empty_like(c)
+            self._check(self.lib.lrt_chamfer_backward(self._h, b, n, _ptr(a), m, _ptr(c), _ptr(g1), _ptr(g2), _ptr(idx1.contiguous()),
+                                                      _ptr(idx2.contiguous()), _ptr(ga), _ptr(gc), _stream(dev)))
+        return ga, gc
 
     # ---- forward / backward
     @staticmethod

@@ -183,3 +183,45 @@ class Ref:
                               _ptr(fwd_out, f), _ptr(dL, f),
                               _ptr(g["means"], f), _ptr(g["shs"], f), _ptr(g["opac"], f), _ptr(g["scales"], f), _ptr(g["rots"], f))
         return g
+
+
+class ChamferOracle:
+    """C restatement of the reference's Chamfer kernels (chamfer_oracle.c; lib/utils/chamfer3D/chamfer3D.cu:11-196)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "libchamfer_oracle.so")
+        if not os.path.exists(path):
+            build()
+        self.lib = ctypes.CDLL(path)
+        self.threads = self.lib.chm_num_threads()
+
+    @staticmethod
+    def _pts(x):
+        a = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        if a.ndim == 2:
+            a = a[None]
+        assert a.ndim == 3 and a.shape[2] == 3
+        return a
+
+    def forward(self, xyz1, xyz2):
+        """-> dist1 (b,n), dist2 (b,m), idx1 (b,n) int32, idx2 (b,m) int32 — the tuple chamfer_3DFunction.forward returns."""
+        a, c = self._pts(xyz1), self._pts(xyz2)
+        b, n, m = a.shape[0], a.shape[1], c.shape[1]
+        assert c.shape[0] == b
+        d1 = np.empty((b, n), np.float32); d2 = np.empty((b, m), np.float32)
+        i1 = np.empty((b, n), np.int32); i2 = np.empty((b, m), np.int32)
+        I = ctypes.c_int32
+        self.lib.chm_forward(c_int(b), c_int(n), _ptr(a, c_float), c_int(m), _ptr(c, c_float), _ptr(d1, c_float), _ptr(i1, I),
+                             _ptr(d2, c_float), _ptr(i2, I))
+        return d1, d2, i1, i2
+
+    def backward(self, xyz1, xyz2, g1, g2, idx1, idx2):
+        a, c = self._pts(xyz1), self._pts(xyz2)
+        b, n, m = a.shape[0], a.shape[1], c.shape[1]
+        g1 = np.ascontiguousarray(g1, np.float32).reshape(b, n); g2 = np.ascontiguousarray(g2, np.float32).reshape(b, m)
+        idx1 = np.ascontiguousarray(idx1, np.int32).reshape(b, n); idx2 = np.ascontiguousarray(idx2, np.int32).reshape(b, m)
+        ga = np.empty_like(a); gc = np.empty_like(c)
+        I = ctypes.c_int32
+        self.lib.chm_backward(c_int(b), c_int(n), _ptr(a, c_float), c_int(m), _ptr(c, c_float), _ptr(g1, c_float), _ptr(g2, c_float),
+                              _ptr(idx1, I), _ptr(idx2, I), _ptr(ga, c_float), _ptr(gc, c_float))
+        return ga, gc
