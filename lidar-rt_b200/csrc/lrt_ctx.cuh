@@ -34,13 +34,13 @@ struct lrt_ctx {
     DevBuf bg_ang, bg_cell_of, bg_cells, bg_sray, bg_wide, bg_plan;   // shared-origin beam grid (lrt_beamgrid.cuh)
     // chamfer distance (lrt_chamfer.cu): one Morton-sorted point hierarchy per cloud, rebuilt every call
     struct ChTree {
-        DevBuf keys_a, keys_b, idx_a, idx_b, pts, boxes;
+        DevBuf pts, boxes;
         int n = 0, n_pad = 0, levels = 0;
         int level_off[LRT_CH_MAX_LEVELS] = {0}, level_cnt[LRT_CH_MAX_LEVELS] = {0};
-        size_t bytes() const { return keys_a.cap + keys_b.cap + idx_a.cap + idx_b.cap + pts.cap + boxes.cap; }
+        size_t bytes() const { return pts.cap + boxes.cap; }
     };
     ChTree ch[2];
-    DevBuf ch_tmp, ch_bounds;
+    DevBuf ch_tmp, ch_bounds, ch_keys_a, ch_keys_b, ch_idx_a, ch_idx_b;
     // options (lrt_set_option)
     int opt_forward_kernel = 4;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray, 3: wavefront,
                                   // 4: shared-origin beam grid (frames with per-ray origins take 3)
@@ -103,7 +103,7 @@ struct lrt_ctx {
         return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
                bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
-               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap;
+               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap + ch_keys_a.cap + ch_keys_b.cap + ch_idx_a.cap + ch_idx_b.cap;
     }
     BvhView view() const
     {
