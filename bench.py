@@ -161,6 +161,20 @@ def make_inputs(args, n_frames, rank, world):
     return sc, frames
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms are meant to use every host thread the box has
+    ("all the host threads it can use"). The OpenMP runtime has already read the variable when torch was imported, so
+    the thread count is set through the runtime itself."""
+    import ctypes
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 # --------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (oracle/_ref = its forward.cu/backward.cu
@@ -168,6 +182,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle.oracle import ORC_BVH, Oracle, Ref, ref_available
+    use_all_host_threads()
     sc, frames = make_inputs(args, args.steps + args.warmup, 0, 1)
     kind = "reference" if ref_available() else "port"
     impl = Ref() if kind == "reference" else Oracle(False)
@@ -217,6 +232,7 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------- CPU baseline leg
 def cpu_baseline(args, sc, frame):
     from oracle.oracle import ORC_BVH, Oracle, Ref, ref_available
+    use_all_host_threads()
     kind = "reference" if ref_available() else "port"
     impl = Ref() if kind == "reference" else Oracle(False)
     cores = Oracle(False).threads

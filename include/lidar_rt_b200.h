@@ -171,7 +171,8 @@ int lrt_chamfer_backward(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, c
  *                           32 lanes of a warp run loops of equal length (default 1)
  *   LRT_OPT_BEAM_CELL_PCT   beam grid: cell edge in percent of the size that gives one ray per cell (default 100)
  *   LRT_OPT_KERNEL_TIMING   1 = record CUDA events around every kernel launch (read with lrt_get_kernel_times)
- *   LRT_OPT_WAVEFRONT_SHADE wavefront compositing: 0 = one warp per ray, 1 = warp sort + one thread per ray (default)
+ *   LRT_OPT_WAVEFRONT_SHADE wavefront compositing: 0 = one warp per ray, 1 = warp sort + one thread per ray,
+ *                           2 = 1 with pipelined record loads and slot opacities computed on acceptance (default)
  *   LRT_OPT_MORTON_BITS     32 = 32-bit keys, bits dealt to the axes so cells stay cubic (default); 63 = 21 bits/axis on
  *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build) */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,

@@ -188,6 +188,30 @@ __device__ __forceinline__ void sh_colour_stream(int deg, const float* dirn, con
     c[0] = r[0] + 0.5f; c[1] = r[1] + 0.5f; c[2] = r[2] + 0.5f;
     if (c[0] < 0.0f) c[0] = -0.0f;     // see sh_colour
 }
+// the same with the basis already evaluated (it depends on the ray only): nb basis values in b. All loads of the row are
+// issued before the first use, so a thread waits for the row once, not once per group of loads the scheduler happens to form.
+__device__ __forceinline__ void sh_colour_stream_b(int nb, const float* b, const float* __restrict__ row, float* c)
+{
+    const int nf = 3 * nb;
+    const float4* p4 = reinterpret_cast<const float4*>(row);
+    float4 v[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) v[i] = (4 * i < nf) ? __ldg(p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float r[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        if (4 * i < nf) {
+            const float vals[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int idx = 4 * i + e, j = idx / 3, ch = idx % 3;
+                if (idx < nf) r[ch] = (j == 0) ? b[0] * vals[e] : r[ch] + b[j] * vals[e];
+            }
+        }
+    }
+    c[0] = r[0] + 0.5f; c[1] = r[1] + 0.5f; c[2] = r[2] + 0.5f;
+    if (c[0] < 0.0f) c[0] = -0.0f;     // see sh_colour
+}
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return __ldg(p); }
 
 #define LRT_CUDA_TRY(ctx, call)                                                                     \

@@ -45,7 +45,8 @@ struct lrt_ctx {
     int opt_forward_kernel = 4;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray, 3: wavefront,
                                   // 4: shared-origin beam grid (frames with per-ray origins take 3)
     int opt_ray_grid_w = 0;       // > 0: rays are a row-major range image of this width (enables 4 x 8 warp tiles)
-    int opt_wavefront_shade = 1;  // wavefront compositing: 0 = one warp per ray (k_wf_shade), 1 = warp-sort + one thread per ray
+    int opt_wavefront_shade = 2;  // wavefront compositing: 0 = one warp per ray (k_wf_shade), 1 = warp-sort + one thread per ray,
+                                  // 2 = the same with pipelined record loads and opacities computed when a slot is accepted (default)
     int opt_beam_cell_pct = 100;  // beam grid: cell edge in percent of the one-ray-per-cell size
     int opt_sort_rays = 1;        // composite / backward replay: process rays in order of descending list length (lanes stay in step)
     int opt_backward_kernel = 2;  // 0: one thread per ray replays its hit list, 1: one warp per ray, one hit per lane (scans),

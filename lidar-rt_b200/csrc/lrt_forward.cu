@@ -625,7 +625,10 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                 w.order = order;
             }
             ctx->span_begin("k_wf_sort", s); k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w); ctx->span_end(s);
-            ctx->span_begin("k_wf_composite", s); k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w); ctx->span_end(s);
+            ctx->span_begin("k_wf_composite", s);
+            if (ctx->opt_wavefront_shade == 2) k_wf_composite2<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
+            else k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
+            ctx->span_end(s);
             ctx->launches += 1;
         }
         ctx->span_begin("k_wf_fallback", s); k_wf_fallback<<<ctx->num_sms, 128, 0, s>>>(bv, a, w); ctx->span_end(s);

@@ -478,6 +478,158 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE_MIN_BLOCKS) k_wf_composite(
     }
 }
 
+// k_wf_composite, second organisation (default, LRT_OPT_WAVEFRONT_SHADE = 2): the same walk, arranged so that a ray's thread
+// waits for memory as rarely as possible — the kernel is bound by exposed load latency (ncu: >90 % of the stall samples are
+// long-scoreboard), not by bandwidth or issue.
+//  * candidates are taken four at a time: their keys, then the outer parts of their four records (centre, cutoff, normal), are
+//    requested together, so the thread waits once per four gathers instead of once per gather;
+//  * a candidate that becomes a slot gets its blending opacity computed right there, from the record it has in registers,
+//    with the arithmetic fwd_shade_round() uses (depth = t' + base, point on the ORIGINAL ray): the round's compositing
+//    loop then needs no record at all (it used to gather all four 16-byte parts again, usually from L2);
+//  * the round's slots (key, opacity) live in shared memory, one column per thread, instead of local memory that competes
+//    with the gathers for L1; slots arrive almost sorted, so appending rarely reads them;
+//  * the SH basis is evaluated once per ray, and the twelve loads of an SH row are issued before the first use.
+// Results are bit-identical to the first organisation (tests/test_gpu_parity.py::test_all_forward_kernels_and_options_agree_bitwise).
+#ifndef LRT_COMPOSITE2_MIN_BLOCKS
+#define LRT_COMPOSITE2_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite2(BvhView bvh, FwdArgs a, WfBufs w)
+{
+    __shared__ unsigned long long s_kb[LRT_KBUF][128];             // the round's slots, ascending (t', id)
+    __shared__ float s_al[LRT_KBUF][128];                          // their blending opacities (0: cannot contribute)
+    const int tx = threadIdx.x;
+    const int S = w.order ? a.R : num_slots(a.R, a.grid_w);
+    const bool sh_fast = (a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0);
+    const SurfelRec* __restrict__ rec = bvh.rec_g;
+    for (int s = blockIdx.x * blockDim.x + tx; s < S; s += gridDim.x * blockDim.x) {
+        const int r = w.order ? w.order[s] : slot_to_ray(s, a.R, a.grid_w);
+        if (r < 0) continue;
+        const int hc = w.hit_count[r];
+        if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }
+        const int n = hc;
+        const unsigned long long* __restrict__ bin = w.bins + (size_t)r * w.hcap;       // sorted by (t from o, id)
+        FwdRay q;
+        fwd_ray_init(q, r, a);
+        float sb[16];
+        const int nb = sh_basis(a.D, q.dirn, sb);
+        int pos = 0;                                               // first candidate that can still matter
+        for (;;) {
+            RaySetup rs;
+            ray_setup(rs, q.o, q.d, q.base);
+            const float thr = q.base - 2.0f * (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
+            while (pos < n && __uint_as_float((unsigned)(bin[pos] >> 32)) < thr) pos++;
+            int cnt = 0;
+            unsigned long long klast = 0ull;                       // s_kb[cnt - 1]
+            bool done = false;
+            for (int i0 = pos; i0 < n && !done; i0 += 4) {
+                unsigned long long ck4[4];
+                float4 b0[4], b3[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) ck4[k] = i0 + k < n ? bin[i0 + k] : LRT_KEY_EMPTY;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (i0 + k < n) {
+                        const int gk = (int)(unsigned)(ck4[k] & 0xffffffffull);
+                        b0[k] = ld_f4(&rec[gk].r0); b3[k] = ld_f4(&rec[gk].r3);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (i0 + k >= n || done) continue;
+                    const unsigned long long ck = ck4[k];
+                    const float4 a0 = b0[k], a3 = b3[k];
+                    if (cnt == LRT_KBUF) {
+                        const float t16 = __uint_as_float((unsigned)(klast >> 32)) + q.base;
+                        if (__uint_as_float((unsigned)(ck >> 32)) - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) { done = true; continue; }
+                    }
+                    const int g = (int)(unsigned)(ck & 0xffffffffull);
+                    // quad_hit(), operation for operation
+                    const float c0 = a0.x - rs.ox, c1 = a0.y - rs.oy, c2 = a0.z - rs.oz;
+                    const float den = a3.x * rs.dx + a3.y * rs.dy + a3.z * rs.dz;
+                    const float num = a3.x * c0 + a3.y * c1 + a3.z * c2;
+                    const float t = num / den;
+                    if (!(t > 0.0f)) continue;
+                    const float4 a1 = ld_f4(&rec[g].r1), a2 = ld_f4(&rec[g].r2);
+                    {
+                        const float r0 = (rs.ox + t * rs.dx) - a0.x, r1 = (rs.oy + t * rs.dy) - a0.y, r2 = (rs.oz + t * rs.dz) - a0.z;
+                        const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
+                        const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+                        if (!(fabsf(u) <= a0.w && fabsf(v) <= a0.w)) continue;
+                        if (!(t < LRT_TMAX)) continue;
+                    }
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                    if (cnt == LRT_KBUF && key >= klast) continue;                              // behind the current 16th
+                    if (sh_fast) {   // a slot of this round: most slots composite, so start pulling its SH row (two 128 B lines at D = 3) into L2 now
+                        const char* row = reinterpret_cast<const char*>(a.shs + (size_t)g * a.M * 3);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                        if (a.D >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+                    }
+                    // its opacity, as fwd_shade_round() computes it (forward.cu:212-251)
+                    float alpha;
+                    {
+                        const float dpt = t + q.base;
+                        const float x0 = q.o[0] + dpt * q.d[0], x1 = q.o[1] + dpt * q.d[1], x2 = q.o[2] + dpt * q.d[2];
+                        const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
+                        const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
+                        const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+                        const float cosv = -((a0.x - q.o[0]) * a3.x + (a0.y - q.o[1]) * a3.y + (a0.z - q.o[2]) * a3.z);
+                        const float rho = u * u + v * v;
+                        const float power = -0.5f * rho;
+                        alpha = (cosv == 0.0f || power > 0.0f) ? 0.0f : fminf(LRT_ALPHA_MAX, a1.w * expf(power));
+                    }
+                    if (cnt < LRT_KBUF && (cnt == 0 || key > klast)) {                          // the usual case: append
+                        s_kb[cnt][tx] = key; s_al[cnt][tx] = alpha; cnt++; klast = key;
+                        continue;
+                    }
+                    if (cnt == LRT_KBUF) cnt--;                                                 // replaces the current 16th
+                    int j = cnt;
+                    while (j > 0 && s_kb[j - 1][tx] > key) { s_kb[j][tx] = s_kb[j - 1][tx]; s_al[j][tx] = s_al[j - 1][tx]; j--; }
+                    s_kb[j][tx] = key; s_al[j][tx] = alpha;
+                    cnt++;
+                    klast = s_kb[cnt - 1][tx];
+                }
+            }
+            // the round's compositing (fwd_shade_round()), opacities at hand
+            bool terminated = false;
+            for (int i = 0; i < cnt; i++) {
+                const unsigned long long key = s_kb[i][tx];
+                const int g = (int)(unsigned)(key & 0xffffffffull);
+                q.nslots++;
+                q.dpt = __uint_as_float((unsigned)(key >> 32)) + q.base;                  // forward.cu:212
+                if (q.dpt < LRT_MIN_T) continue;                                          // :214
+                if (g == q.last) continue;                                                // :220-224
+                q.last = g;
+                const float alpha = s_al[i][tx];
+                if (alpha < 1.0f / 255.0f) continue;
+                q.testT = q.T * (1.0f - alpha);
+                if (q.testT < LRT_T_MIN) { terminated = true; break; }                    // :253-257
+                const float wgt = alpha * q.T;
+                float c[3];
+                if (sh_fast) {
+                    sh_colour_stream_b(nb, sb, a.shs + (size_t)g * a.M * 3, c);
+                } else {
+                    float sh[48]; bool cl;
+                    load_sh(a.shs, g, a.M, nb, sh);
+                    sh_colour<false>(a.D, q.dirn, sh, c, cl, nullptr);
+                }
+                q.C0 += wgt * c[0]; q.C1 += wgt * c[1]; q.C2 += wgt * c[2];
+                q.Dp += wgt * q.dpt; q.W += wgt;
+                atomicAdd(a.accum_w + g, wgt);                                            // :272
+                if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
+                    a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g;
+                    a.hit_t[(size_t)q.ncontrib * a.R + q.r] = q.dpt;
+                    if (a.hit_aux) a.hit_aux[(size_t)q.ncontrib * a.R + q.r] = make_float4(alpha, c[0], c[1], c[2]);
+                }
+                q.ncontrib++;
+                q.T = q.testT;
+            }
+            if (terminated || q.testT < LRT_T_MIN || cnt < LRT_KBUF) break;               // :282-285
+            q.base = (float)((double)q.dpt + LRT_STEP_EPS);                               // :288
+        }
+        fwd_write(q, a, 0);
+    }
+}
+
 // Rays the wavefront handed back (normally none or a handful): the per-ray code path, one thread per ray.
 __global__ void __launch_bounds__(128) k_wf_fallback(BvhView bvh, FwdArgs a, WfBufs w)
 {

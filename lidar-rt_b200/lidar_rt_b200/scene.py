@@ -85,3 +85,23 @@ class LidarSensor:
         if getattr(self, "_nctx", None) is None:
             self._nctx = native.Context(self.device)
         return self._nctx.range_rays(self.H, self.W, self.inclinations, self.sensor2world[frame], self.pixel_offset)
+
+    def range2point(self, frame, range_map):
+        """World points (H, W, 3) of a range map: one kernel (lrt_range_points) for lidar_sensor.py:325-393."""
+        from . import native
+        if getattr(self, "_nctx", None) is None:
+            self._nctx = native.Context(self.device)
+        rm = torch.as_tensor(range_map, dtype=torch.float32, device=self.device)
+        if rm.dim() == 3:
+            rm = rm[0] if rm.shape[0] == 1 else rm[..., 0]
+        return self._nctx.range_points(rm.detach().contiguous(), self.inclinations, self.sensor2world[frame], self.pixel_offset)
+
+    def inverse_projection_with_range(self, frame, range_map, mask):
+        """lidar_sensor.py:170-191: the points of the pixels `mask` keeps, (N, 3). As in the reference no gradient reaches
+        `range_map` (it re-wraps the points with torch.tensor(), :183)."""
+        pts = self.range2point(frame, range_map)
+        if mask.dim() == 2:
+            pts = pts[mask.bool()]
+        else:
+            pts = pts * mask
+        return pts.view(-1, 3)

@@ -1,5 +1,5 @@
 """BASELINE config #5: the shape of the reference's train.py iteration (train.py:120-290) on a synthetic Waymo-dynamic scene:
-random frame -> raytracing() -> depth / intensity / ray-drop losses -> backward -> Adam step on every Gaussian parameter.
+random frame -> raytracing() -> depth / intensity / ray-drop / Chamfer losses -> backward -> Adam step on every Gaussian parameter.
 Reports iterations/s on one GPU. Data loading, densification and logging are out of scope.
    python scripts/train_loop.py [--gaussians 2000000] [--actors 40] [--iters 60] [--frames 16]"""
 import argparse, os, sys, time, types
@@ -9,6 +9,7 @@ import numpy as np, torch
 from lidar_rt_b200 import synthetic as syn
 from lidar_rt_b200.scene import GaussianAsset, LidarSensor
 import lib.gaussian_renderer as gr
+from lib.utils.chamfer3D.dist_chamfer_3D import chamfer_3DDist
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--gaussians", type=int, default=2_000_000)
@@ -17,6 +18,7 @@ ap.add_argument("--iters", type=int, default=60)
 ap.add_argument("--warmup", type=int, default=8)
 ap.add_argument("--frames", type=int, default=16)
 ap.add_argument("--no-fused-prepare", action="store_true")
+ap.add_argument("--no-chamfer", action="store_true", help="leave out the Chamfer term of train.py:196-207")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 P = a.gaussians + a.actors * 10000
@@ -49,6 +51,7 @@ for name, lr in lrs.items():
     groups.append({"params": [getattr(x, name) for x in assets], "lr": lr})
 opt = torch.optim.Adam(groups, eps=1e-15, fused=True)
 rng = np.random.default_rng(0)
+chamLoss = chamfer_3DDist()
 
 def iteration():
     f = int(rng.integers(0, a.frames))
@@ -56,6 +59,12 @@ def iteration():
     d_gt, i_gt, r_gt = gt[f]
     loss = (pkg["depth"] - d_gt).abs().mean() * 0.1 + (pkg["intensity"] - i_gt).abs().mean() + \
         torch.nn.functional.binary_cross_entropy(pkg["raydrop"].clamp(1e-6, 1 - 1e-6), r_gt) * 0.1
+    if not a.no_chamfer:          # train.py:196-207 (lambda_cd = 0.01)
+        mask = r_gt[..., 0] < 0.5 if r_gt.dim() == 3 else r_gt < 0.5
+        gt_pts = sensor.inverse_projection_with_range(f, d_gt, mask)
+        pred_pts = sensor.inverse_projection_with_range(f, pkg["depth"], mask)
+        dist1, dist2, _, _ = chamLoss(pred_pts[None, ...], gt_pts[None, ...])
+        loss = loss + 0.01 * (dist1 + dist2).mean() * 0.5
     loss.backward()
     opt.step()
     opt.zero_grad(set_to_none=True)
@@ -67,5 +76,5 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(a.iters):
     loss = iteration()
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print(f"config #5 (synthetic): P = {P} Gaussians ({a.actors} actors), {H} x {W} rays, SH degree 3, fused_prepare={not a.no_fused_prepare}: "
+print(f"config #5 (synthetic): P = {P} Gaussians ({a.actors} actors), {H} x {W} rays, SH degree 3, fused_prepare={not a.no_fused_prepare}, chamfer={not a.no_chamfer}: "
       f"{a.iters / dt:.1f} it/s ({1e3 * dt / a.iters:.2f} ms/it, {H * W * a.iters / dt / 1e6:.1f} Mrays/s), final loss {float(loss):.4f}")

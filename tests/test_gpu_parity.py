@@ -148,10 +148,10 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
         for kernel in (0, 1, 2, 3, 4):
             for tiled in (True, False):
                 for morton in (32, 63, 30):
-                  for shade in ((0, 1, 2) if kernel >= 3 else (1,)):
-                    # shade 2 = default compositing kernel with the by-length ray ordering switched off
-                    ctx.set_option(native.OPT_SORT_RAYS, 0 if shade == 2 else 1)
-                    shade = min(shade, 1)
+                  for shade in ((0, 1, 2, 3) if kernel >= 3 else (2,)):
+                    # shade 3 = default compositing kernel with the by-length ray ordering switched off
+                    ctx.set_option(native.OPT_SORT_RAYS, 0 if shade == 3 else 1)
+                    shade = min(shade, 2)
                     ctx.set_option(native.OPT_FORWARD_KERNEL, kernel)
                     ctx.set_option(native.OPT_MORTON_BITS, morton)
                     ctx.set_option(native.OPT_WAVEFRONT_SHADE, shade)
@@ -165,7 +165,7 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
                         for a_, b_ in zip(ref, key):
                             assert np.array_equal(a_, b_), f"kernel={kernel} tiled={tiled} morton={morton} shade={shade} differs"
     finally:
-        ctx.set_option(native.OPT_FORWARD_KERNEL, 4); ctx.set_option(native.OPT_MORTON_BITS, 32); ctx.set_option(native.OPT_WAVEFRONT_SHADE, 1)
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 4); ctx.set_option(native.OPT_MORTON_BITS, 32); ctx.set_option(native.OPT_WAVEFRONT_SHADE, 2)
         ctx.set_option(native.OPT_SORT_RAYS, 1)
     assert_close(res["accum_w"], run_cuda(ctx, o, d, as_dict(sc), 3)["accum_w"], 1e-5, 1e-5, "accum (atomic order)")
 
