@@ -513,11 +513,20 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite
         float sb[16];
         const int nb = sh_basis(a.D, q.dirn, sb);
         int pos = 0;                                               // first candidate that can still matter
+        int i_end = 0;                                             // where the previous round's scan stopped: everything from there on lies beyond thr
         for (;;) {
             RaySetup rs;
             ray_setup(rs, q.o, q.d, q.base);
             const float thr = q.base - 2.0f * (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
-            while (pos < n && __uint_as_float((unsigned)(bin[pos] >> 32)) < thr) pos++;
+            {   // first candidate at or beyond thr: lower bound in [pos, i_end] (the bin is sorted by t) — a few dependent loads instead of one per skipped candidate
+                int lo = pos, hi = i_end;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__uint_as_float((unsigned)(bin[mid] >> 32)) < thr) lo = mid + 1; else hi = mid;
+                }
+                pos = lo;
+            }
+            i_end = n;
             int cnt = 0;
             unsigned long long klast = 0ull;                       // s_kb[cnt - 1]
             bool done = false;
@@ -540,7 +549,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite
                     const float4 a0 = b0[k], a3 = b3[k];
                     if (cnt == LRT_KBUF) {
                         const float t16 = __uint_as_float((unsigned)(klast >> 32)) + q.base;
-                        if (__uint_as_float((unsigned)(ck >> 32)) - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) { done = true; continue; }
+                        if (__uint_as_float((unsigned)(ck >> 32)) - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) { done = true; i_end = i0 + k; continue; }
                     }
                     const int g = (int)(unsigned)(ck & 0xffffffffull);
                     // quad_hit(), operation for operation
