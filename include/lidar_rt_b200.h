@@ -155,6 +155,22 @@ int lrt_chamfer_backward(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, c
                          const float* grad_dist1, const float* grad_dist2, const int32_t* idx1, const int32_t* idx2,
                          float* grad_xyz1, float* grad_xyz2, void* stream);
 
+/* ---- the optimiser step under the tracer's gradients ----
+ * lrt_adam_step replaces the per-asset, per-group torch.optim.Adam(l, lr=0.0, eps=1e-15).step() calls of the reference
+ * (lib/scene/gaussian_model.py:186-201 sets the groups up; train.py steps every asset's optimizer each iteration): every
+ * parameter tensor of every asset is one row of `tensors` (HOST array) and all rows are updated by one launch, with the arithmetic
+ * of torch's single-tensor Adam (amsgrad off, no weight decay):
+ *   m = m + (g - m)(1 - beta1);  v = v beta2 + ((1 - beta2) g) g;  p = p + (-(lr / (1 - beta1^step)) m) / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * param / exp_avg / exp_avg_sq are updated in place; `step` is the 1-based count of THIS tensor's update (state re-created by
+ * densification restarts at 1). */
+typedef struct lrt_adam_tensor {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq;   /* device, n floats each */
+    int64_t n;
+    float lr;
+    int32_t step;
+} lrt_adam_tensor;
+int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, float beta1, float beta2, float eps, void* stream);
+
 /* Tuning knobs; none of them changes results.
  *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill, 2 = 8 lanes per ray,
  *                           3 = breadth-first wavefront through the hierarchy + per-ray sort + compositing,

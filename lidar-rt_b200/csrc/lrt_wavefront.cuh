@@ -372,6 +372,40 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
     }
 }
 
+// warp-wide bitonic sort of 32 K keys held in registers, K per lane: k[j] = element lane + 32 j (ascending). Partners at
+// strides >= 32 are the lane's own keys (no shuffle); with the loops unrolled every direction that does not depend on the lane is
+// a compile-time constant.
+template <int K>
+__device__ __forceinline__ void warp_sort_regs(unsigned long long (&k)[K], int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 32 * K; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int sj = stride >> 5;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    if ((j & sj) == 0) {
+                        const bool up = (((32 * j) & size) == 0);          // size >= 64 here: the bit belongs to j
+                        const unsigned long long a = k[j], b = k[j | sj];
+                        const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+                        k[j] = up ? lo : hi; k[j | sj] = up ? hi : lo;
+                    }
+                }
+            } else {
+                const bool lower = ((lane & stride) == 0);
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[j], stride);
+                    const bool up = (((lane + 32 * j) & size) == 0);
+                    k[j] = (lower == up) ? (k[j] < o ? k[j] : o) : (k[j] < o ? o : k[j]);
+                }
+            }
+        }
+    }
+}
+
 // ---- split compositing (default): k_wf_sort (one warp per ray: bitonic sort of the bin, written back) followed by
 // k_wf_composite (one THREAD per ray). With traversal gone, what is left per ray is a walk over a short sorted
 // candidate list — 16 lanes of a warp shading while 32 replicate the fold (k_wf_shade) costs ~3x the instructions
@@ -400,7 +434,25 @@ __global__ void __launch_bounds__(128) k_wf_sort(FwdArgs a, WfBufs w)
             if (lane + 32 < n) bin[lane + 32] = k1;
             continue;
         }
-        int m = 128; while (m < n) m <<= 1;
+        if (n <= 128) {                                            // four keys per lane
+            unsigned long long k[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) k[j] = lane + 32 * j < n ? bin[lane + 32 * j] : LRT_KEY_EMPTY;
+            warp_sort_regs<4>(k, lane);
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (lane + 32 * j < n) bin[lane + 32 * j] = k[j];
+            continue;
+        }
+        if (n <= 256) {                                            // eight keys per lane
+            unsigned long long k[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) k[j] = lane + 32 * j < n ? bin[lane + 32 * j] : LRT_KEY_EMPTY;
+            warp_sort_regs<8>(k, lane);
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (lane + 32 * j < n) bin[lane + 32 * j] = k[j];
+            continue;
+        }
+        int m = 512; while (m < n) m <<= 1;
         // shared memory for the common sizes; the few bins beyond WF_HCAP are sorted in place in global memory
         // (padding entries up to m live in the bin itself: m <= hcap because hcap is a power of two)
         unsigned long long* buf = (m <= WF_HCAP) ? keys : bin;

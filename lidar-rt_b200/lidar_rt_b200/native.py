@@ -42,6 +42,12 @@ class LrtAsset(ctypes.Structure):
                 ("d_features_dc", c_void_p), ("d_features_rest", c_void_p)]
 
 
+class LrtAdamTensor(ctypes.Structure):
+    """lrt_adam_tensor of include/lidar_rt_b200.h: one parameter tensor with its gradient and Adam state."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("n", c_int64), ("lr", c_float), ("step", c_int32)]
+
+
 MAX_ASSETS = 128
 _lib = None
 
@@ -76,6 +82,8 @@ def load_library() -> ctypes.CDLL:
     lib.lrt_chamfer_forward.argtypes = [c_void_p, c_int, c_int, fp, c_int, fp, fp, ip, fp, ip, c_void_p]
     lib.lrt_chamfer_backward.argtypes = [c_void_p, c_int, c_int, fp, c_int, fp, fp, fp, ip, ip, fp, fp, c_void_p]
     lib.lrt_chamfer_forward.restype = c_int; lib.lrt_chamfer_backward.restype = c_int
+    lib.lrt_adam_step.argtypes = [c_void_p, c_int, POINTER(LrtAdamTensor), c_float, c_float, c_float, c_void_p]
+    lib.lrt_adam_step.restype = c_int
     lib.lrt_set_option.argtypes = [c_void_p, c_int, c_int]
     lib.lrt_get_kernel_times.argtypes = [c_void_p, c_char_p, POINTER(c_float), POINTER(c_int), c_int]
     lib.lrt_get_kernel_times.restype = c_int
@@ -289,6 +297,26 @@ class Context:
             self._check(self.lib.lrt_range_points(self._h, H, W, _ptr(table), c_float(lo), c_float(hi), c_float(pixel_offset),
                                                   c_float(angle_offset), _ptr(s2w), _ptr(rm), _ptr(p), _stream(dev)))
         return p
+
+    # ---- Adam step over many tensors
+    def adam_step(self, rows, beta1: float, beta2: float, eps: float):
+        """lrt_adam_step. rows: iterable of (param, grad, exp_avg, exp_avg_sq, lr, step); all float32 CUDA contiguous, same numel."""
+        rows = list(rows)
+        tab = (LrtAdamTensor * max(len(rows), 1))()
+        for k, (p, g, m, v, lr, step) in enumerate(rows):
+            for t, nm in ((p, "param"), (g, "grad"), (m, "exp_avg"), (v, "exp_avg_sq")):
+                if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise LrtError(f"adam_step: row {k}: {nm} must be a contiguous float32 CUDA tensor")
+                if t.device != self.device:
+                    raise LrtError(f"adam_step: row {k}: {nm} lives on {t.device}, the context on {self.device}")
+            n = p.numel()
+            if g.numel() != n or m.numel() != n or v.numel() != n:
+                raise LrtError(f"adam_step: row {k}: param / grad / state sizes differ")
+            e = tab[k]
+            e.param, e.grad, e.exp_avg, e.exp_avg_sq = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+            e.n, e.lr, e.step = n, float(lr), int(step)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.lrt_adam_step(self._h, len(rows), tab, c_float(beta1), c_float(beta2), c_float(eps), _stream(self.device)))
 
     # ---- Chamfer distance (SURVEY 8f N2)
     @staticmethod

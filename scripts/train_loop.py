@@ -19,6 +19,8 @@ ap.add_argument("--warmup", type=int, default=8)
 ap.add_argument("--frames", type=int, default=16)
 ap.add_argument("--no-fused-prepare", action="store_true")
 ap.add_argument("--no-chamfer", action="store_true", help="leave out the Chamfer term of train.py:196-207")
+ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused=True) over all tensors instead of lrt_adam_step")
+ap.add_argument("--profile", action="store_true", help="print the torch profiler's top CUDA kernels of 10 iterations")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 P = a.gaussians + a.actors * 10000
@@ -49,7 +51,11 @@ groups = []
 lrs = dict(_xyz=1.6e-4, _features_dc=2.5e-3, _features_rest=1.25e-4, _opacity=0.05, _scaling=5e-3, _rotation=1e-3)     # configs/exp.yaml
 for name, lr in lrs.items():
     groups.append({"params": [getattr(x, name) for x in assets], "lr": lr})
-opt = torch.optim.Adam(groups, eps=1e-15, fused=True)
+if a.torch_adam:
+    opt = torch.optim.Adam(groups, eps=1e-15, fused=True)
+else:
+    from lidar_rt_b200.optim import FusedAdam       # every tensor of every asset in one launch (lrt_adam_step)
+    opt = FusedAdam(groups, eps=1e-15)
 rng = np.random.default_rng(0)
 chamLoss = chamfer_3DDist()
 
@@ -72,9 +78,17 @@ def iteration():
 
 for _ in range(a.warmup):
     iteration()
+if a.profile:
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for _ in range(10):
+            iteration()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(a.iters):
     loss = iteration()
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print(f"config #5 (synthetic): P = {P} Gaussians ({a.actors} actors), {H} x {W} rays, SH degree 3, fused_prepare={not a.no_fused_prepare}, chamfer={not a.no_chamfer}: "
+print(f"config #5 (synthetic): P = {P} Gaussians ({a.actors} actors), {H} x {W} rays, SH degree 3, fused_prepare={not a.no_fused_prepare}, chamfer={not a.no_chamfer}, adam={'torch fused' if a.torch_adam else 'lrt_adam_step'}: "
       f"{a.iters / dt:.1f} it/s ({1e3 * dt / a.iters:.2f} ms/it, {H * W * a.iters / dt / 1e6:.1f} Mrays/s), final loss {float(loss):.4f}")

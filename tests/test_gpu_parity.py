@@ -264,6 +264,29 @@ def test_refit_matches_rebuild(ctx):
     assert info.refits >= 1 and info.P == 30000
 
 
+def test_kitti_dynamic_refit_long_bins_vs_oracle(ctx, oracle32):
+    """BASELINE config #3 shape at test size: KITTI-360 ray grid (linear inclinations, pixel offset 0), moving actors, structure
+    refit to a later frame; large surfels so that many rays carry 65-256+ candidates (the register sorts of k_wf_sort)."""
+    H, W = 22, 103
+    sc0 = syn.make_street_scene(40_000 + 4 * 2000, seed=21, n_actors=4, per_actor=2000, scale_mult=3.0)
+    inc = syn.kitti_inclinations(syn.KITTI_H)[::3]
+    o, d = syn.lidar_rays(H, W, inc, syn.sensor_pose(4), pixel_offset=0.0)
+    rng = np.random.default_rng(21)
+    dL = np.zeros((H * W, 9), np.float32); dL[:, :4] = rng.standard_normal((H * W, 4))
+    run_cuda(ctx, o, d, as_dict(sc0), 3)                                     # structure of frame 0 ...
+    sc = syn.scene_at_frame(sc0, 4)
+    res = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=256, refit=True)       # ... refit to frame 4
+    assert res["slot_cnt"].max() > 128 and (res["slot_cnt"] > 64).mean() > 0.2, "scene too thin to exercise the long-bin sorts"
+    args = (o, d, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, 3)
+    f = oracle32.forward(*args, flags=ORC_BVH, cap=256)
+    assert hit_lists(res) == oracle_lists(f), "hit indices must be bit-exact"
+    assert np.array_equal(res["slot_cnt"], f["slot_cnt"])
+    assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
+    b = oracle32.backward(*args, f["out"], dL, flags=ORC_BVH)
+    for k in ("means", "shs", "opac", "scales", "rots"):
+        grad_close(res[f"g_{k}"], b[k], GRAD_REL, f"d_{k}")
+
+
 def test_full_size_properties(ctx):
     """BASELINE config #2 shape (1M Gaussians, 64 x 2650 rays): size-independent invariants."""
     sc = syn.make_street_scene(1_000_000, seed=1)
