@@ -253,6 +253,37 @@ def cpu_baseline(args, sc, frame):
                       f"traced-sample time ({t_all - t_build:.2f} s) x {R / n:.0f}"}
 
 
+def chamfer_leg(ctx, dev):
+    """lrt_chamfer_forward / _backward on the two clouds of one Waymo frame (the train.py:197-207 call), CUDA events, median of 20;
+    next to it the recorded time of the unmodified reference extension on a B200 of this pool (profiles/, oracle/run_ref_chamfer.py)."""
+    import torch
+    from lidar_rt_b200 import synthetic as syn
+    o, d = syn.lidar_rays(H, W, syn.waymo_inclinations(), syn.sensor_pose(3))
+    rng = np.random.default_rng(11)
+    dd = d.reshape(-1, 3)
+    r = np.where(dd[:, 2] < -0.02, np.minimum(2.0 / np.maximum(-dd[:, 2], 1e-3), 75.0), rng.uniform(8.0, 40.0, dd.shape[0])).astype(np.float32)
+    keep = rng.random(dd.shape[0]) > 0.15
+    gt = torch.as_tensor((o.reshape(1, 3) + dd * r[:, None])[keep].astype(np.float32)[None], device=dev)
+    pr = torch.as_tensor((o.reshape(1, 3) + dd * (r + rng.normal(0, 0.05, r.shape).astype(np.float32))[:, None])[keep].astype(np.float32)[None], device=dev)
+    g1 = torch.randn(1, pr.shape[1], device=dev); g2 = torch.randn(1, gt.shape[1], device=dev)
+    tf, tb = [], []
+    for i in range(23):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(); d1, d2, i1, i2 = ctx.chamfer_forward(pr, gt); e[1].record(); ctx.chamfer_backward(pr, gt, g1, g2, i1, i2); e[2].record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            tf.append(e[0].elapsed_time(e[1])); tb.append(e[1].elapsed_time(e[2]))
+    out = {"points_per_cloud": int(pr.shape[1]), "forward_ms": float(np.median(tf)), "backward_ms": float(np.median(tb)),
+           "chamfer_distance": float(d1.mean() + d2.mean())}
+    rp = os.path.join(ROOT, "profiles", "r1_i_chamfer_vs_reference_b200.json")
+    if os.path.exists(rp):
+        rj = json.load(open(rp))
+        out["reference_on_gpu"] = {"forward_ms": rj["reference_forward_ms"], "backward_ms": rj["reference_backward_ms"], "points_per_cloud": rj["n"],
+                                   "bit_exact_vs_reference": bool(rj["dist_bit_exact"] and rj["idx_exact"]),
+                                   "what": "lib/utils/chamfer3D of the reference, unmodified, same B200 pool (recorded, not re-measured)"}
+    return out
+
+
 # --------------------------------------------------------------------------------- B200 arm
 def run_b200(args, rank, world, local_rank):
     import torch
@@ -369,7 +400,8 @@ def run_b200(args, rank, world, local_rank):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj.get("kernels", {}).get(dom, None)
+            tk = tj.get("kernels", {})
+            traffic = tk.get(dom, tk.get(dom + "2"))       # the default compositing kernel is k_wf_composite2 in ncu's list
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
@@ -465,6 +497,13 @@ def run_b200(args, rank, world, local_rank):
                                "pool, same workload; measured by oracle/run_ref_optix.py bench, recorded in profiles/ (not re-measured by this run)"}
         except Exception:
             ref_gpu = None
+    # ---- 5. the rows next to the path, outside the timed regions above: Chamfer distance of one frame's clouds
+    next_rows = None
+    if rank == 0 and world == 1:
+        try:
+            next_rows = {"chamfer": chamfer_leg(ctx, dev)}
+        except Exception as ex:
+            next_rows = {"chamfer": {"error": str(ex)}}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -474,7 +513,7 @@ def run_b200(args, rank, world, local_rank):
                            "l2": "inputs larger than L2 (Gaussian parameters 464 MB + SH gradients 384 MB per step vs 126 MB L2)",
                            "frames_per_rank": K, "sharding": "frame-parallel, replicated Gaussians, one gather of rendered buffers per sweep"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "reference_on_gpu": ref_gpu}
+                "reference_on_gpu": ref_gpu, "next_rows": next_rows}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

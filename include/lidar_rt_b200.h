@@ -161,6 +161,7 @@ int lrt_chamfer_backward(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, c
  * parameter tensor of every asset is one row of `tensors` (HOST array) and all rows are updated by one launch, with the arithmetic
  * of torch's single-tensor Adam (amsgrad off, no weight decay):
  *   m = m + (g - m)(1 - beta1);  v = v beta2 + ((1 - beta2) g) g;  p = p + (-(lr / (1 - beta1^step)) m) / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * beta1 / beta2 / eps are doubles because torch forms 1 - beta in double before rounding it to the tensor's type.
  * param / exp_avg / exp_avg_sq are updated in place; `step` is the 1-based count of THIS tensor's update (state re-created by
  * densification restarts at 1). */
 typedef struct lrt_adam_tensor {
@@ -169,7 +170,7 @@ typedef struct lrt_adam_tensor {
     float lr;
     int32_t step;
 } lrt_adam_tensor;
-int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, float beta1, float beta2, float eps, void* stream);
+int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, double beta1, double beta2, double eps, void* stream);
 
 /* Tuning knobs; none of them changes results.
  *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill, 2 = 8 lanes per ray,

@@ -73,14 +73,14 @@ __global__ void __launch_bounds__(AD_TB) k_adam(const __grid_constant__ AdamTabl
 
 } // namespace
 
-int lrt_adam_step_impl(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, float beta1, float beta2, float eps, cudaStream_t s)
+int lrt_adam_step_impl(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, double beta1, double beta2, double eps, cudaStream_t s)
 {
     if (n_tensors < 0 || (n_tensors > 0 && !tensors)) { ctx->set_error("lrt_adam_step: bad table"); return LRT_ERR_INVALID; }
     LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     static_assert(sizeof(AdamTable) <= 32000, "the table must fit the kernel parameter space");
     AdamTable t;
     // torch converts the python scalars 1 - beta1, beta2, 1 - beta2, eps to the tensor dtype when the op runs
-    t.w1 = (float)(1.0 - (double)beta1); t.beta2 = beta2; t.w2 = (float)(1.0 - (double)beta2); t.eps = eps;
+    t.w1 = (float)(1.0 - beta1); t.beta2 = (float)beta2; t.w2 = (float)(1.0 - beta2); t.eps = (float)eps;
     int k = 0;
     while (k < n_tensors) {
         t.n_rows = 0; t.n_blocks = 0;
@@ -94,7 +94,7 @@ int lrt_adam_step_impl(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tenso
             if (t.n_blocks + nb > 0x7fffffffLL) break;
             AdamRow& r = t.r[t.n_rows++];
             r.p = e.param; r.g = e.grad; r.m = e.exp_avg; r.v = e.exp_avg_sq; r.n = e.n;
-            const double bc1 = 1.0 - pow((double)beta1, (double)e.step), bc2 = 1.0 - pow((double)beta2, (double)e.step);
+            const double bc1 = 1.0 - pow(beta1, (double)e.step), bc2 = 1.0 - pow(beta2, (double)e.step);
             r.neg_step_size = (float)(-((double)e.lr / bc1));
             r.bc2_sqrt = (float)sqrt(bc2);
             r.block0 = t.n_blocks; r.pad = 0;

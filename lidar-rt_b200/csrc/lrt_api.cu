@@ -134,7 +134,7 @@ int lrt_chamfer_backward(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, c
     return lrt_chamfer_backward_impl(ctx, b, n, xyz1, m, xyz2, grad_dist1, grad_dist2, idx1, idx2, grad_xyz1, grad_xyz2, (cudaStream_t)stream);
 }
 
-int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, float beta1, float beta2, float eps, void* stream)
+int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, double beta1, double beta2, double eps, void* stream)
 {
     if (!ctx) return LRT_ERR_INVALID;
     return lrt_adam_step_impl(ctx, n_tensors, tensors, beta1, beta2, eps, (cudaStream_t)stream);

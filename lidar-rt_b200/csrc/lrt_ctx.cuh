@@ -144,6 +144,6 @@ int lrt_chamfer_forward_impl(lrt_ctx* ctx, int b, int n, const float* xyz1, int 
 int lrt_chamfer_backward_impl(lrt_ctx* ctx, int b, int n, const float* xyz1, int m, const float* xyz2,
                               const float* grad_dist1, const float* grad_dist2, const int32_t* idx1, const int32_t* idx2,
                               float* grad_xyz1, float* grad_xyz2, cudaStream_t s);
-int lrt_adam_step_impl(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, float beta1, float beta2, float eps, cudaStream_t s);
+int lrt_adam_step_impl(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, double beta1, double beta2, double eps, cudaStream_t s);
 int lrt_range_rays_impl(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc_lo, float inc_hi, float pixel_offset,
                         float angle_offset, const float* sensor2world, const float* range_map, float* out, float* centre, cudaStream_t s);

@@ -123,6 +123,46 @@ __global__ void __launch_bounds__(256) k_prepare_sh(const __grid_constant__ Prep
     }
 }
 
+// The same for rows that are a whole number of 16-byte groups (3 M % 4 == 0, shs 16-byte aligned; M = 16 always in the
+// reference): one thread per float4 of the concatenated row, 32-bit index arithmetic, one asset search per four floats.
+// The one-float-per-thread form above spends ~80 instructions per float on a 64-bit division and the search and runs at a
+// third of the copy bandwidth.
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256) k_prepare_sh4(const __grid_constant__ PrepTable t, float4* __restrict__ shs4)
+{
+    const unsigned row = 3u * (unsigned)t.M, row4 = row >> 2;
+    const unsigned n4 = (unsigned)t.total * row4;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += gridDim.x * blockDim.x) {
+        const unsigned i = e / row4, c = (e - i * row4) << 2;          // Gaussian, first float of this group within its row
+        const PrepAsset& a = t.a[find_asset(t, (int)i)];
+        const size_t j = (size_t)((int)i - a.first);
+        const float* __restrict__ rest = a.rest + (size_t)(row - 3) * j;
+        if (!BACKWARD) {
+            float4 v;
+            if (c == 0) v = make_float4(a.dc[3 * j], a.dc[3 * j + 1], a.dc[3 * j + 2], rest[0]);
+            else v = make_float4(rest[c - 3], rest[c - 2], rest[c - 1], rest[c]);
+            shs4[e] = v;
+        } else {
+            const float4 v = shs4[e];
+            float* d_rest = a.d_rest ? a.d_rest + (size_t)(row - 3) * j : nullptr;
+            if (c == 0) {
+                if (a.d_dc) { a.d_dc[3 * j] = v.x; a.d_dc[3 * j + 1] = v.y; a.d_dc[3 * j + 2] = v.z; }
+                if (d_rest) d_rest[0] = v.w;
+            } else if (d_rest) {
+                d_rest[c - 3] = v.x; d_rest[c - 2] = v.y; d_rest[c - 1] = v.z; d_rest[c] = v.w;
+            }
+        }
+    }
+}
+
+template <bool BACKWARD>
+void launch_prepare_sh(const PrepTable& t, float* shs, cudaStream_t s)
+{
+    const bool fast = ((3 * t.M) & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0 && (long long)t.total * (3 * t.M / 4) < 0xffffffffLL - 148 * 32 * 256;
+    if (fast) k_prepare_sh4<BACKWARD><<<148 * 32, 256, 0, s>>>(t, reinterpret_cast<float4*>(shs));
+    else k_prepare_sh<BACKWARD><<<148 * 16, 256, 0, s>>>(t, shs);
+}
+
 __global__ void __launch_bounds__(256) k_prepare_backward(const __grid_constant__ PrepTable t, const float* __restrict__ g_means,
                                                           const float* __restrict__ g_scales, const float* __restrict__ g_rots,
                                                           const float* __restrict__ g_opac)
@@ -215,7 +255,7 @@ int lrt_prepare_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M,
     LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->span_begin("k_prepare", s);
     k_prepare<<<(t.total + 255) / 256, 256, 0, s>>>(t, means, scales, rots, opac);
-    k_prepare_sh<false><<<148 * 16, 256, 0, s>>>(t, shs);
+    launch_prepare_sh<false>(t, shs, s);
     ctx->span_end(s);
     ctx->launches += 2;
     LRT_CUDA_TRY(ctx, cudaGetLastError());
@@ -238,7 +278,7 @@ int lrt_prepare_backward_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* asset
     LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->span_begin("k_prepare_backward", s);
     k_prepare_backward<<<(t.total + 255) / 256, 256, 0, s>>>(t, g_means, g_scales, g_rots, g_opac);
-    k_prepare_sh<true><<<148 * 16, 256, 0, s>>>(t, const_cast<float*>(g_shs));
+    launch_prepare_sh<true>(t, const_cast<float*>(g_shs), s);
     ctx->span_end(s);
     ctx->launches += 2;
     LRT_CUDA_TRY(ctx, cudaGetLastError());

@@ -81,11 +81,12 @@ for _ in range(a.warmup):
 if a.profile:
     from torch.profiler import profile, ProfilerActivity
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=False) as prof:
         for _ in range(10):
             iteration()
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+    print(prof.key_averages(group_by_stack_n=0).table(sort_by="self_cpu_time_total", row_limit=30, max_name_column_width=70))
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(a.iters):
     loss = iteration()
