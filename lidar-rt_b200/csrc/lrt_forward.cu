@@ -545,7 +545,8 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_b, sizeof(uint2) * (size_t)cap_items));
         }
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_hit_count, sizeof(int) * (size_t)R));
-        // bin capacity: 2048 candidates per ray while that stays under ~6 GB, never below what the shared-memory sort takes
+        // bin capacity: 8192 candidates per ray while that stays under ~6 GB (4096 at one Waymo frame), never below what the
+        // shared-memory sort takes
         int hcap = WF_HCAP_MAX;
         while (hcap > WF_HCAP && (size_t)R * hcap * sizeof(unsigned long long) > ((size_t)6 << 30)) hcap >>= 1;
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_bins, sizeof(unsigned long long) * (size_t)R * hcap));
@@ -612,15 +613,15 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             ctx->span_begin("k_wf_shade", s); k_wf_shade<<<min((S + 3) / 4, ctx->num_sms * 8), 128, 0, s>>>(bv, a, w); ctx->span_end(s);
         } else {
             if (ctx->opt_sort_rays) {
-                // rays by descending candidate count (11-bit keys: 2 radix passes over R pairs)
+                // rays by descending candidate count (14-bit keys: 2 radix passes over R pairs)
                 int* order = (int*)ctx->wf_ids.p + R;
                 size_t tb = 0;
                 LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const int*)w.hit_count, (int*)ctx->wf_keys.p,
-                                                                            (const int*)w.ray_ids, order, R, 0, 12, s));
+                                                                            (const int*)w.ray_ids, order, R, 0, 14, s));
                 LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_sort_tmp, tb));
                 ctx->span_begin("ray_order_sort", s);
                 LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairsDescending(ctx->wf_sort_tmp.p, tb, (const int*)w.hit_count, (int*)ctx->wf_keys.p,
-                                                                            (const int*)w.ray_ids, order, R, 0, 12, s));
+                                                                            (const int*)w.ray_ids, order, R, 0, 14, s));
                 ctx->span_end(s);
                 w.order = order;
             }

@@ -20,8 +20,10 @@
 #pragma once
 
 #define WF_HCAP 512                 // bins up to this size are sorted in shared memory (and are all k_wf_shade can take)
-#define WF_HCAP_MAX 2048            // bin capacity per ray in memory (a full, un-culled ray carries ~40 candidates on street scenes;
-                                    // a few grazing rays reach several hundred); beyond it the ray goes to the per-ray fallback
+#define WF_HCAP_MAX 8192            // bin capacity per ray in memory (a full, un-culled ray carries ~40 candidates on street scenes,
+                                    // a few grazing rays several hundred, a ray skimming the side of a vehicle next to the sensor
+                                    // thousands); beyond it the ray goes to the per-ray fallback, which costs MILLISECONDS per ray
+                                    // (one thread re-walking the hierarchy once per 16 hits). Only touched lines cost traffic.
 #define WF_TAINT 0x40000000         // hit_count flag: work item or hit dropped -> fallback
 #define WF_WINDOW_MARGIN 1e-3f
 

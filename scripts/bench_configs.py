@@ -85,10 +85,29 @@ if 3 in want and rank == 0:
         refit = f % a.rebuild_every != 0
         torch.cuda.synchronize()                 # the frame's uploads are not part of the step
         e = [ev() for _ in range(4)]
-        e[0].record(); ctx.build(means, scales, rots, opac, refit=refit)
-        e[1].record(); r = ctx.forward(ro, rd, BG, means, scales, rots, opac, shs, 3)
-        e[2].record(); gr = ctx.backward(ro, rd, BG, means, scales, rots, opac, shs, 3, r["out"], gl, hits=r)
+        import time as _t
+        h = [_t.perf_counter()]
+        na = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        e[0].record(); ctx.build(means, scales, rots, opac, refit=refit); h.append(_t.perf_counter())
+        e[1].record(); r = ctx.forward(ro, rd, BG, means, scales, rots, opac, shs, 3); h.append(_t.perf_counter())
+        e[2].record(); gr = ctx.backward(ro, rd, BG, means, scales, rots, opac, shs, 3, r["out"], gl, hits=r); h.append(_t.perf_counter())
         e[3].record(); torch.cuda.synchronize()
+        if os.environ.get("LRT_VERBOSE") == "2":          # which kernel makes a frame slow: re-run its forward with per-kernel timing
+            fw = e[1].elapsed_time(e[2])
+            if fw > 4.0 or f in (5, 20, 35):
+                import ctypes as _ct
+                ctx.set_option(native.OPT_KERNEL_TIMING, 1); ctx.kernel_times()
+                r3 = ctx.forward(ro, rd, BG, means, scales, rots, opac, shs, 3, want_slots=True); torch.cuda.synchronize()
+                kt = {k: round(v[0], 2) for k, v in ctx.kernel_times().items() if v[0] > 0.05}
+                ctx.set_option(native.OPT_KERNEL_TIMING, 0)
+                c = (_ct.c_int * 16)(); ctx.lib.lrt_debug_counters(ctx._h, c)
+                sl = r3["slot_cnt"]; hcn = r3["hit_cnt"]
+                print("cfg3 frame", f, "fwd ms", round(fw, 2), kt, "fallback rays", c[8], "heavy items", c[9], "slots/ray mean", round(float(sl.float().mean()), 1),
+                      "max", int(sl.max()), ">256:", int((sl > 256).sum()), ">512:", int((sl > 512).sum()), "hits max", int(hcn.max()), flush=True)
+                del r3
+        if os.environ.get("LRT_VERBOSE") == "1" and f < 14:
+            print("cfg3 frame", f, "refit" if refit else "build", "device ms", [round(e[i].elapsed_time(e[i + 1]), 2) for i in range(3)],
+                  "host ms", [round(1e3 * (h[i + 1] - h[i]), 2) for i in range(3)], "cudaMalloc", torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - na, flush=True)
         if f >= 2:
             ts.append([refit] + [e[i].elapsed_time(e[i + 1]) for i in range(3)])
         if refit and f % 7 == 3:        # the refit structure must give what a fresh build of the same frame gives

@@ -287,6 +287,40 @@ def test_kitti_dynamic_refit_long_bins_vs_oracle(ctx, oracle32):
         grad_close(res[f"g_{k}"], b[k], GRAD_REL, f"d_{k}")
 
 
+@pytest.mark.parametrize("n_stack", [700, 3000, 9000])
+def test_very_long_candidate_bins_and_bin_overflow(ctx, oracle32, n_stack):
+    """Rays that cross hundreds to thousands of surfels (a vehicle's side seen at a grazing angle does this): 700 candidates take
+    the in-place global-memory sort, 3000 a 4096-entry bin, 9000 exceed any bin and go to the per-ray fallback. All must equal
+    the per-ray traversal kernel bit for bit and the oracle's hit lists."""
+    from lidar_rt_b200 import native
+    rng = np.random.default_rng(n_stack)
+    P = n_stack + 500
+    means = np.zeros((P, 3), np.float32)
+    means[:n_stack, 0] = 5.0 + 0.002 * np.arange(n_stack); means[:n_stack, 1:] = 0.01 * rng.standard_normal((n_stack, 2))
+    means[n_stack:] = rng.uniform(-20, 20, (P - n_stack, 3)) + np.array([30, 0, 0], np.float32)
+    scales = np.full((P, 2), 0.4, np.float32)
+    rots = np.tile(np.array([np.cos(np.pi / 4), 0, np.sin(np.pi / 4), 0], np.float32), (P, 1))      # normal along +x
+    rots[n_stack:] = rng.standard_normal((P - n_stack, 4))
+    opac = np.full((P, 1), 0.012, np.float32)
+    shs = (0.05 * rng.standard_normal((P, 16, 3))).astype(np.float32); shs[:, 0, :] = 0.5
+    sc = dict(means=means, scales=scales, rots=rots, opac=opac, shs=shs)
+    yy, zz = np.meshgrid(np.linspace(-0.03, 0.03, 8), np.linspace(-0.03, 0.03, 8), indexing="ij")
+    d = np.stack([np.ones_like(yy), yy, zz], -1).astype(np.float32); d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    o = np.zeros((1, 3), np.float32)
+    res = run_cuda(ctx, o, d, sc, 3, cap=256)
+    assert res["slot_cnt"].max() >= 256, "the stack must keep rays alive for hundreds of slots"
+    try:
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 0)
+        ref = run_cuda(ctx, o, d, sc, 3, cap=256)
+    finally:
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 4)
+    _same_forward(res, ref, f"stack of {n_stack}")
+    f = oracle32.forward(o, d.reshape(-1, 3), BG, means, scales, rots, opac, shs, 3, flags=ORC_BVH, cap=256)
+    assert hit_lists(res) == oracle_lists(f), "hit indices must be bit-exact"
+    assert np.array_equal(res["slot_cnt"], f["slot_cnt"])
+    assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
+
+
 def test_full_size_properties(ctx):
     """BASELINE config #2 shape (1M Gaussians, 64 x 2650 rays): size-independent invariants."""
     sc = syn.make_street_scene(1_000_000, seed=1)
