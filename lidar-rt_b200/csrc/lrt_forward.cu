@@ -551,14 +551,14 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         while (hcap > WF_HCAP && (size_t)R * hcap * sizeof(unsigned long long) > ((size_t)6 << 30)) hcap >>= 1;
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_bins, sizeof(unsigned long long) * (size_t)R * hcap));
         w.hcap = hcap;
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_fb, sizeof(int) * (size_t)R));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_fb, sizeof(int) * (size_t)R * 2));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_ids, sizeof(int) * (size_t)R * 2));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_keys, sizeof(int) * (size_t)R));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 16));
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 16, s));
         w.rs = (RaySetup*)ctx->wf_rs.p; w.list_a = (uint2*)ctx->wf_list_a.p; w.list_b = (uint2*)ctx->wf_list_b.p;
         w.cap_items = (int)cap_items; w.counts = (int*)ctx->counter.p; w.hit_count = (int*)ctx->wf_hit_count.p;
-        w.bins = (unsigned long long*)ctx->wf_bins.p; w.fb_list = (int*)ctx->wf_fb.p;
+        w.bins = (unsigned long long*)ctx->wf_bins.p; w.fb_list = (int*)ctx->wf_fb.p; w.big_list = (int*)ctx->wf_fb.p + R;
         w.ray_ids = (int*)ctx->wf_ids.p; w.order = nullptr;
         if (ctx->num_sms == 0) {
             int sms = 0;
@@ -625,7 +625,15 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                 ctx->span_end(s);
                 w.order = order;
             }
-            ctx->span_begin("k_wf_sort", s); k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w); ctx->span_end(s);
+            ctx->span_begin("k_wf_sort", s);
+            k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w);
+            {   // the few bins beyond 512 candidates: one block each, keys in dynamic shared memory (64 KB at hcap = 8192)
+                const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
+                LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
+            }
+            ctx->span_end(s);
+            ctx->launches += 1;
             ctx->span_begin("k_wf_composite", s);
             if (ctx->opt_wavefront_shade == 2) k_wf_composite2<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
             else k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);

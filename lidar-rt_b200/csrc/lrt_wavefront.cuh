@@ -31,11 +31,12 @@ struct WfBufs {
     RaySetup* rs;                   // (R) per-ray slab constants for base = 0
     uint2* list_a; uint2* list_b;   // ping-pong work lists {ray, node}
     int cap_items;
-    int* counts;                    // [0..7] items per level, [8] fallback count
+    int* counts;                    // [0..7] items per level, [8] fallback count, [9] heavy beam-grid items, [10] bins beyond 512 candidates
     int* hit_count;                 // (R) hits in bin | WF_TAINT
     unsigned long long* bins;       // (R, hcap)
     int hcap;                       // bin capacity (<= WF_HCAP_MAX)
     int* fb_list;                   // (R) fallback ray ids
+    int* big_list;                  // (R) rays whose bin holds more than WF_HCAP candidates: sorted by k_wf_sort_big, one block each
     int* ray_ids;                   // (R) identity, input of the by-length sort
     const int* order;               // (R) rays sorted by descending candidate count, or nullptr (tile order)
 };
@@ -454,26 +455,55 @@ __global__ void __launch_bounds__(128) k_wf_sort(FwdArgs a, WfBufs w)
             for (int j = 0; j < 8; j++) if (lane + 32 * j < n) bin[lane + 32 * j] = k[j];
             continue;
         }
-        int m = 512; while (m < n) m <<= 1;
-        // shared memory for the common sizes; the few bins beyond WF_HCAP are sorted in place in global memory
-        // (padding entries up to m live in the bin itself: m <= hcap because hcap is a power of two)
-        unsigned long long* buf = (m <= WF_HCAP) ? keys : bin;
-        if (buf == keys) { for (int i = lane; i < m; i += 32) keys[i] = i < n ? bin[i] : LRT_KEY_EMPTY; }
-        else { for (int i = n + lane; i < m; i += 32) bin[i] = LRT_KEY_EMPTY; }
+        if (n > WF_HCAP) {                                         // a whole block sorts it (k_wf_sort_big): one warp would take ~1 ms alone
+            if (lane == 0) w.big_list[atomicAdd(w.counts + 10, 1)] = r;
+            continue;
+        }
+        const int m = WF_HCAP;                                     // 257..512 candidates: this warp's slice of shared memory
+        for (int i = lane; i < m; i += 32) keys[i] = i < n ? bin[i] : LRT_KEY_EMPTY;
         __syncwarp(FULL);
         for (int size = 2; size <= m; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 for (int i = lane; i < (m >> 1); i += 32) {
                     const int lo = ((i / stride) * stride * 2) + (i % stride), hi = lo + stride;
-                    const unsigned long long x = buf[lo], y = buf[hi];
+                    const unsigned long long x = keys[lo], y = keys[hi];
                     const bool up = ((lo & size) == 0);
-                    if ((x > y) == up) { buf[lo] = y; buf[hi] = x; }
+                    if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
                 }
                 __syncwarp(FULL);
             }
         }
-        if (buf == keys) { for (int i = lane; i < n; i += 32) bin[i] = keys[i]; }
+        for (int i = lane; i < n; i += 32) bin[i] = keys[i];
         __syncwarp(FULL);
+    }
+}
+
+// Bins beyond WF_HCAP candidates (a ray skimming a wall or a vehicle's side: hundreds to thousands), listed by k_wf_sort: one
+// 256-thread block per bin, bitonic sort of up to hcap (<= 8192) keys in dynamic shared memory (8 B x hcap).
+__global__ void __launch_bounds__(256) k_wf_sort_big(FwdArgs a, WfBufs w)
+{
+    extern __shared__ unsigned long long s_big[];
+    const int nbig = min(w.counts[10], a.R);
+    for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
+        const int r = w.big_list[b];
+        const int n = min(w.hit_count[r] & (WF_TAINT - 1), w.hcap);
+        unsigned long long* bin = w.bins + (size_t)r * w.hcap;
+        int m = 2 * WF_HCAP; while (m < n) m <<= 1;                // <= hcap: hcap is a power of two
+        for (int i = threadIdx.x; i < m; i += blockDim.x) s_big[i] = i < n ? bin[i] : LRT_KEY_EMPTY;
+        __syncthreads();
+        for (int size = 2; size <= m; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
+                    const int lo = ((i / stride) * stride * 2) + (i % stride), hi = lo + stride;
+                    const unsigned long long x = s_big[lo], y = s_big[hi];
+                    const bool up = ((lo & size) == 0);
+                    if ((x > y) == up) { s_big[lo] = y; s_big[hi] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) bin[i] = s_big[i];
+        __syncthreads();
     }
 }
 
