@@ -132,7 +132,9 @@ class FusedAdam(torch.optim.Optimizer):
 
     def state_dict(self):
         self._flush_steps()
-        return super().state_dict()
+        sd = super().state_dict()
+        sd["state"] = {k: dict(v) for k, v in sd["state"].items()}      # plain dicts: nothing of this optimizer travels with a saved state
+        return sd
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)

@@ -68,6 +68,24 @@ def test_fused_adam_has_torch_adams_interface_and_fails_loudly_on_cpu():
     sd = opt.state_dict(); opt.load_state_dict(sd)
 
 
+def test_fused_adam_state_dict_is_plain_and_picklable():
+    import pickle
+    from lidar_rt_b200.optim import FusedAdam, _State
+    p = torch.zeros(4, 3, requires_grad=True)
+    opt = FusedAdam([{"params": [p], "lr": 0.1, "name": "xyz"}], lr=0.0, eps=1e-15)
+    st = _State(step=torch.tensor(3.0), exp_avg=torch.ones(4, 3), exp_avg_sq=torch.ones(4, 3)); st.owner = opt
+    opt.state[p] = st
+    sd = opt.state_dict()
+    assert type(sd["state"][0]) is dict and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    blob = pickle.dumps(sd)
+    assert len(blob) < 4000, "a saved state must not drag the optimizer along"
+    opt2 = FusedAdam([{"params": [torch.zeros(4, 3, requires_grad=True)], "lr": 0.1, "name": "xyz"}], lr=0.0, eps=1e-15)
+    opt2.load_state_dict(pickle.loads(blob))
+    assert int(opt2.state_dict()["state"][0]["step"]) == 3
+    st["exp_avg"] = torch.zeros(4, 3)               # an outside edit (densification) marks the native table stale
+    assert opt._dirty
+
+
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "lidar-rt_b200"))
