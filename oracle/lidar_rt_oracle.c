@@ -68,6 +68,10 @@ typedef float real;
 #define ORC_TRIANGLES 1          /* literal two-triangle proxy instead of the analytic quad */
 #define ORC_BVH 2                /* candidate filter (median BVH) instead of testing every Gaussian */
 #define ORC_FIX_BG 4             /* drop the duplicated background term of backward.cu:595-598 */
+#define ORC_FLAT 8               /* ANALYSIS MODE, not the reference's arithmetic: the ray's hits are collected ONCE from the original
+                                  * origin and walked in (t, id) order; a round is the next 16 of them with t > base, and the depth of a
+                                  * hit is its t (the reference re-traces from o + base d each round and uses t' + base). Same rules
+                                  * otherwise. Quantifies what a candidate-parallel evaluation of the hits would change. */
 
 static const real SH_C0 = (real)0.28209479177387814;          /* auxiliary.h:23-40 */
 static const real SH_C1 = (real)0.4886025119029199;
@@ -416,18 +420,28 @@ static void ray_program(const job_t* J, int r, const real* ro, const real* rd, h
         for (int c = 0; c < 3; c++) { F_c[c] = J->fwd_out[ORC_NCH * r + c]; F_n[c] = J->fwd_out[ORC_NCH * r + 5 + c]; }
         F_d = J->fwd_out[ORC_NCH * r + 3]; F_T = J->fwd_out[ORC_NCH * r + 8];
     }
+    const int flat = (J->flags & ORC_FLAT) != 0;
+    int fpos = 0;                                    /* ORC_FLAT: next unread hit of the one list */
+    if (flat) collect_hits(s, ro, rd, J->flags, hb);
     for (;;) {
         const real om[3] = {ro[0] + base * rd[0], ro[1] + base * rd[1], ro[2] + base * rd[2]};   /* forward.cu:291 */
-        collect_hits(s, om, rd, J->flags, hb);
-        const int cnt = hb->n;                       /* >= 16 iff the k-buffer filled */
+        int cnt, first = 0;
+        if (!flat) {
+            collect_hits(s, om, rd, J->flags, hb);
+            cnt = hb->n;                             /* >= 16 iff the k-buffer filled */
+        } else {
+            while (fpos < hb->n && !(hb->h[fpos].t > base)) fpos++;      /* t' = t - base > 0 */
+            first = fpos; cnt = hb->n - fpos;
+        }
         const int lim = cnt < ORC_CHUNK ? cnt : ORC_CHUNK;
+        if (flat) fpos += lim;
         int terminated = 0;
-        for (int i = 0; i < lim; i++) {
+        for (int i = first; i < first + lim; i++) {
             const int pid = hb->h[i].id;
             const int gi = (J->flags & ORC_TRIANGLES) ? pid / 2 : pid;
             const gauss_t* g = &s->g[gi];
             nslots++;
-            dpt = hb->h[i].t + base;                                     /* forward.cu:212 */
+            dpt = flat ? hb->h[i].t : hb->h[i].t + base;                 /* forward.cu:212 */
             const real xyz[3] = {ro[0] + dpt * rd[0], ro[1] + dpt * rd[1], ro[2] + dpt * rd[2]};
             if (dpt < (real)0.2) continue;                               /* :214 */
             if (gi == last) continue;                                    /* :220-224 */

@@ -23,6 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORC_TRIANGLES = 1
 ORC_BVH = 2
 ORC_FIX_BG = 4
+ORC_FLAT = 8          # analysis mode: one hit list from the original origin, depth = t (lidar_rt_oracle.c)
 
 
 def build(quiet: bool = True) -> None:

@@ -205,3 +205,15 @@ def test_backward_is_the_gradient_fp64_finite_differences(oracle64):
     dL0 = dL.copy(); dL0[:, :3] = 0
     a = oracle64.backward(*args_of(params), out0, dL0, flags=0); b = oracle64.backward(*args_of(params), out0, dL0, flags=ORC_FIX_BG)
     assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_flat_depth_analysis_mode_stays_within_tolerance_of_reference_mode(oracle32):
+    """ORC_FLAT (one hit list from the original origin, depth = t) is an analysis mode: on config #1 it must give the
+    reference-mode hit lists on every ray and outputs within the 1e-4 parity tolerance."""
+    from oracle.oracle import ORC_FLAT
+    sc = syn.make_street_scene(10_000, seed=0)
+    o, d = syn.ray_patch(64, 64)
+    a = (o, d.reshape(-1, 3), BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, 3)
+    f0 = oracle32.forward(*a, flags=ORC_BVH, cap=128); f1 = oracle32.forward(*a, flags=ORC_BVH | ORC_FLAT, cap=128)
+    assert np.array_equal(f0["hit_cnt"], f1["hit_cnt"]) and np.array_equal(f0["hit_list"], f1["hit_list"])
+    assert (np.abs(f0["out"] - f1["out"]) / (1.0 + np.abs(f0["out"]))).max() < 1e-4
