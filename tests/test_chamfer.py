@@ -60,6 +60,19 @@ def test_oracle_vs_fp64_brute_force_and_tie_rule(chm):
     assert np.array_equal(i1[0], D.argmin(1)) and np.array_equal(d1[0], D.min(1))      # numpy argmin = first occurrence
 
 
+def test_oracle_vs_independent_kd_tree(chm):
+    """An implementation that shares nothing with the oracle (scipy's cKDTree, fp64): same nearest distances on LiDAR-shaped clouds;
+    same neighbour wherever the nearest distance is not tied within fp32 resolution."""
+    from scipy.spatial import cKDTree
+    pr, gt = lidar_clouds(20000, seed=4)
+    d1, d2, i1, i2 = chm.forward(pr[None], gt[None])
+    for (q, t, d, i) in ((pr, gt, d1[0], i1[0]), (gt, pr, d2[0], i2[0])):
+        dist, idx = cKDTree(t.astype(np.float64)).query(q.astype(np.float64), k=2)
+        assert np.allclose(d, dist[:, 0] ** 2, rtol=2e-5, atol=1e-10)
+        clear = dist[:, 1] ** 2 - dist[:, 0] ** 2 > 1e-5 * (1.0 + dist[:, 0] ** 2)      # runner-up clearly farther
+        assert clear.mean() > 0.9 and np.array_equal(i[clear], idx[clear, 0])
+
+
 def test_oracle_backward_is_the_gradient(chm):
     rng = np.random.default_rng(4)
     a = rng.normal(size=(2, 300, 3)).astype(np.float32); c = rng.normal(size=(2, 200, 3)).astype(np.float32)
