@@ -189,7 +189,10 @@ int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, d
  *   LRT_OPT_BEAM_CELL_PCT   beam grid: cell edge in percent of the size that gives one ray per cell (default 100)
  *   LRT_OPT_KERNEL_TIMING   1 = record CUDA events around every kernel launch (read with lrt_get_kernel_times)
  *   LRT_OPT_WAVEFRONT_SHADE wavefront compositing: 0 = one warp per ray, 1 = warp sort + one thread per ray,
- *                           2 = 1 with pipelined record loads and slot opacities computed on acceptance (default)
+ *                           2 = 1 with pipelined record loads and slot opacities computed on acceptance (default),
+ *                           3 = EXPERIMENTAL and the one value that DOES change results (ulp-level, ~0.07 % of rays): depth of a hit
+ *                               taken from the ray's own origin instead of the round's re-based origin; not yet
+ *                               verified on a GPU
  *   LRT_OPT_MORTON_BITS     32 = 32-bit keys, bits dealt to the axes so cells stay cubic (default); 63 = 21 bits/axis on
  *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build) */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,

@@ -149,7 +149,7 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
     case LRT_OPT_BEAM_CELL_PCT: if (value < 10 || value > 1000) break; ctx->opt_beam_cell_pct = value; return LRT_OK;
     case LRT_OPT_SORT_RAYS: if (value != 0 && value != 1) break; ctx->opt_sort_rays = value; return LRT_OK;
     case LRT_OPT_KERNEL_TIMING: if (value != 0 && value != 1) break; ctx->opt_kernel_timing = value; return LRT_OK;
-    case LRT_OPT_WAVEFRONT_SHADE: if (value < 0 || value > 2) break; ctx->opt_wavefront_shade = value; return LRT_OK;
+    case LRT_OPT_WAVEFRONT_SHADE: if (value < 0 || value > 3) break; ctx->opt_wavefront_shade = value; return LRT_OK;
     case LRT_OPT_BACKWARD_KERNEL: if (value < 0 || value > 2) break; ctx->opt_backward_kernel = value; return LRT_OK;
     case LRT_OPT_MORTON_BITS: if (value != 30 && value != 32 && value != 63) break; ctx->opt_morton_bits = value; return LRT_OK;
     case LRT_OPT_VECTOR_ATOMICS: if (value != 0 && value != 1) break; ctx->opt_vector_atomics = value; return LRT_OK;

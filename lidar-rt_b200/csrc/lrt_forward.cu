@@ -635,7 +635,8 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             ctx->span_end(s);
             ctx->launches += 1;
             ctx->span_begin("k_wf_composite", s);
-            if (ctx->opt_wavefront_shade == 2) k_wf_composite2<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
+            if (ctx->opt_wavefront_shade == 3) k_wf_composite_flat<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);     // experimental, see its header
+            else if (ctx->opt_wavefront_shade == 2) k_wf_composite2<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
             else k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
             ctx->span_end(s);
             ctx->launches += 1;

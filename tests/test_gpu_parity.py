@@ -7,6 +7,8 @@ Tolerances (north_star: fp32 within 1e-4 on depth/intensity, bit-exact hit indic
                    |a-b| <= 2e-5 + 2e-5 |b|   vs the oracle (same arithmetic except expf/logf ulps)
    gradients       max|a-b| / max|b| <= 2e-3  (float atomics reorder sums; reference says the same, train.py:51-64)
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -317,6 +319,24 @@ def test_very_long_candidate_bins_and_bin_overflow(ctx, oracle32, n_stack):
     _same_forward(res, ref, f"stack of {n_stack}")
     f = oracle32.forward(o, d.reshape(-1, 3), BG, means, scales, rots, opac, shs, 3, flags=ORC_BVH, cap=256)
     assert hit_lists(res) == oracle_lists(f), "hit indices must be bit-exact"
+    assert np.array_equal(res["slot_cnt"], f["slot_cnt"])
+    assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
+
+
+@pytest.mark.skipif(not os.environ.get("LRT_EXPERIMENTAL"), reason="experimental kernel, not yet verified on a GPU (DESIGN.md 7.1): set LRT_EXPERIMENTAL=1")
+def test_flat_depth_compositing_vs_flat_oracle(ctx, oracle32):
+    """LRT_OPT_WAVEFRONT_SHADE = 3 (depth of a hit from the ray's own origin) against the oracle's ORC_FLAT mode: hit lists bit-exact."""
+    from lidar_rt_b200 import native
+    from oracle.oracle import ORC_FLAT
+    sc = syn.make_street_scene(200_000, seed=5)
+    o, d = syn.ray_patch(16, 512, frame=2)
+    try:
+        ctx.set_option(native.OPT_WAVEFRONT_SHADE, 3)
+        res = run_cuda(ctx, o, d, as_dict(sc), 3, cap=96)
+    finally:
+        ctx.set_option(native.OPT_WAVEFRONT_SHADE, 2)
+    f = oracle32.forward(o, d, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, 3, flags=ORC_BVH | ORC_FLAT, cap=96)
+    assert hit_lists(res) == oracle_lists(f), "hit indices must be bit-exact against the flat-mode oracle"
     assert np.array_equal(res["slot_cnt"], f["slot_cnt"])
     assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
 
