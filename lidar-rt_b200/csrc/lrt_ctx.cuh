@@ -15,6 +15,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+#define LRT_INTERNAL_HIT_CAP 256  // hit-list depth of the split forward passes when the caller records no lists
 #define LRT_CH_MAX_LEVELS 10      // chamfer point hierarchy, 8-wide: 8^10 points
 
 struct lrt_ctx {
@@ -31,6 +32,7 @@ struct lrt_ctx {
     DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, rec_g, sort_tmp, bounds, counter;
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
     DevBuf bw_off, bw_rec_a, bw_rec_b;   // hit-parallel backward (lrt_backward.cu)
+    DevBuf sp_cnt, sp_rec, sp_scan_tmp, sp_hits;   // split forward passes (lrt_split.cuh): slice offsets, sorted record stream, internal hit lists
     DevBuf bg_ang, bg_cell_of, bg_cells, bg_sray, bg_wide, bg_plan;   // shared-origin beam grid (lrt_beamgrid.cuh)
     // chamfer distance (lrt_chamfer.cu): one Morton-sorted point hierarchy per cloud, rebuilt every call
     struct ChTree {
@@ -45,8 +47,9 @@ struct lrt_ctx {
     int opt_forward_kernel = 4;   // 0: one thread per ray, 1: persistent threads with per-lane refill, 2: 8 lanes per ray, 3: wavefront,
                                   // 4: shared-origin beam grid (frames with per-ray origins take 3)
     int opt_ray_grid_w = 0;       // > 0: rays are a row-major range image of this width (enables 4 x 8 warp tiles)
-    int opt_wavefront_shade = 2;  // wavefront compositing: 0 = one warp per ray (k_wf_shade), 1 = warp-sort + one thread per ray,
-                                  // 2 = the same with pipelined record loads and opacities computed when a slot is accepted (default)
+    int opt_wavefront_shade = 3;  // wavefront compositing: 0 = one warp per ray (k_wf_shade), 1 = warp-sort + one thread per ray,
+                                  // 2 = the same with pipelined record loads and opacities computed when a slot is accepted,
+                                  // 3 = split passes over a sorted record stream: slots / colour / fold (lrt_split.cuh, default)
     int opt_beam_cell_pct = 100;  // beam grid: cell edge in percent of the one-ray-per-cell size
     int opt_sort_rays = 1;        // composite / backward replay: process rays in order of descending list length (lanes stay in step)
     int opt_backward_kernel = 2;  // 0: one thread per ray replays its hit list, 1: one warp per ray, one hit per lane (scans),
@@ -104,7 +107,7 @@ struct lrt_ctx {
         return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
                bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
-               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap + ch_keys_a.cap + ch_keys_b.cap + ch_idx_a.cap + ch_idx_b.cap;
+               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + sp_cnt.cap + sp_rec.cap + sp_scan_tmp.cap + sp_hits.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap + ch_keys_a.cap + ch_keys_b.cap + ch_idx_a.cap + ch_idx_b.cap;
     }
     BvhView view() const
     {

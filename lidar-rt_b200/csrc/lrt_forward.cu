@@ -100,7 +100,7 @@ __device__ __forceinline__ bool fwd_shade_round(FwdRay& q, const unsigned long l
         }
         q.C0 += w * c[0]; q.C1 += w * c[1]; q.C2 += w * c[2];
         q.Dp += w * q.dpt; q.W += w;
-        atomicAdd(a.accum_w + g, w);                                              // :272
+        if (a.accum_w) atomicAdd(a.accum_w + g, w);                               // :272 (nullptr: redone ray, weights already accumulated)
         if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
             a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g;
             a.hit_t[(size_t)q.ncontrib * a.R + q.r] = q.dpt;
@@ -493,6 +493,7 @@ __global__ void __launch_bounds__(128, LRT_G8_MIN_BLOCKS) k_forward_g8(BvhView b
 }
 
 #include "lrt_wavefront.cuh"
+#include "lrt_split.cuh"
 #include "lrt_beamgrid.cuh"
 
 } // namespace
@@ -551,7 +552,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         while (hcap > WF_HCAP && (size_t)R * hcap * sizeof(unsigned long long) > ((size_t)6 << 30)) hcap >>= 1;
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_bins, sizeof(unsigned long long) * (size_t)R * hcap));
         w.hcap = hcap;
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_fb, sizeof(int) * (size_t)R * 2));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_fb, sizeof(int) * (size_t)R * 3));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_ids, sizeof(int) * (size_t)R * 2));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_keys, sizeof(int) * (size_t)R));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 16));
@@ -559,6 +560,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         w.rs = (RaySetup*)ctx->wf_rs.p; w.list_a = (uint2*)ctx->wf_list_a.p; w.list_b = (uint2*)ctx->wf_list_b.p;
         w.cap_items = (int)cap_items; w.counts = (int*)ctx->counter.p; w.hit_count = (int*)ctx->wf_hit_count.p;
         w.bins = (unsigned long long*)ctx->wf_bins.p; w.fb_list = (int*)ctx->wf_fb.p; w.big_list = (int*)ctx->wf_fb.p + R;
+        w.ov_list = (int*)ctx->wf_fb.p + 2 * (size_t)R;
         w.ray_ids = (int*)ctx->wf_ids.p; w.order = nullptr;
         if (ctx->num_sms == 0) {
             int sms = 0;
@@ -612,7 +614,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         if (ctx->opt_wavefront_shade == 0) {
             ctx->span_begin("k_wf_shade", s); k_wf_shade<<<min((S + 3) / 4, ctx->num_sms * 8), 128, 0, s>>>(bv, a, w); ctx->span_end(s);
         } else {
-            if (ctx->opt_sort_rays) {
+            if (ctx->opt_sort_rays && ctx->opt_wavefront_shade != 3) {
                 // rays by descending candidate count (14-bit keys: 2 radix passes over R pairs)
                 int* order = (int*)ctx->wf_ids.p + R;
                 size_t tb = 0;
@@ -625,23 +627,72 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                 ctx->span_end(s);
                 w.order = order;
             }
-            ctx->span_begin("k_wf_sort", s);
-            k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w);
-            {   // the few bins beyond 512 candidates: one block each, keys in dynamic shared memory (64 KB at hcap = 8192)
-                const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
-                LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
+            if (ctx->opt_wavefront_shade == 3) {
+                // ---- split passes (lrt_split.cuh): sort + gather into one sorted record stream, slots / colour / fold
+                SpBufs sp;
+                long long capacity = (long long)R * 96; if (capacity < (1LL << 20)) capacity = 1LL << 20;
+                sp.capacity = capacity;
+                LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sp_cnt, sizeof(int) * 2 * ((size_t)R + 1)));
+                LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sp_rec, sizeof(float4) * 4 * (size_t)capacity));
+                sp.ccnt = (int*)ctx->sp_cnt.p; sp.cbase = sp.ccnt + (R + 1); sp.srec = (float4*)ctx->sp_rec.p;
+                size_t tb = 0;
+                LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)sp.ccnt, sp.cbase, R + 1, s));
+                LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sp_scan_tmp, tb));
+                // the passes talk through the hit lists: the caller's (kept for the backward) or the context's own
+                if (!a.hit_gidx || !a.hit_aux) {
+                    const int icap = a.hit_gidx ? a.cap : LRT_INTERNAL_HIT_CAP;
+                    const size_t per = (size_t)icap * R;
+                    LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sp_hits, per * (sizeof(int32_t) + sizeof(float) + sizeof(float4)) + sizeof(int32_t) * (size_t)R + 64));
+                    char* base_ = (char*)ctx->sp_hits.p;
+                    float4* i_aux = (float4*)base_; int32_t* i_g = (int32_t*)(base_ + per * sizeof(float4));
+                    float* i_t = (float*)(i_g + per); int32_t* i_c = (int32_t*)(i_t + per);
+                    if (!a.hit_gidx) { a.hit_gidx = i_g; a.hit_t = i_t; a.hit_cnt = i_c; a.cap = icap; }
+                    a.hit_aux = i_aux;
+                }
+                ctx->span_begin("k_sp_sort", s);
+                k_sp_counts<<<(R + 1 + 255) / 256, 256, 0, s>>>(R, w, sp);
+                LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->sp_scan_tmp.p, tb, (const int*)sp.ccnt, sp.cbase, R + 1, s));
+                k_sp_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(bv, a, w, sp);
+                {   // the few bins beyond 512 candidates: one block each (sort in place, then gather)
+                    const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
+                    LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
+                    k_sp_gather_big<<<ctx->num_sms, 256, 0, s>>>(bv, a, w, sp);
+                }
+                ctx->span_end(s);
+                LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));
+                ctx->span_begin("k_sp_slots", s); k_sp_slots<<<(R + 127) / 128, 128, SP_SLOTS_SMEM, s>>>(a, w, sp); ctx->span_end(s);
+                ctx->span_begin("k_sp_colour", s);
+                if ((a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)) k_sp_colour<true><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
+                else k_sp_colour<false><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
+                ctx->span_end(s);
+                ctx->span_begin("k_sp_fold", s); k_sp_fold<<<(R + 127) / 128, 128, 0, s>>>(a); ctx->span_end(s);
+                ctx->launches += 9;
+            } else {
+                ctx->span_begin("k_wf_sort", s);
+                k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w);
+                {   // the few bins beyond 512 candidates: one block each, keys in dynamic shared memory (64 KB at hcap = 8192)
+                    const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
+                    LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
+                }
+                ctx->span_end(s);
+                ctx->launches += 1;
+                ctx->span_begin("k_wf_composite", s);
+                if (ctx->opt_wavefront_shade == 2) k_wf_composite2<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
+                else k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
+                ctx->span_end(s);
+                ctx->launches += 1;
             }
-            ctx->span_end(s);
-            ctx->launches += 1;
-            ctx->span_begin("k_wf_composite", s);
-            if (ctx->opt_wavefront_shade == 3) k_wf_composite_flat<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);     // experimental, see its header
-            else if (ctx->opt_wavefront_shade == 2) k_wf_composite2<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
-            else k_wf_composite<<<(S + 127) / 128, 128, 0, s>>>(bv, a, w);
-            ctx->span_end(s);
+        }
+        ctx->span_begin("k_wf_fallback", s);
+        k_wf_fallback<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
+        if (ctx->opt_wavefront_shade == 3) {        // rays whose hit list outgrew cap: redone per ray, weights already accumulated
+            FwdArgs a2 = a; a2.accum_w = nullptr;
+            k_wf_fallback_overflow<<<ctx->num_sms, 128, 0, s>>>(bv, a2, w);
             ctx->launches += 1;
         }
-        ctx->span_begin("k_wf_fallback", s); k_wf_fallback<<<ctx->num_sms, 128, 0, s>>>(bv, a, w); ctx->span_end(s);
+        ctx->span_end(s);
         ctx->launches += 2;
     } else if (ctx->opt_forward_kernel == 2) {
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 4));

@@ -1,0 +1,381 @@
+// lrt_split.cuh — forward compositing as SPLIT PASSES (default, LRT_OPT_WAVEFRONT_SHADE = 3).
+// Included by lrt_forward.cu inside its anonymous namespace, after lrt_wavefront.cuh (shares WfBufs, the candidate bins, the
+// register sorts, k_wf_sort_big and the fallbacks).
+//
+// k_wf_composite2 (one thread per ray doing everything) was bound by exposed load latency: 168 registers, 17 % of the warps
+// resident, each thread walking a chain of dependent gathers bin key -> 64 B surfel record -> 192 B SH row (ncu:
+// profiles/r1_j_composite_stalls.txt, profiles/r2_a_fwd_chain_before_ncu.txt). The reference's round loop (forward.cu:195-292) is
+// only sequential in WHICH hits become slots and how the transmittance evolves; the colour of a hit depends on nothing but the
+// ray direction and the Gaussian's SH row. So the work is cut where the dependencies are:
+//
+// Rays are taken in their natural order by every pass (the by-length ordering of the one-kernel form scattered the hit-list
+// writes and the per-Gaussian atomics of neighbouring lanes over unrelated rays: 0.34 -> 0.29 ms for pass A without it).
+//
+//   k_sp_sort    one WARP per ray (as k_wf_sort): sorts the ray's candidate bin by (t from the origin, id) in registers, then
+//                every lane GATHERS the 64-byte surfel record of its candidate and writes it, in sorted order, to the ray's
+//                slice of one contiguous stream (slice offsets = exclusive scan of the candidate counts). 32 gathers in flight
+//                per warp instead of one per thread; the candidate's t rides in the record's spare word.
+//   k_sp_slots   pass A, one THREAD per ray: the round loop — exact re-test from the re-based origin, 16-slot k-buffer,
+//                opacity, termination — reading its candidates as a sequential stream (addresses known up front, no key ->
+//                record dependency, neighbouring candidates share cache lines). No SH: writes (id, depth, alpha) of every
+//                contributing hit, the per-Gaussian weights, and the channels that do not depend on colour (depth, accum, T).
+//   k_sp_colour  pass B, one thread per (ray, hit): SH colour of every recorded hit at full occupancy, in natural ray order
+//                (neighbouring rays hit the same Gaussians: each SH row comes from DRAM about once per frame instead of once per
+//                ray that touches it out of a by-length-sorted order).
+//   k_sp_fold    pass C, one thread per ray: the ordered fold C += (alpha T) c over the ray's recorded (alpha, colour), coalesced
+//                across rays -> out[0:3].
+// The arithmetic of every output is operation for operation that of fwd_shade_round(): results are bit-identical to the other
+// forward kernels (tests/test_gpu_parity.py::test_all_forward_kernels_and_options_agree_bitwise).
+#pragma once
+
+struct SpBufs {
+    int* ccnt;                      // (R + 1) candidates per ray that go through the stream (0: ray handed to the fallback)
+    int* cbase;                     // (R + 1) exclusive scan of ccnt = first record of each ray's slice
+    float4* srec;                   // the stream: 4 x float4 per candidate = SurfelRec with r3.w = t from the ray's origin
+    long long capacity;             // records the stream can hold
+};
+
+__global__ void __launch_bounds__(256) k_sp_counts(int R, WfBufs w, SpBufs sp)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > R) return;
+    int c = 0;
+    if (r < R) { const int hc = w.hit_count[r]; c = ((hc & WF_TAINT) || hc > w.hcap) ? 0 : hc; }
+    sp.ccnt[r] = c;
+}
+
+// gather the record of candidate `key` and drop it at its sorted position of the stream
+__device__ __forceinline__ void sp_emit(const SurfelRec* __restrict__ rec_g, float4* __restrict__ dst, unsigned long long key)
+{
+    const int g = (int)(unsigned)(key & 0xffffffffull);
+    const float4 r0 = ld_f4(&rec_g[g].r0), r1 = ld_f4(&rec_g[g].r1), r2 = ld_f4(&rec_g[g].r2);
+    float4 r3 = ld_f4(&rec_g[g].r3);
+    r3.w = __uint_as_float((unsigned)(key >> 32));
+    dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
+}
+
+// One warp per ray.
+__global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs w, SpBufs sp)
+{
+    __shared__ unsigned long long s_keys[4][WF_HCAP];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned long long* keys = s_keys[wib];
+    const SurfelRec* __restrict__ rec_g = bvh.rec_g;
+    for (int s = blockIdx.x * 4 + wib; s < a.R; s += gridDim.x * 4) {
+        const int r = w.order ? w.order[s] : s;
+        const int n = sp.ccnt[r];
+        if (n <= 0) continue;
+        const long long base = sp.cbase[r];
+        if (base + n > sp.capacity) {                              // the stream is full: this ray takes the per-ray fallback
+            if (lane == 0) atomicOr(w.hit_count + r, WF_TAINT);
+            continue;
+        }
+        const unsigned long long* bin = w.bins + (size_t)r * w.hcap;
+        float4* dst = sp.srec + 4 * (size_t)base;
+        if (n <= 32) {
+            unsigned long long k = lane < n ? bin[lane] : LRT_KEY_EMPTY;
+            k = warp_sort32(k, lane);
+            if (lane < n) sp_emit(rec_g, dst + 4 * lane, k);
+            continue;
+        }
+        if (n <= 64) {
+            unsigned long long k0 = bin[lane], k1 = lane + 32 < n ? bin[lane + 32] : LRT_KEY_EMPTY;
+            warp_sort64(k0, k1, lane);
+            sp_emit(rec_g, dst + 4 * lane, k0);
+            if (lane + 32 < n) sp_emit(rec_g, dst + 4 * (lane + 32), k1);
+            continue;
+        }
+        if (n <= 128) {
+            unsigned long long k[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) k[j] = lane + 32 * j < n ? bin[lane + 32 * j] : LRT_KEY_EMPTY;
+            warp_sort_regs<4>(k, lane);
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (lane + 32 * j < n) sp_emit(rec_g, dst + 4 * (lane + 32 * j), k[j]);
+            continue;
+        }
+        if (n <= 256) {
+            unsigned long long k[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) k[j] = lane + 32 * j < n ? bin[lane + 32 * j] : LRT_KEY_EMPTY;
+            warp_sort_regs<8>(k, lane);
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (lane + 32 * j < n) sp_emit(rec_g, dst + 4 * (lane + 32 * j), k[j]);
+            continue;
+        }
+        if (n > WF_HCAP) {                                         // k_wf_sort_big sorts the bin in place, k_sp_gather_big emits it
+            if (lane == 0) w.big_list[atomicAdd(w.counts + 10, 1)] = r;
+            continue;
+        }
+        const int m = WF_HCAP;                                     // 257..512 candidates: this warp's slice of shared memory
+        for (int i = lane; i < m; i += 32) keys[i] = i < n ? bin[i] : LRT_KEY_EMPTY;
+        __syncwarp(FULL);
+        for (int size = 2; size <= m; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = lane; i < (m >> 1); i += 32) {
+                    const int lo = ((i / stride) * stride * 2) + (i % stride), hi = lo + stride;
+                    const unsigned long long x = keys[lo], y = keys[hi];
+                    const bool up = ((lo & size) == 0);
+                    if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+                }
+                __syncwarp(FULL);
+            }
+        }
+        for (int i = lane; i < n; i += 32) sp_emit(rec_g, dst + 4 * i, keys[i]);
+        __syncwarp(FULL);
+    }
+}
+
+// the few bins beyond WF_HCAP candidates, sorted in place by k_wf_sort_big: one block each
+__global__ void __launch_bounds__(256) k_sp_gather_big(BvhView bvh, FwdArgs a, WfBufs w, SpBufs sp)
+{
+    const int nbig = min(w.counts[10], a.R);
+    for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
+        const int r = w.big_list[b];
+        const int n = sp.ccnt[r];
+        const unsigned long long* bin = w.bins + (size_t)r * w.hcap;
+        float4* dst = sp.srec + 4 * (size_t)sp.cbase[r];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sp_emit(bvh.rec_g, dst + 4 * i, bin[i]);
+    }
+}
+
+#ifndef LRT_SLOTS_MIN_BLOCKS
+#define LRT_SLOTS_MIN_BLOCKS 4
+#endif
+#define SP_BATCH 4                                                  // candidates staged per wait
+#define SP_SLOTS_SMEM (128 * (LRT_KBUF * (8 + 4) + SP_BATCH * 64)) // k-buffer keys + opacities + staging, per block of 128 threads
+
+__device__ __forceinline__ void sp_cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void sp_cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+// Pass A. The walk of k_wf_composite2 over the ray's candidates, now a contiguous stream of records sorted by (t from o, id);
+// everything that needs an SH row is gone. A thread stages SP_BATCH candidates (all four 16-byte parts of each) into its own
+// column of shared memory with cp.async and waits ONCE per batch: ncu showed the first form of this kernel (records fetched into
+// registers, the inner parts on demand) waiting five times per four candidates, every wait a full L2 / DRAM round trip
+// (profiles/r2_b_split_first_ncu.txt). Columns are [slot][thread]: consecutive lanes touch consecutive 16-byte words (no bank
+// conflicts) and no thread ever reads another thread's column, so no block-level barrier is needed.
+__global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs a, WfBufs w, SpBufs sp)
+{
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    float4 (*s_st)[128] = reinterpret_cast<float4 (*)[128]>(sp_smem);                                      // [SP_BATCH * 4][128] staging
+    unsigned long long (*s_kb)[128] = reinterpret_cast<unsigned long long (*)[128]>(sp_smem + 128 * SP_BATCH * 64);   // the round's slots, ascending (t', id)
+    float (*s_al)[128] = reinterpret_cast<float (*)[128]>(sp_smem + 128 * (SP_BATCH * 64 + LRT_KBUF * 8));             // their blending opacities
+    const int tx = threadIdx.x;
+    for (int s = blockIdx.x * blockDim.x + tx; s < a.R; s += gridDim.x * blockDim.x) {
+        const int r = w.order ? w.order[s] : s;
+        const int hc = w.hit_count[r];
+        if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; a.hit_cnt[r] = 0; continue; }
+        const int n = hc;
+        const float4* __restrict__ rec = sp.srec + 4 * (size_t)sp.cbase[r];              // candidate i = rec[4 i .. 4 i + 3]
+        FwdRay q;
+        fwd_ray_init(q, r, a);
+        int pos = 0;                                               // first candidate that can still matter
+        int i_end = 0;                                             // where the previous round's scan stopped: everything from there on lies beyond thr
+        for (;;) {
+            RaySetup rs;
+            ray_setup(rs, q.o, q.d, q.base);
+            const float thr = q.base - 2.0f * (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
+            {   // first candidate at or beyond thr (the stream is sorted by t). It lies a few entries in front of where the
+                // previous round stopped: walk back from there eight independent loads at a time (one wait per eight).
+                int hi = i_end;
+                while (hi > pos) {
+                    float tv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) tv[k] = hi - 1 - k >= pos ? __ldg(reinterpret_cast<const float*>(rec + 4 * (hi - 1 - k) + 3) + 3) : -1.0f;
+                    int back = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if (back == k && hi - 1 - k >= pos && !(tv[k] < thr)) back = k + 1;
+                    hi -= back;
+                    if (back < 8) break;
+                }
+                pos = hi;
+            }
+            i_end = n;
+            int cnt = 0;
+            unsigned long long klast = 0ull;                       // s_kb[cnt - 1]
+            bool done = false;
+            for (int i0 = pos; i0 < n && !done; i0 += SP_BATCH) {
+                {
+                    const float4* src = rec + 4 * (size_t)i0;
+                    const int nv = 4 * min(SP_BATCH, n - i0);
+#pragma unroll
+                    for (int v = 0; v < 4 * SP_BATCH; v++) if (v < nv) sp_cp_async16(&s_st[v][tx], src + v);
+                    sp_cp_async_wait_all();
+                }
+                // phase 1, branch-free: the exact test and the opacity of all SP_BATCH staged candidates, independent of each other
+                // (the instruction streams interleave: this kernel runs few warps per scheduler and every dependent chain of
+                // shared-memory loads, divisions and expf would otherwise be paid in full, one candidate after the other)
+                float t0v[SP_BATCH], alv[SP_BATCH];
+                unsigned long long keyv[SP_BATCH];
+                bool hitv[SP_BATCH];
+#pragma unroll
+                for (int k = 0; k < SP_BATCH; k++) {
+                    const float4 a0 = s_st[4 * k][tx], a1 = s_st[4 * k + 1][tx], a2 = s_st[4 * k + 2][tx], a3 = s_st[4 * k + 3][tx];
+                    t0v[k] = a3.w;
+                    // quad_hit(), operation for operation
+                    const float c0 = a0.x - rs.ox, c1 = a0.y - rs.oy, c2 = a0.z - rs.oz;
+                    const float den = a3.x * rs.dx + a3.y * rs.dy + a3.z * rs.dz;
+                    const float num = a3.x * c0 + a3.y * c1 + a3.z * c2;
+                    const float t = num / den;
+                    bool h = t > 0.0f;
+                    {
+                        const float r0 = (rs.ox + t * rs.dx) - a0.x, r1 = (rs.oy + t * rs.dy) - a0.y, r2 = (rs.oz + t * rs.dz) - a0.z;
+                        const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
+                        const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+                        h = h && (fabsf(u) <= a0.w && fabsf(v) <= a0.w) && (t < LRT_TMAX);
+                    }
+                    hitv[k] = h;
+                    keyv[k] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)__float_as_int(a2.w);
+                    // its opacity, as fwd_shade_round() computes it (forward.cu:212-251)
+                    {
+                        const float dpt = t + q.base;
+                        const float x0 = q.o[0] + dpt * q.d[0], x1 = q.o[1] + dpt * q.d[1], x2 = q.o[2] + dpt * q.d[2];
+                        const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
+                        const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
+                        const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+                        const float cosv = -((a0.x - q.o[0]) * a3.x + (a0.y - q.o[1]) * a3.y + (a0.z - q.o[2]) * a3.z);
+                        const float rho = u * u + v * v;
+                        const float power = -0.5f * rho;
+                        alv[k] = (cosv == 0.0f || power > 0.0f) ? 0.0f : fminf(LRT_ALPHA_MAX, a1.w * expf(power));
+                    }
+                }
+                // phase 2, in order: window stop, k-buffer
+#pragma unroll
+                for (int k = 0; k < SP_BATCH; k++) {
+                    if (i0 + k >= n || done) continue;
+                    if (cnt == LRT_KBUF) {
+                        const float t16 = __uint_as_float((unsigned)(klast >> 32)) + q.base;
+                        if (t0v[k] - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) { done = true; i_end = i0 + k; continue; }
+                    }
+                    if (!hitv[k]) continue;
+                    const unsigned long long key = keyv[k];
+                    const float alpha = alv[k];
+                    if (cnt == LRT_KBUF && key >= klast) continue;                              // behind the current 16th
+                    if (cnt < LRT_KBUF && (cnt == 0 || key > klast)) {                          // the usual case: append
+                        s_kb[cnt][tx] = key; s_al[cnt][tx] = alpha; cnt++; klast = key;
+                        continue;
+                    }
+                    if (cnt == LRT_KBUF) cnt--;                                                 // replaces the current 16th
+                    int j = cnt;
+                    while (j > 0 && s_kb[j - 1][tx] > key) { s_kb[j][tx] = s_kb[j - 1][tx]; s_al[j][tx] = s_al[j - 1][tx]; j--; }
+                    s_kb[j][tx] = key; s_al[j][tx] = alpha;
+                    cnt++;
+                    klast = s_kb[cnt - 1][tx];
+                }
+            }
+            // the round's compositing (fwd_shade_round()) without the colour: weights, depth, transmittance, hit records
+            bool terminated = false;
+            for (int i4 = 0; i4 < cnt && !terminated; i4 += 4) {
+                unsigned long long kq[4]; float aq[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { kq[j] = s_kb[(i4 + j) & (LRT_KBUF - 1)][tx]; aq[j] = s_al[(i4 + j) & (LRT_KBUF - 1)][tx]; }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (i4 + j >= cnt || terminated) continue;
+                    const unsigned long long key = kq[j];
+                    const int g = (int)(unsigned)(key & 0xffffffffull);
+                    q.nslots++;
+                    q.dpt = __uint_as_float((unsigned)(key >> 32)) + q.base;              // forward.cu:212
+                    if (q.dpt < LRT_MIN_T) continue;                                      // :214
+                    if (g == q.last) continue;                                            // :220-224
+                    q.last = g;
+                    const float alpha = aq[j];
+                    if (alpha < 1.0f / 255.0f) continue;
+                    q.testT = q.T * (1.0f - alpha);
+                    if (q.testT < LRT_T_MIN) { terminated = true; continue; }             // :253-257
+                    const float wgt = alpha * q.T;
+                    q.Dp += wgt * q.dpt; q.W += wgt;
+                    atomicAdd(a.accum_w + g, wgt);                                        // :272
+                    if (q.ncontrib < a.cap) {
+                        const size_t at = (size_t)q.ncontrib * a.R + q.r;
+                        a.hit_gidx[at] = g;
+                        a.hit_t[at] = q.dpt;
+                        reinterpret_cast<float*>(a.hit_aux + at)[0] = alpha;              // colour: k_sp_colour
+                    }
+                    q.ncontrib++;
+                    q.T = q.testT;
+                }
+            }
+            if (terminated || q.testT < LRT_T_MIN || cnt < LRT_KBUF) break;               // :282-285
+            q.base = (float)((double)q.dpt + LRT_STEP_EPS);                               // :288
+        }
+        float* op = a.out + (size_t)LRT_NCH * q.r;                                        // :296-305 minus the colour channels (k_sp_fold)
+        op[3] = q.Dp; op[4] = q.W; op[5] = 0.f; op[6] = 0.f; op[7] = 0.f; op[8] = q.T;
+        a.hit_cnt[q.r] = q.ncontrib;
+        if (a.slot_cnt) a.slot_cnt[q.r] = q.nslots;
+        if (q.ncontrib > a.cap) w.ov_list[atomicAdd(w.counts + 12, 1)] = q.r;             // list truncated: the ray is redone per ray
+    }
+}
+
+// Pass B: SH colour of every recorded hit (forward.cu:67-111, :261-266). Thread (x, y) owns ray x and its hits y, y + gridDim.y, ...
+#ifndef LRT_COLOUR_MIN_BLOCKS
+#define LRT_COLOUR_MIN_BLOCKS 4
+#endif
+template <bool SH_FAST>                                             // SH rows 16-byte aligned (M % 4 == 0): 128-bit loads
+__global__ void __launch_bounds__(256, LRT_COLOUR_MIN_BLOCKS) k_sp_colour(FwdArgs a)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const int cnt = min(a.hit_cnt[r], a.cap);
+    if ((int)blockIdx.y >= cnt) return;
+    float d[3], dirn[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) d[k] = a.ray_d[3 * (size_t)r + k];
+    const float dl = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);                     // fwd_ray_init()
+#pragma unroll
+    for (int k = 0; k < 3; k++) dirn[k] = d[k] / dl;
+    float sb[16];
+    const int nb = sh_basis(a.D, dirn, sb);
+    int g_nx = a.hit_gidx[(size_t)blockIdx.y * a.R + r];
+    for (int k = blockIdx.y; k < cnt; k += gridDim.y) {
+        const size_t at = (size_t)k * a.R + r;
+        const int g = g_nx;
+        if (k + (int)gridDim.y < cnt) {                            // the thread's next hit: its SH row starts moving towards L2 now
+            g_nx = a.hit_gidx[at + (size_t)gridDim.y * a.R];
+            const char* row = reinterpret_cast<const char*>(a.shs + (size_t)g_nx * a.M * 3);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+            if (nb > 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+        }
+        float c[3];
+        if (SH_FAST) {
+            sh_colour_stream_b(nb, sb, a.shs + (size_t)g * a.M * 3, c);
+        } else {
+            float sh[48]; bool cl;
+            load_sh(a.shs, g, a.M, nb, sh);
+            sh_colour<false>(a.D, dirn, sh, c, cl, nullptr);
+        }
+        float* ax = reinterpret_cast<float*>(a.hit_aux + at);
+        ax[1] = c[0]; ax[2] = c[1]; ax[3] = c[2];
+    }
+}
+
+// Pass C: the ordered fold of the colour channels (forward.cu:253-270, :296-298) over the recorded (alpha, colour).
+__global__ void __launch_bounds__(128) k_sp_fold(FwdArgs a)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const int cnt = a.hit_cnt[r];
+    if (cnt > a.cap) return;                                       // redone by k_wf_fallback_overflow
+    float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
+    for (int k0 = 0; k0 < cnt; k0 += 8) {                          // eight independent loads per wait
+        float4 h[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (k0 + j < cnt) h[j] = a.hit_aux[(size_t)(k0 + j) * a.R + r];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (k0 + j < cnt) {
+                const float testT = T * (1.0f - h[j].x);
+                const float wgt = h[j].x * T;
+                C0 += wgt * h[j].y; C1 += wgt * h[j].z; C2 += wgt * h[j].w;
+                T = testT;
+            }
+        }
+    }
+    float* op = a.out + (size_t)LRT_NCH * r;
+    op[0] = C0 + T * a.bg[0]; op[1] = C1 + T * a.bg[1]; op[2] = C2 + T * a.bg[2];
+}

@@ -31,12 +31,14 @@ struct WfBufs {
     RaySetup* rs;                   // (R) per-ray slab constants for base = 0
     uint2* list_a; uint2* list_b;   // ping-pong work lists {ray, node}
     int cap_items;
-    int* counts;                    // [0..7] items per level, [8] fallback count, [9] heavy beam-grid items, [10] bins beyond 512 candidates
+    int* counts;                    // [0..7] items per level, [8] fallback count, [9] heavy beam-grid items, [10] bins beyond 512 candidates,
+                                    // [12] rays whose hit list overflowed in the split passes, [13] candidate records in the sorted stream
     int* hit_count;                 // (R) hits in bin | WF_TAINT
     unsigned long long* bins;       // (R, hcap)
     int hcap;                       // bin capacity (<= WF_HCAP_MAX)
     int* fb_list;                   // (R) fallback ray ids
     int* big_list;                  // (R) rays whose bin holds more than WF_HCAP candidates: sorted by k_wf_sort_big, one block each
+    int* ov_list;                   // (R) split passes: rays whose contributing-hit list overflowed `cap`
     int* ray_ids;                   // (R) identity, input of the by-length sort
     const int* order;               // (R) rays sorted by descending candidate count, or nullptr (tile order)
 };
@@ -723,120 +725,17 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite
     }
 }
 
-// EXPERIMENTAL, NOT THE DEFAULT, NOT YET RUN ON A GPU (LRT_OPT_WAVEFRONT_SHADE = 3): compositing with the
-// depth of every hit taken from the ORIGINAL origin — the oracle's ORC_FLAT mode, not the reference's round-by-round re-tracing.
-// The sorted candidates are walked once: exact quad test from the ray's origin, a round is the next 16 hits with t > base, depth =
-// t. No re-based ray, no k-buffer (the bin order IS the hit order: the candidate key carries the same t the exact test computes),
-// no per-round search. It differs from the default on ~0.07 % of rays (ulp-level ties at round boundaries; oracle analysis in
-// profiles/r1_j_flat_depth_analysis.json) and is the first half of evaluating hits candidate-parallel. Parity target:
-// Oracle.forward(flags=ORC_FLAT); tests/test_gpu_parity.py::test_flat_depth_compositing_vs_flat_oracle runs only with
-// LRT_EXPERIMENTAL=1 until it has been verified on a B200.
-__global__ void __launch_bounds__(128, 3) k_wf_composite_flat(BvhView bvh, FwdArgs a, WfBufs w)
-{
-    const int S = w.order ? a.R : num_slots(a.R, a.grid_w);
-    const bool sh_fast = (a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0);
-    const SurfelRec* __restrict__ rec = bvh.rec_g;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-        const int r = w.order ? w.order[s] : slot_to_ray(s, a.R, a.grid_w);
-        if (r < 0) continue;
-        const int hc = w.hit_count[r];
-        if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }
-        const int n = hc;
-        const unsigned long long* __restrict__ bin = w.bins + (size_t)r * w.hcap;       // sorted by (t from o, id)
-        FwdRay q;
-        fwd_ray_init(q, r, a);
-        float sb[16];
-        const int nb = sh_basis(a.D, q.dirn, sb);
-        RaySetup rs;
-        ray_setup(rs, q.o, q.d, 0.0f);
-        int in_round = 0;                                          // slots of the current round (0..16)
-        bool stop = false;
-        for (int i0 = 0; i0 < n && !stop; i0 += 4) {
-            unsigned long long ck4[4];
-            float4 b0[4], b3[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) ck4[k] = i0 + k < n ? bin[i0 + k] : LRT_KEY_EMPTY;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (i0 + k < n) {
-                    const int gk = (int)(unsigned)(ck4[k] & 0xffffffffull);
-                    b0[k] = ld_f4(&rec[gk].r0); b3[k] = ld_f4(&rec[gk].r3);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (i0 + k >= n || stop) continue;
-                const float4 a0 = b0[k], a3 = b3[k];
-                const int g = (int)(unsigned)(ck4[k] & 0xffffffffull);
-                // quad_hit() from the ray's own origin, operation for operation
-                const float c0 = a0.x - rs.ox, c1 = a0.y - rs.oy, c2 = a0.z - rs.oz;
-                const float den = a3.x * rs.dx + a3.y * rs.dy + a3.z * rs.dz;
-                const float num = a3.x * c0 + a3.y * c1 + a3.z * c2;
-                const float t = num / den;
-                if (!(t > 0.0f)) continue;
-                const float4 a1 = ld_f4(&rec[g].r1), a2 = ld_f4(&rec[g].r2);
-                float u, v;
-                {
-                    const float r0 = (rs.ox + t * rs.dx) - a0.x, r1 = (rs.oy + t * rs.dy) - a0.y, r2 = (rs.oz + t * rs.dz) - a0.z;
-                    u = a1.x * r0 + a1.y * r1 + a1.z * r2;
-                    v = a2.x * r0 + a2.y * r1 + a2.z * r2;
-                    if (!(fabsf(u) <= a0.w && fabsf(v) <= a0.w)) continue;
-                    if (!(t < LRT_TMAX)) continue;
-                }
-                if (!(t > q.base)) continue;                                              // t' = t - base > 0
-                // a slot of the current round (forward.cu:207-292 with depth = t)
-                in_round++;
-                q.nslots++;
-                q.dpt = t;
-                bool composite = q.dpt >= LRT_MIN_T && g != q.last;                       // :214, :220-224
-                if (q.dpt >= LRT_MIN_T && g != q.last) q.last = g;
-                if (composite) {
-                    const float x0 = q.o[0] + q.dpt * q.d[0], x1 = q.o[1] + q.dpt * q.d[1], x2 = q.o[2] + q.dpt * q.d[2];
-                    const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
-                    const float uu = a1.x * r0 + a1.y * r1 + a1.z * r2;
-                    const float vv = a2.x * r0 + a2.y * r1 + a2.z * r2;
-                    const float cosv = -((a0.x - q.o[0]) * a3.x + (a0.y - q.o[1]) * a3.y + (a0.z - q.o[2]) * a3.z);
-                    const float rho = uu * uu + vv * vv;
-                    const float power = -0.5f * rho;
-                    const float alpha = (cosv == 0.0f || power > 0.0f) ? 0.0f : fminf(LRT_ALPHA_MAX, a1.w * expf(power));
-                    if (alpha >= 1.0f / 255.0f) {
-                        q.testT = q.T * (1.0f - alpha);
-                        if (q.testT < LRT_T_MIN) { stop = true; continue; }               // :253-257: this hit is not composited
-                        const float wgt = alpha * q.T;
-                        float c[3];
-                        if (sh_fast) {
-                            sh_colour_stream_b(nb, sb, a.shs + (size_t)g * a.M * 3, c);
-                        } else {
-                            float sh[48]; bool cl;
-                            load_sh(a.shs, g, a.M, nb, sh);
-                            sh_colour<false>(a.D, q.dirn, sh, c, cl, nullptr);
-                        }
-                        q.C0 += wgt * c[0]; q.C1 += wgt * c[1]; q.C2 += wgt * c[2];
-                        q.Dp += wgt * q.dpt; q.W += wgt;
-                        atomicAdd(a.accum_w + g, wgt);                                    // :272
-                        if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
-                            a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g;
-                            a.hit_t[(size_t)q.ncontrib * a.R + q.r] = q.dpt;
-                            if (a.hit_aux) a.hit_aux[(size_t)q.ncontrib * a.R + q.r] = make_float4(alpha, c[0], c[1], c[2]);
-                        }
-                        q.ncontrib++;
-                        q.T = q.testT;
-                    }
-                }
-                if (in_round == LRT_KBUF) {                                               // :282-291: the round is full
-                    if (q.testT < LRT_T_MIN) { stop = true; continue; }
-                    q.base = (float)((double)q.dpt + LRT_STEP_EPS);
-                    in_round = 0;
-                }
-            }
-        }
-        fwd_write(q, a, 0);
-    }
-}
-
 // Rays the wavefront handed back (normally none or a handful): the per-ray code path, one thread per ray.
 __global__ void __launch_bounds__(128) k_wf_fallback(BvhView bvh, FwdArgs a, WfBufs w)
 {
     const int n = min(w.counts[8], a.R);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) forward_one_ray(bvh, a, w.fb_list[i]);
+}
+// Rays whose contributing-hit list outgrew `cap` in the split passes (lrt_split.cuh): their per-Gaussian weights are already
+// accumulated, the colour fold cannot run from a truncated list — the whole ray is redone by the per-ray path with the weight
+// accumulation switched off (a.accum_w == nullptr).
+__global__ void __launch_bounds__(128) k_wf_fallback_overflow(BvhView bvh, FwdArgs a, WfBufs w)
+{
+    const int n = min(w.counts[12], a.R);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) forward_one_ray(bvh, a, w.ov_list[i]);
 }

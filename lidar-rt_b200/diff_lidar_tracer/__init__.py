@@ -52,6 +52,13 @@ class _Handle:
         self.hit_cap = native.DEFAULT_HIT_CAP
         self.record_hits = True
         self.bwd_flags = 0
+        # The reference reads means3D / scales / rotations / opacities on EVERY forward (forward.cu:228-251) and uses the
+        # mesh only for the BVH, so a caller may build once and keep tracing while the parameters change. Here the
+        # structure holds derived surfel records, so a forward without a pending build request refits them first
+        # (k_records + k_fit, ~0.17 ms at 2 M Gaussians). Tensor identity cannot stand in for "unchanged": activations
+        # return fresh tensors that the caching allocator places at the same address. Callers that KNOW the parameters
+        # are those of the last build (a sweep over static Gaussians) may set this to True and skip the refit.
+        self.assume_static = False
 
     @property
     def ctx(self) -> native.Context:
@@ -65,7 +72,7 @@ class _Handle:
         P = means3D.shape[0]
         if self.pending == "build" or info_P != P:
             ctx.build(means3D, scales, rotations, opacities, scale_modifier, refit=False)
-        elif self.pending == "refit":
+        elif self.pending == "refit" or not self.assume_static:
             ctx.build(means3D, scales, rotations, opacities, scale_modifier, refit=True)
         self.pending = None
         return ctx.generation

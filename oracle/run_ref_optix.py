@@ -16,6 +16,8 @@ with the proxy mesh of lib/utils/primitive_utils.py:182-224 (`build2DRectangle`,
     python oracle/run_ref_optix.py golden OUT.npz   # real-OptiX outputs for the inputs of tests/golden/*
     python oracle/run_ref_optix.py bench  OUT.json  # B1: Mrays/s of the reference on the BASELINE workload,
                                                     # and full-size parity of this repo's library against it
+    python oracle/run_ref_optix.py fullsize OUT.npz [P frame seed]   # full-size goldens: outputs on every 16th ray +
+                                                    # sparse gradients for dL_dout on every 128th ray
 
 Each mode runs in a child process (a missing OptiX makes the reference segfault: its failed
 optixInit() is only printed, optix_wrapper.cpp:186).
@@ -256,6 +258,48 @@ def mode_bench(out_path, P=2_000_000, steps=10, warmup=3, seed=1):
     print(json.dumps({"parity_full_size": par}))
 
 
+def fullsize_subsets(R, out_stride=16, grad_stride=128):
+    """The fixed ray subsets of the full-size goldens: outputs on every `out_stride`-th ray, upstream gradients on every
+    `grad_stride`-th ray (zero elsewhere). Shared with tests/test_optix_golden.py through the npz itself."""
+    return np.arange(0, R, out_stride, dtype=np.int32), np.arange(0, R, grad_stride, dtype=np.int32)
+
+
+def fullsize_dL(R, grad_rays, dl_seed):
+    """dL_dout of the full-size goldens: N(0,1) on channels 0-3 of the `grad_rays`, zero elsewhere (SURVEY 8d config #2)."""
+    dL = np.zeros((R, 9), np.float32)
+    dL[grad_rays, :4] = np.random.default_rng(dl_seed).standard_normal((len(grad_rays), 4)).astype(np.float32)
+    return dL
+
+
+def mode_fullsize(out_path, P=2_000_000, frame=5, seed=1, out_stride=16, grad_stride=128, dl_seed=4242, sh_keep=8):
+    """Full-size golden vectors from the reference on OptiX: one 64 x 2650 frame over P Gaussians, forward outputs on
+    every 16th ray, and the GRADIENTS the reference's backward produces when dL_dout is non-zero on every 128th ray only.
+    The gradients are stored sparsely (rows of the Gaussians they touch; SH rows for every `sh_keep`-th of those)."""
+    from lidar_rt_b200 import synthetic as syn
+    H, W = 64, 2650
+    R = H * W
+    tr = RefTracer()
+    scn = syn.make_street_scene(P, seed=seed)
+    o, d = syn.lidar_rays(H, W, syn.waymo_inclinations(), syn.sensor_pose(frame))
+    out_rays, grad_rays = fullsize_subsets(R, out_stride, grad_stride)
+    dL = fullsize_dL(R, grad_rays, dl_seed)
+    sc = dict(means=scn.means, scales=scn.scales, rots=scn.rots, opac=scn.opac, shs=scn.shs)
+    res = run_case(tr, o, d, sc, 3, dL)
+    chans = np.array([0, 1, 2, 3, 4, 8], np.int32)
+    touched = np.flatnonzero((np.abs(res["g_means"]).sum(1) + np.abs(res["g_opac"]) + np.abs(res["g_scales"]).sum(1) +
+                              np.abs(res["g_rots"]).sum(1) + np.abs(res["g_shs"]).reshape(P, -1).sum(1)) > 0).astype(np.int32)
+    sh_rows = touched[::sh_keep]
+    out = dict(P=np.int32(P), seed=np.int32(seed), frame=np.int32(frame), ray_index=out_rays, channels=chans,
+               out=res["out"][out_rays][:, chans], grad_rays=grad_rays, dl_seed=np.int32(dl_seed),
+               out_grad_rays=res["out"][grad_rays], g_index=touched, g_means=res["g_means"][touched], g_opac=res["g_opac"][touched],
+               g_scales=res["g_scales"][touched], g_rots=res["g_rots"][touched], g_sh_index=sh_rows, g_shs=res["g_shs"][sh_rows],
+               g_norms=np.array([np.linalg.norm(res[k].astype(np.float64)) for k in ("g_means", "g_shs", "g_opac", "g_scales", "g_rots")]),
+               accum_w_touched=res["accum_w"][touched])
+    np.savez_compressed(out_path, **out)
+    print(json.dumps({"fullsize": out_path, "P": P, "touched_gaussians": int(len(touched)), "sh_rows": int(len(sh_rows)),
+                      "bytes": os.path.getsize(out_path)}))
+
+
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "probe"
     if os.environ.get("_LRT_REF_OPTIX_CHILD") == "1":
@@ -265,6 +309,8 @@ def main():
             mode_golden(sys.argv[2])
         elif mode == "bench":
             mode_bench(sys.argv[2], *(int(a) for a in sys.argv[3:]))
+        elif mode == "fullsize":
+            mode_fullsize(sys.argv[2], *(int(a) for a in sys.argv[3:]))
         return 0
     if not os.path.exists(os.path.join(PKG, "_C.so")):
         print(json.dumps({"unavailable": "oracle/_ref_optix not built (oracle/build_ref_optix.sh needs /root/reference)"}))

@@ -18,7 +18,7 @@ ap.add_argument("--no-vec", action="store_true")
 ap.add_argument("--cap", type=int, default=native.DEFAULT_HIT_CAP)
 ap.add_argument("--morton", type=int, default=32)
 ap.add_argument("--bwd-kernel", type=int, default=2)
-ap.add_argument("--shade", type=int, default=2)
+ap.add_argument("--shade", type=int, default=3)
 a = ap.parse_args()
 BG = np.array([0, 0, 1], np.float32)
 cu = lambda x: torch.as_tensor(np.ascontiguousarray(x), device="cuda")

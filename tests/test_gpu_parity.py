@@ -150,24 +150,25 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
         for kernel in (0, 1, 2, 3, 4):
             for tiled in (True, False):
                 for morton in (32, 63, 30):
-                  for shade in ((0, 1, 2, 3) if kernel >= 3 else (2,)):
-                    # shade 3 = default compositing kernel with the by-length ray ordering switched off
-                    ctx.set_option(native.OPT_SORT_RAYS, 0 if shade == 3 else 1)
-                    shade = min(shade, 2)
+                  for shade in ((0, 1, 2, 3, 4, 5) if kernel >= 3 else (3,)):
+                    # shade 3 = split passes (default); 4 / 5 = kernels 2 / 3 with the by-length ray ordering switched off
+                    ctx.set_option(native.OPT_SORT_RAYS, 0 if shade >= 4 else 1)
+                    shade = shade - 2 if shade >= 4 else shade
                     ctx.set_option(native.OPT_FORWARD_KERNEL, kernel)
                     ctx.set_option(native.OPT_MORTON_BITS, morton)
                     ctx.set_option(native.OPT_WAVEFRONT_SHADE, shade)
                     dd = d if tiled else d.reshape(-1, 3)
                     res = run_cuda(ctx, o, dd, as_dict(sc), 3, cap=128)
                     valid = np.arange(res["hit_gidx"].shape[0])[:, None] < res["hit_cnt"][None, :]
-                    key = (res["out"], res["hit_cnt"], res["slot_cnt"], np.where(valid, res["hit_gidx"], -1), np.where(valid, res["hit_t"], 0.0))
+                    key = (res["out"], res["hit_cnt"], res["slot_cnt"], np.where(valid, res["hit_gidx"], -1), np.where(valid, res["hit_t"], 0.0),
+                           np.where(valid[..., None], res["hit_aux"], 0.0))
                     if ref is None:
                         ref = key
                     else:
                         for a_, b_ in zip(ref, key):
                             assert np.array_equal(a_, b_), f"kernel={kernel} tiled={tiled} morton={morton} shade={shade} differs"
     finally:
-        ctx.set_option(native.OPT_FORWARD_KERNEL, 4); ctx.set_option(native.OPT_MORTON_BITS, 32); ctx.set_option(native.OPT_WAVEFRONT_SHADE, 2)
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 4); ctx.set_option(native.OPT_MORTON_BITS, 32); ctx.set_option(native.OPT_WAVEFRONT_SHADE, 3)
         ctx.set_option(native.OPT_SORT_RAYS, 1)
     assert_close(res["accum_w"], run_cuda(ctx, o, d, as_dict(sc), 3)["accum_w"], 1e-5, 1e-5, "accum (atomic order)")
 
@@ -323,24 +324,6 @@ def test_very_long_candidate_bins_and_bin_overflow(ctx, oracle32, n_stack):
     assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
 
 
-@pytest.mark.skipif(not os.environ.get("LRT_EXPERIMENTAL"), reason="experimental kernel, not yet verified on a GPU (DESIGN.md 7.1): set LRT_EXPERIMENTAL=1")
-def test_flat_depth_compositing_vs_flat_oracle(ctx, oracle32):
-    """LRT_OPT_WAVEFRONT_SHADE = 3 (depth of a hit from the ray's own origin) against the oracle's ORC_FLAT mode: hit lists bit-exact."""
-    from lidar_rt_b200 import native
-    from oracle.oracle import ORC_FLAT
-    sc = syn.make_street_scene(200_000, seed=5)
-    o, d = syn.ray_patch(16, 512, frame=2)
-    try:
-        ctx.set_option(native.OPT_WAVEFRONT_SHADE, 3)
-        res = run_cuda(ctx, o, d, as_dict(sc), 3, cap=96)
-    finally:
-        ctx.set_option(native.OPT_WAVEFRONT_SHADE, 2)
-    f = oracle32.forward(o, d, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, 3, flags=ORC_BVH | ORC_FLAT, cap=96)
-    assert hit_lists(res) == oracle_lists(f), "hit indices must be bit-exact against the flat-mode oracle"
-    assert np.array_equal(res["slot_cnt"], f["slot_cnt"])
-    assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
-
-
 def test_full_size_properties(ctx):
     """BASELINE config #2 shape (1M Gaussians, 64 x 2650 rays): size-independent invariants."""
     sc = syn.make_street_scene(1_000_000, seed=1)
@@ -410,6 +393,47 @@ def test_autograd_surface_end_to_end():
     for t in (asset._xyz, asset._scaling, asset._rotation, asset._opacity, asset._features):
         assert t.grad is not None and torch.isfinite(t.grad).all() and t.grad.abs().sum() > 0
     assert pkg["means3D"].grad is None or torch.isfinite(pkg["means3D"].grad).all()
+
+
+def test_tracer_forward_reads_current_parameters(oracle32):
+    """The reference reads the Gaussian parameters on every forward (forward.cu:228-251) and uses the mesh only for its
+    BVH: build once, change opacity / scales / means, trace again WITHOUT another build request -> the outputs and the
+    gradients must be those of the new parameters (records captured at the last build went stale)."""
+    from diff_lidar_tracer import Tracer, TracingSettings
+    sc = syn.make_street_scene(30000, seed=12)
+    o, d = syn.ray_patch(16, 64)
+    H, W = d.shape[:2]
+    tracer = Tracer()
+    centre = cu(o.reshape(-1)[:3])
+    rays_o = centre[None, None].expand(H, W, 3)
+    st = TracingSettings(None, None, None, None, cu(BG), 1.0, torch.empty(0, device="cuda"), torch.empty(0, device="cuda"), 3, centre, False, False)
+    rng = np.random.default_rng(12)
+    dL = np.zeros((H * W, 9), np.float32); dL[:, :4] = rng.standard_normal((H * W, 4))
+
+    def trace(means, scales, rots, opac, request_build):
+        ts = [cu(x).requires_grad_(True) for x in (means, scales, rots, opac.reshape(-1, 1), sc.shs)]
+        if request_build:
+            tracer.build_acceleration_structure(None, None, rebuild=True)
+        out, _ = tracer(rays_o, cu(d), None, ts[0], torch.zeros_like(ts[0]), shs=ts[4], opacities=ts[3], scales=ts[1], rotations=ts[2],
+                        tracer_settings=st)
+        (out.reshape(-1, 9) * cu(dL)).sum().backward()
+        return out.detach().reshape(-1, 9).cpu().numpy(), [t.grad.cpu().numpy() for t in ts]
+
+    trace(sc.means, sc.scales, sc.rots, sc.opac, True)
+    means2 = (sc.means + rng.normal(0, 0.02, sc.means.shape)).astype(np.float32)
+    scales2 = (sc.scales * rng.uniform(0.7, 1.4, sc.scales.shape)).astype(np.float32)
+    opac2 = np.clip(sc.opac * rng.uniform(0.5, 1.5, sc.opac.shape), 0.01, 0.999).astype(np.float32)
+    out, grads = trace(means2, scales2, sc.rots, opac2, False)
+    args = (o, d, BG, means2, scales2, sc.rots, opac2, sc.shs, 3)
+    f = oracle32.forward(*args, flags=ORC_BVH, cap=128)
+    assert_close(out, f["out"], ORC_ATOL, ORC_RTOL, "forward after a parameter change without a rebuild request")
+    b = oracle32.backward(*args, f["out"], dL, flags=ORC_BVH)
+    for gt, k in zip(grads, ("means", "scales", "rots", "opac", "shs")):
+        grad_close(gt.reshape(b[k].shape), b[k], GRAD_REL, f"d_{k} after a parameter change")
+    # assume_static skips the refresh: the caller vouches that nothing changed
+    tracer.optix_context.assume_static = True
+    out3, _ = trace(means2, scales2, sc.rots, opac2, False)
+    assert np.array_equal(out3, out)
 
 
 # ------------------------------------------------------------------------------------------- edge cases
