@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--sh-degree", type=int, default=3)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="static", choices=["static", "dynamic_sweep"],
+                    help="static = the headline (default); dynamic_sweep = BASELINE config #4 (200-frame dynamic sweep, refit, forward only)")
+    ap.add_argument("--sweep-frames", type=int, default=200)
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -81,6 +85,7 @@ class ClockSampler:
                     idx = index
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)       # first query outside the timed region (it is the slow one)
             self.nvml = pynvml
         except Exception:
             self.nvml = None
@@ -152,6 +157,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+POSE_WINDOW_M = 60.0       # sensor x of the sweep's frames: [0, 60) m, the stretch of the street scene that is populated all around
+
+
+def frame_pose(f, total):
+    """sensor2world of frame f of a `total`-frame sweep. The sweep always covers the same 60 m of the scene whatever the
+    number of ranks (round 1 placed frame f at x = f metres: at N = 8 the ranks drove off the populated part of the scene and
+    per-frame work fell by 24 %, which made the scaling curve super-linear)."""
+    from lidar_rt_b200 import synthetic as syn
+    return syn.sensor_pose(POSE_WINDOW_M * f / max(total, 1))
+
+
 def make_inputs(args, n_frames, rank, world):
     from lidar_rt_b200 import synthetic as syn
     sc = syn.make_street_scene(args.gaussians, seed=args.seed)
@@ -160,7 +176,7 @@ def make_inputs(args, n_frames, rank, world):
     rng = np.random.default_rng(1000 + rank)
     for i in range(n_frames):
         f = rank + i * world
-        o, d = syn.lidar_rays(H, W, inc, syn.sensor_pose(f))
+        o, d = syn.lidar_rays(H, W, inc, frame_pose(f, n_frames * world))
         dL = np.zeros((H, W, 9), np.float32)
         dL[..., :4] = rng.standard_normal((H, W, 4)).astype(np.float32)       # N(0,1) on channels 0-3
         frames.append((f, o, d, dL))
@@ -181,82 +197,83 @@ def use_all_host_threads():
     return n
 
 
-# --------------------------------------------------------------------------------- reference arm
-def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path (oracle/_ref = its forward.cu/backward.cu
-    compiled as host code; the C restatement if _ref was never built), on a bounded ray sample."""
-    if rank != 0:
-        return
-    from oracle.oracle import ORC_BVH, Oracle, Ref, ref_available
-    use_all_host_threads()
-    sc, frames = make_inputs(args, args.steps + args.warmup, 0, 1)
-    kind = "reference" if ref_available() else "port"
-    impl = Ref() if kind == "reference" else Oracle(False)
-    cores = Oracle(False).threads
-    R = H * W
-    stride_h, stride_w = 4, 10                     # 16 x 265 = 4240 rays spread over the whole range image
-    times = []
-    t_build = None
+# --------------------------------------------------------------------------------- the reference's CPU path
+class CpuReference:
+    """The reference's own implementation of the path on the host cores: oracle/_ref (its forward.cu / backward.cu compiled
+    as host code; the C restatement if _ref was never built), all host threads. ONE method for the `cpu_baseline` object and the
+    `--impl reference` arm: a frame's time = acceleration-structure build (measured once, uncached) + the time of a bounded,
+    strided ray sample traced with the structure cached, scaled to the frame's 169 600 rays."""
+    STRIDE_H, STRIDE_W = 4, 10                     # 16 x 265 = 4240 rays spread over the whole range image
 
-    def fwd_bwd(o, ds, dLs):
-        a = (o, ds, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, args.sh_degree)
-        kw = {} if kind == "reference" else {"flags": ORC_BVH}
+    def __init__(self, args, sc):
+        from oracle.oracle import ORC_BVH, Oracle, Ref, ref_available
+        self.cores = use_all_host_threads()
+        self.kind = "reference" if ref_available() else "port"
+        self.impl = Ref() if self.kind == "reference" else Oracle(False)
+        self.kw = {} if self.kind == "reference" else {"flags": ORC_BVH}
+        self.sc, self.D, self.P = sc, args.sh_degree, args.gaussians
+        self.t_build = None
+        self.n = None
+
+    def _fwd_bwd(self, o, ds, dLs):
+        sc = self.sc
+        a = (o, ds, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, self.D)
         t0 = time.perf_counter()
-        out = impl.forward(*a, **kw); impl.backward(*a, out["out"], dLs, **kw)
+        out = self.impl.forward(*a, **self.kw); self.impl.backward(*a, out["out"], dLs, **self.kw)
         return time.perf_counter() - t0
 
-    for i, (f, o, d, dL) in enumerate(frames):
-        ds = np.ascontiguousarray(d[::stride_h, ::stride_w]); dLs = np.ascontiguousarray(dL[::stride_h, ::stride_w]).reshape(-1, 9)
-        n = ds.shape[0] * ds.shape[1]
-        if t_build is None:
-            # accel-build share of a pass, measured once (uncached): the same calls on a single ray. Later steps
-            # let the OptiX stand-in keep its BVH (static scene) and add this build time back, so every reported
-            # frame time = accel build + traced-sample time scaled to the full 169 600-ray frame.
+    def frame_seconds(self, frame):
+        f, o, d, dL = frame
+        ds = np.ascontiguousarray(d[::self.STRIDE_H, ::self.STRIDE_W])
+        dLs = np.ascontiguousarray(dL.reshape(H, W, 9)[::self.STRIDE_H, ::self.STRIDE_W]).reshape(-1, 9)
+        self.n = ds.shape[0] * ds.shape[1]
+        one, dL1 = np.ascontiguousarray(ds[:1, :1]), dLs[:1]
+        if self.t_build is None:
             os.environ["ORC_REF_CACHE_BVH"] = "0"
-            t_build = fwd_bwd(o, np.ascontiguousarray(ds[:1, :1]), dLs[:1])
+            self.t_build = self._fwd_bwd(o, one, dL1)                      # one ray, structure built from scratch
             os.environ["ORC_REF_CACHE_BVH"] = "1"
-            fwd_bwd(o, np.ascontiguousarray(ds[:1, :1]), dLs[:1])          # fills the cache
-        t_one = fwd_bwd(o, np.ascontiguousarray(ds[:1, :1]), dLs[:1])     # per-call overhead without build
-        t_all = fwd_bwd(o, ds, dLs)
-        t_frame = t_build + max(t_all - t_one, 1e-9) * (R / n)
-        if i >= args.warmup:
-            times.append(t_frame)
+            self._fwd_bwd(o, one, dL1)                                     # fills the cache (static scene)
+        t_one = self._fwd_bwd(o, one, dL1)                                 # per-call overhead without the build
+        t_all = self._fwd_bwd(o, ds, dLs)
+        return self.t_build + max(t_all - t_one, 1e-9) * (H * W / self.n)
+
+    def sample(self):
+        R = H * W
+        return (f"{H // self.STRIDE_H}x{W // self.STRIDE_W}={self.n} of {R} rays per frame (every {self.STRIDE_H}th beam, every "
+                f"{self.STRIDE_W}th azimuth), P={self.P}, fwd+bwd; frame time = accel build ({self.t_build:.2f} s, once) + traced-sample time x {R / self.n:.0f}")
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sc, frames = make_inputs(args, args.steps + args.warmup, 0, 1)
+    cpu = CpuReference(args, sc)
+    R = H * W
+    times = [cpu.frame_seconds(fr) for fr in frames][args.warmup:]
     ms = 1e3 * float(np.mean(times))
     val = R / (ms * 1e-3) / 1e6
-    sample = (f"{H // stride_h}x{W // stride_w}={n} of {R} rays per frame (every {stride_h}th beam, every {stride_w}th azimuth), "
-              f"P={args.gaussians}; frame time = accel build + traced-sample time x {R / n:.0f}")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"waymo_static_{args.gaussians // 1000}k_gaussians_64x2650_rays_fwd_bwd_sh{args.sh_degree}",
-                       "gaussians": args.gaussians, "rays_per_frame": R, "sh_degree": args.sh_degree},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.sample()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def workload_config(args):
+    """The `config` object both arms print: the driver compares them for equality."""
+    return {"workload": f"waymo_static_{args.gaussians // 1000}k_gaussians_64x2650_rays_fwd_bwd_sh{args.sh_degree}",
+            "gaussians": args.gaussians, "rays_per_frame": H * W, "sh_degree": args.sh_degree,
+            "step": "lbvh rebuild + forward + backward per frame", "frames": f"sensor poses spread over {POSE_WINDOW_M:.0f} m of the scene, every step a different frame",
+            "l2": "inputs larger than L2 (Gaussian parameters 464 MB + SH gradients 384 MB per step vs 126 MB L2)",
+            "sharding": "frame-parallel, replicated Gaussians, rendered buffers gathered per frame (overlapped)"}
+
+
 # --------------------------------------------------------------------------------- CPU baseline leg
 def cpu_baseline(args, sc, frame):
-    from oracle.oracle import ORC_BVH, Oracle, Ref, ref_available
-    use_all_host_threads()
-    kind = "reference" if ref_available() else "port"
-    impl = Ref() if kind == "reference" else Oracle(False)
-    cores = Oracle(False).threads
-    f, o, d, dL = frame
-    R = H * W
-    n_target = args.cpu_sample_rays or max(1060, min(R, 330 * cores))
-    sw = max(1, int(round((R / n_target) / 4)))
-    ds = np.ascontiguousarray(d[::4, ::sw]); dLs = np.ascontiguousarray(dL[::4, ::sw]).reshape(-1, 9)
-    n = ds.shape[0] * ds.shape[1]
-    kw = {} if kind == "reference" else {"flags": ORC_BVH}
-    a = (o, ds, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, args.sh_degree)
-    t0 = time.perf_counter(); out = impl.forward(*a, **kw); impl.backward(*a, out["out"], dLs, **kw); t_all = time.perf_counter() - t0
-    one = np.ascontiguousarray(ds[:1, :1]); a1 = (o, one, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, args.sh_degree)
-    t0 = time.perf_counter(); o1 = impl.forward(*a1, **kw); impl.backward(*a1, o1["out"], dLs[:1], **kw); t_build = time.perf_counter() - t0
-    t_frame = t_build + max(t_all - t_build, 1e-9) * (R / n)
-    return {"value": R / t_frame / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{n} of {R} rays of one frame (P={args.gaussians}), fwd+bwd; frame time = accel build ({t_build:.2f} s) + "
-                      f"traced-sample time ({t_all - t_build:.2f} s) x {R / n:.0f}"}
+    cpu = CpuReference(args, sc)
+    t = cpu.frame_seconds(frame)
+    return {"value": H * W / t / 1e6, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.sample()}
 
 
 def chamfer_leg(ctx, dev):
@@ -296,7 +313,6 @@ def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from lidar_rt_b200 import native
     from lidar_rt_b200.scene import GaussianAsset
-    from lidar_rt_b200.sweep import gather_frames
     import lib.gaussian_renderer as gr
 
     torch.cuda.set_device(local_rank)
@@ -334,48 +350,72 @@ def run_b200(args, rank, world, local_rank):
             keep.append(f["out"])
         return f
 
-    # ---- 1. kernel-only throughput (inputs resident in HBM)
+    # ---- 1. kernel-only throughput (inputs resident in HBM). The step (rebuild + forward + backward, ~45 launches) is captured
+    # once as a CUDA graph and replayed per frame: the rays and upstream gradients of the frame are copied device-to-device
+    # into the graph's static buffers (8.1 MB per step, inside the timed region). --no-graph launches the kernels one by one.
     for i in range(Wm):
         step_kernels(i)
+    graph = None
+    if not args.no_graph:
+        graph = ctx.graphed_step(o_dev[0], d_dev[0], dL_dev[0], bg, means, scales, rots, opac, shs, D)
+        for i in range(Wm):
+            graph.run(o_dev[i], d_dev[i], dL_dev[i])
+    # the sweep's one collective: every frame's rendered channels that consumers read (intensity, hit and drop logits, depth:
+    # lib/gaussian_renderer/__init__.py:163-166) are all-gathered as soon as the frame is done, on NCCL's own stream, while
+    # the next frames render; (K, world, H, W, 4) is already frame order f = k * world + rank
+    gathered = torch.empty((K, world, H, W, 4), device=dev) if world > 1 else None
     if world > 1:                                  # communicator set-up is not part of a sweep: warm the gather path once
-        gather_frames(torch.zeros((K, H, W, 9), device=dev), K * world, rank, world)
+        dist.all_gather_into_tensor(gathered[0], torch.zeros((H, W, 4), device=dev))
+    kc_acc = torch.zeros(1, device=dev, dtype=torch.float64)      # contributing hits summed over the timed steps
+    ks_acc = torch.zeros(1, device=dev, dtype=torch.float64)      # evaluated k-buffer slots over the same frames (instrumented pass)
 
     def timed_region():
         """EXACTLY K steps between a barrier + synchronize on both sides, CUDA events, clocks sampled meanwhile; max over ranks."""
         sampler = ClockSampler(local_rank)
+        kc_acc.zero_()
         barrier()
         sampler.start()
         l0 = ctx.info().kernel_launches
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        outs = []
+        works, keep = [], []
         h0 = time.perf_counter()
         ev0.record()
-        for i in range(Wm, Wm + K):
-            step_kernels(i, outs)
-        if world > 1:                                                              # the sweep's only collective
-            gather_frames(torch.stack(outs, 0), K * world, rank, world)
+        for k, i in enumerate(range(Wm, Wm + K)):
+            if graph is not None:
+                f, _ = graph.run(o_dev[i], d_dev[i], dL_dev[i])
+            else:
+                f = step_kernels(i)
+            kc_acc[0] += f["hit_cnt"].sum()
+            if world > 1:
+                send = f["out"][..., :4].contiguous()
+                keep.append(send)
+                works.append(dist.all_gather_into_tensor(gathered[k], send, async_op=True))
+        for w_ in works:
+            w_.wait()
         ev1.record()
         host_ms = 1e3 * (time.perf_counter() - h0)                                 # time the host needed to ENQUEUE the region
         barrier()
         ck = sampler.stop()
         ms = ev0.elapsed_time(ev1)
-        n_launch = ctx.info().kernel_launches - l0
-        del outs
+        n_launch = (ctx.info().kernel_launches - l0) if graph is None else K * launches_per_step
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), n_launch, ck, host_ms
 
+    l0 = ctx.info().kernel_launches
+    step_kernels(Wm)
+    launches_per_step = ctx.info().kernel_launches - l0                            # kernels of ONE step (a graph replay launches the same kernels)
     ms_total, launches, clocks, host_ms = timed_region()
 
     # ---- 2. per-phase device times + hit statistics (separate instrumented pass)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
-    Ksum = Kcsum = 0.0
     for j, i in enumerate(range(Wm, Wm + K)):
         evs[j][0].record(); ctx.build(means, scales, rots, opac)
-        evs[j][1].record(); f = ctx.forward(o_dev[i], d_dev[i], bg, means, scales, rots, opac, shs, D)
+        evs[j][1].record(); f = ctx.forward(o_dev[i], d_dev[i], bg, means, scales, rots, opac, shs, D, want_slots=True)
         evs[j][2].record(); ctx.backward(o_dev[i], d_dev[i], bg, means, scales, rots, opac, shs, D, f["out"], dL_dev[i], hits=f)
         evs[j][3].record()
+        ks_acc[0] += f["slot_cnt"].sum()
     torch.cuda.synchronize()
     t_build = float(np.median([e[0].elapsed_time(e[1]) for e in evs]))       # medians: robust to an allocator hiccup
     t_fwd = float(np.median([e[1].elapsed_time(e[2]) for e in evs]))
@@ -394,15 +434,20 @@ def run_b200(args, rank, world, local_rank):
         ms_total, launches, clocks, host_ms = timed_region()
     ms_step = ms_total / K
     value = world * K * R / (ms_total * 1e-3) / 1e6
-    f = ctx.forward(o_dev[Wm], d_dev[Wm], bg, means, scales, rots, opac, shs, D, want_slots=True)
-    Ksum = float(f["slot_cnt"].sum().item()); Kcsum = float(f["hit_cnt"].sum().item())
+    # hit statistics over ALL ranks and ALL timed frames (they determine the algorithmic bytes; SURVEY 8d asks for them with every number)
+    kc_all = torch.cat([kc_acc, ks_acc])
+    if world > 1:
+        dist.all_reduce(kc_all, op=dist.ReduceOp.SUM)
+    Kc_mean_all = float(kc_all[0].item()) / (world * K * R)
+    K_mean_all = float(kc_all[1].item()) / (world * K * R)
+    Kcsum = float(kc_acc[0].item()) / K; Ksum = float(ks_acc[0].item()) / K      # this rank's per-frame means (rank 0 prints its own kernels)
     overflow = float((f["hit_cnt"] > f["cap"]).float().mean().item())
     nsh = 12 * (D + 1) ** 2
     P = args.gaussians
     # algorithmic bytes per launch, SURVEY.md §8d (shared ray origin); see DESIGN.md §Roofline
     B_fwd = R * (12 + 36) + Ksum * 40 + Kcsum * (nsh + 8)
     B_bwd = R * (12 + 36 + 36) + Kcsum * (8 + 40 + nsh + 2 * (40 + nsh))
-    B_build = P * (40 + 64 + 24) + 2 * P * 8 * 4 + (P / 7.0) * 192
+    B_build = P * (40 + 48 + 32) + 2 * P * 8 * 4 + (2 * P - 1) * 32                   # §8d: read 40 + packed record 48 + AABB 32; 4 sort passes; nodes
     peak, peak_src = measured_peak()
     phases = {"build": (t_build, B_build), "forward": (t_fwd, B_fwd), "backward": (t_bwd, B_bwd)}
     # live per-kernel device times: CUDA events recorded by the library around every launch, on the launch stream
@@ -413,31 +458,47 @@ def run_b200(args, rank, world, local_rank):
     kt = ctx.kernel_times()
     ctx.set_option(native.OPT_KERNEL_TIMING, 0)
     kernels = {k: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K} for k, v in kt.items()}
-    # algorithmic bytes of the kernels that own a SURVEY §8d term (per step): the backward replay owns B_bwd; the
-    # forward bytes are split: candidate geometry (K x 40 B) to the leaf kernel, rays + SH + outputs to the composite
-    kalg = {"k_backward_list": B_bwd, "k_bw_hits": B_bwd, "k_wf_leaf": Ksum * 40, "k_bg_bin": Ksum * 40, "k_wf_composite": R * (12 + 36) + Kcsum * (nsh + 8),
-            "k_records": P * (40 + 64 + 24 + 4 + 10), "radix_sort": 2 * P * 8 * 4}
+    # algorithmic bytes of the kernels that own a SURVEY §8d term (per step). The forward term R (12 + 36) + K 40 + Kc (nsh + 8)
+    # is split by what each pass moves: candidate geometry (K x 40 B) to the binning pass; the rays, the outputs' colour-free
+    # channels and the per-Gaussian weights (Kc x 8 B) to the slot pass; the SH rows (Kc x nsh) to the colour pass. The
+    # backward term belongs to the kernel that does the scatter (k_bw_hits); the fallbacks own nothing.
+    kalg = {"k_bw_hits": B_bwd, "k_bg_bin": Ksum * 40, "k_wf_leaf": Ksum * 40,
+            "k_wf_composite": R * (12 + 36) + Kcsum * (nsh + 8),
+            "k_sp_slots": R * (12 + 36) + Kcsum * 8, "k_sp_colour": Kcsum * nsh,
+            "k_records": P * (40 + 48 + 32), "radix_sort": 2 * P * 8 * 4}
+    # the compositing chain of the forward (sort + slots + colour + fold) against the compositing term of §8d
+    chain = [k for k in ("k_sp_sort", "k_sp_slots", "k_sp_colour", "k_sp_fold", "k_wf_sort", "k_wf_composite") if k in kernels]
+    chain_ms = sum(kernels[k]["ms_per_step"] for k in chain)
+    chain_bytes = R * (12 + 36) + Kcsum * (nsh + 8)
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else "forward"
     dom_ms = kernels[dom]["ms_per_step"] if kernels else t_fwd
     dom_bytes = kalg.get(dom, 0.0)
-    traffic = None
+    traffic, step_traffic = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             tk = tj.get("kernels", {})
-            traffic = tk.get(dom, tk.get(dom + "2"))       # the default compositing kernel is k_wf_composite2 in ncu's list
+            traffic = tk.get(dom, tk.get(dom + "2"))       # ncu names (k_wf_composite2 ...) -> span names
+            step_traffic = tj.get("step_total")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+                # the same kernel by the bytes it really moved (ncu dram__bytes_read + write of the committed capture)
+                "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "ms": dom_ms,
                 "kernels": {k: dict(v, algorithmic_bytes=kalg.get(k), gbs=(kalg[k] / (v["ms_per_step"] * 1e-3) / 1e9 if k in kalg and v["ms_per_step"] > 0 else None))
                             for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_per_step"])},
-                "phases": {k: {"ms": v[0], "algorithmic_bytes": v[1], "gbs": v[1] / (v[0] * 1e-3) / 1e9} for k, v in phases.items()},
+                "composite_chain": {"kernels": chain, "ms": chain_ms, "algorithmic_bytes": chain_bytes,
+                                    "frac": (chain_bytes / (chain_ms * 1e-3) / 1e9 / peak) if chain_ms > 0 else None},
+                "phases": {k: {"ms": v[0], "algorithmic_bytes": v[1], "gbs": v[1] / (v[0] * 1e-3) / 1e9, "frac": v[1] / (v[0] * 1e-3) / 1e9 / peak} for k, v in phases.items()},
                 "step_algorithmic_bytes": B_fwd + B_bwd + B_build,
                 "step_frac_of_peak": (B_fwd + B_bwd + B_build) / (ms_step * 1e-3) / 1e9 / peak,
-                "hits_per_ray_evaluated": Ksum / R, "hits_per_ray_contributing": Kcsum / R, "hit_list_overflow_frac": overflow}
+                "step_dram_bytes": step_traffic,
+                "step_dram_frac_of_peak": (step_traffic / (ms_step * 1e-3) / 1e9 / peak) if step_traffic else None,
+                "hits_per_ray_evaluated": K_mean_all, "hits_per_ray_contributing": Kc_mean_all,
+                "hits_per_ray_contributing_this_rank": Kcsum / R, "hit_list_overflow_frac": overflow}
 
     # ---- 3. end to end through the public API (raytracing() + autograd), host buffers in pinned memory
     asset = GaussianAsset(sc, device=dev)
@@ -533,12 +594,99 @@ def run_b200(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": f"waymo_static_{P // 1000}k_gaussians_64x2650_rays_fwd_bwd_sh{D}", "gaussians": P,
-                           "rays_per_frame": R, "sh_degree": D, "step": "lbvh rebuild + forward + backward per frame",
-                           "l2": "inputs larger than L2 (Gaussian parameters 464 MB + SH gradients 384 MB per step vs 126 MB L2)",
-                           "frames_per_rank": K, "sharding": "frame-parallel, replicated Gaussians, one gather of rendered buffers per sweep"},
+                "config": workload_config(args),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "reference_on_gpu": ref_gpu, "next_rows": next_rows, "host_enqueue_ms_per_step": host_ms / K, "remeasured": remeasured}
+                "reference_on_gpu": ref_gpu, "next_rows": next_rows, "host_enqueue_ms_per_step": host_ms / K, "cuda_graph": graph is not None,
+                "frames_per_rank": K, "remeasured": remeasured}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------- BASELINE config #4
+def run_dynamic_sweep(args, rank, world, local_rank):
+    """BASELINE.json config #4 as specified: Waymo dynamic, 2 M background Gaussians + 40 actors x 10 k moving rigidly every frame,
+    a 200-frame sweep sharded frame-parallel over the ranks (STRONG scaling: the sweep is fixed), acceleration structure REFIT
+    per frame (full rebuild every 10th of a rank's frames), forward only, every frame's rendered channels all-gathered (NCCL, overlapped).
+        python bench.py --workload dynamic_sweep --gpus N        (torchrun for N > 1)"""
+    import torch
+    import torch.distributed as dist
+    from lidar_rt_b200 import native, synthetic as syn
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_actors, per_actor, total = 40, 10_000, args.sweep_frames
+    sc0 = syn.make_street_scene(args.gaussians + n_actors * per_actor, seed=4, n_actors=n_actors, per_actor=per_actor)
+    cu = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)
+    ctx = native.Context(dev)
+    shs, scales, rots, opac, means0 = cu(sc0.shs), cu(sc0.scales), cu(sc0.rots), cu(sc0.opac), cu(sc0.means)
+    aid = cu(sc0.actor_id.astype(np.int64))
+    bg = cu(BG)
+    inc = syn.waymo_inclinations()
+    mine = list(range(rank, total, world))
+    warm = [mine[0], mine[min(1, len(mine) - 1)]]
+    rays, shift = {}, {}
+    for f in sorted(set(mine + warm)):                      # host-side inputs prepared up front (data loading is outside the path)
+        o, d = syn.lidar_rays(H, W, inc, frame_pose(f, total))
+        rays[f] = (cu(o), cu(d))
+        t = np.zeros((n_actors + 1, 3), np.float32)
+        for k in range(n_actors):
+            t[k] = syn.actor_transform(k, f)[1]
+        shift[f] = cu(t)                                    # background rows (actor id -1) index the zero row
+
+    def render(f, refit):
+        means = means0 + shift[f][aid]                      # the actors' rigid per-frame motion (gaussian_model.py:129-134)
+        ctx.build(means, scales, rots, opac, refit=refit)
+        return ctx.forward(rays[f][0], rays[f][1], bg, means, scales, rots, opac, shs, args.sh_degree, record_hits=False)
+
+    for f in warm:
+        render(f, False)
+    n_max = (total + world - 1) // world
+    gathered = torch.empty((n_max, world, H, W, 4), device=dev) if world > 1 else None
+    if world > 1:
+        dist.all_gather_into_tensor(gathered[0], torch.zeros((H, W, 4), device=dev))
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    works, keep = [], []
+    kc = torch.zeros(1, device=dev, dtype=torch.float64)
+    e0.record()
+    for k in range(n_max):
+        if k < len(mine):
+            out = render(mine[k], refit=(k % 10 != 0))["out"]
+            kc += out[..., 4].sum()
+            send = out[..., :4].contiguous()
+        else:
+            send = torch.zeros((H, W, 4), device=dev)       # ranks with one frame fewer still take part in the collective
+        if world > 1:
+            keep.append(send)
+            works.append(dist.all_gather_into_tensor(gathered[k], send, async_op=True))
+    for w_ in works:
+        w_.wait()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    info = ctx.info()
+    if rank == 0:
+        R = H * W
+        line = {"metric": "lidar_mrays_per_s_fwd_sweep", "value": total * R / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": total,
+                "warmup": 2, "ms_per_step": ms / n_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"waymo_dynamic_{args.gaussians // 1000}k+{n_actors}x{per_actor // 1000}k_gaussians_{total}_frame_sweep_fwd_sh{args.sh_degree}",
+                           "gaussians": sc0.P, "actors": n_actors, "rays_per_frame": R, "sweep_frames": total, "frames_per_rank": n_max,
+                           "step": "actor motion + lbvh refit (rebuild every 10th frame of a rank) + forward; 4 channels of every frame all-gathered",
+                           "sharding": "frame f on rank f mod N, Gaussians replicated"},
+                "ms_sweep": ms, "mean_accum_per_ray_rank0": float(kc.item()) / (len(mine) * R), "refits": int(info.refits), "builds": int(info.builds),
+                "clocks": clocks}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
@@ -558,6 +706,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if args.workload == "dynamic_sweep":
+        run_dynamic_sweep(args, rank, world, local_rank)
+        return
     run_b200(args, rank, world, local_rank)
 
 

@@ -10,8 +10,12 @@ either) raise instead of silently rendering garbage.
 Assets are duck-typed like the reference's GaussianModel (lib/scene/gaussian_model.py:112-148):
 `get_world_xyz(frame)`, `get_opacity`, `get_scaling`, `get_rotation(frame) -> (obj_quat, local_quat)`,
 `get_features`, `active_sh_degree`. Sensors: anything with `get_range_rays(frame)` and
-`sensor_center[frame]` (lib/scene/lidar_sensor.py:395-434), or a tuple (rays_o, rays_d, centre).
+`sensor_center[frame]` (lib/scene/lidar_sensor.py:395-434), a pinhole camera shaped like lib/scene/cameras.py::Camera
+(`camera_center`, `image_width`, `image_height`, `FoVx`, `world_view_transform`; reference :31-41), or a tuple
+(rays_o, rays_d, centre).
 """
+import math
+
 import torch
 import torch.nn.functional as F
 
@@ -29,6 +33,25 @@ def quaternion_raw_multiply(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
                         aw * bx + ax * bw + ay * bz - az * by,
                         aw * by - ax * bz + ay * bw + az * bx,
                         aw * bz + ax * by - ay * bx + az * bw), -1)
+
+
+def get_rays(K, c2w):
+    """Pinhole rays of the Camera branch (lib/utils/graphics_utils.py:88-95, called at lib/gaussian_renderer/__init__.py:41):
+    one ray per pixel through K, rotated into the world by c2w (3,4); directions are NOT normalised (z = 1 in the camera
+    frame), exactly as the reference hands them to its tracer. rays_o is the camera centre as a stride-0 view (the reference
+    materialises the expansion; the values are the same and the tracer takes the shared-origin path)."""
+    W, H = int(K[0][2] * 2), int(K[1][2] * 2)
+    dev = c2w.device
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(H - 1, 0, H), indexing="ij")
+    i, j = i.t(), j.t()
+    dirs = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], torch.ones_like(i)], -1).to(dev)
+    rays_d = dirs @ c2w.T[:3, :3]
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return rays_o, rays_d
+
+
+def _is_camera(sensor) -> bool:
+    return all(hasattr(sensor, a) for a in ("camera_center", "image_width", "image_height", "FoVx", "world_view_transform"))
 
 
 def _arg(args, group, name, default):
@@ -73,6 +96,11 @@ def raytracing(frame, gaussian_assets, sensor, background, args, scaling_modifie
 
     if isinstance(sensor, tuple):
         rays_o, rays_d, sensor_center = sensor[0], sensor[1], sensor[2]
+    elif _is_camera(sensor):                                               # reference :31-41
+        sensor_center = sensor.camera_center
+        focal = 0.5 * sensor.image_width / math.tan(0.5 * sensor.FoVx)
+        K = [[focal, 0, 0.5 * sensor.image_width], [0, focal, 0.5 * sensor.image_height], [0, 0, 1]]
+        rays_o, rays_d = get_rays(K, sensor.world_view_transform.T.inverse()[:3, :4])
     elif hasattr(sensor, "get_range_rays"):
         rays_o, rays_d = sensor.get_range_rays(frame)
         sensor_center = sensor.sensor_center[frame]
@@ -119,7 +147,9 @@ def raytracing(frame, gaussian_assets, sensor, background, args, scaling_modifie
     rayhit_logits = rendered[..., 1:2]
     raydrop_logits = rendered[..., 2:3]
     depth = rendered[..., 3:4]
-    if _arg(args, "opt", "use_rayhit", True):
+    # the reference reads args.opt.use_rayhit unconditionally (:168); with args=None (this repository's benches) its
+    # configured value applies (configs/exp.yaml:44: True)
+    if args.opt.use_rayhit if (args is not None and hasattr(args, "opt")) else True:
         prob = F.softmax(torch.cat([rayhit_logits, raydrop_logits], dim=-1), dim=-1)
         raydrop_prob = prob[..., 1:2]
     else:

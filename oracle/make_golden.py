@@ -14,6 +14,10 @@ Two sources, both the reference's OWN code:
       lib/utils/general_utils.py::build_rotation, quaternion_raw_multiply
       lib/utils/primitive_utils.py::build2DRectangle
       lib/scene/lidar_sensor.py::LiDARSensor.get_range_rays
+      lib/scene/gaussian_model.py::GaussianModel.get_world_xyz / get_rotation / get_scaling / get_opacity / get_features
+          and the accessor loop + concatenations + rotation composition of lib/gaussian_renderer/__init__.py:68-134
+          (statements cut out of raytracing() and executed as they are) -> ref_prepare.npz, values AND leaf gradients
+      lib/utils/graphics_utils.py::get_rays                    (pinhole rays of the Camera branch of raytracing())
 The fixtures are small; the GPU box has no /root/reference, so tests read only these files.
 """
 from __future__ import annotations
@@ -65,7 +69,7 @@ def cuda_to_cpu():
         torch.Tensor.cuda = saved_cuda
 
 
-def lift(path: str, names: list[str], ns: dict | None = None) -> dict:
+def lift(path: str, names: list[str], ns: dict | None = None, strip_decorators: bool = False) -> dict:
     """exec only the named top-level defs / assignments (or methods `Class.method`) of a file."""
     src = open(path).read()
     tree = ast.parse(src)
@@ -78,6 +82,8 @@ def lift(path: str, names: list[str], ns: dict | None = None) -> dict:
         elif isinstance(node, ast.ClassDef):
             for sub in node.body:
                 if isinstance(sub, ast.FunctionDef) and f"{node.name}.{sub.name}" in names:
+                    if strip_decorators:
+                        sub.decorator_list = []           # @property accessors become plain functions of `self`
                     picked.append(sub)
     ns = ns if ns is not None else {}
     ns.setdefault("torch", torch); ns.setdefault("np", np); ns.setdefault("F", torch.nn.functional)
@@ -129,6 +135,94 @@ def gen_python_fixtures():
             out[f"rays_{tag}_pose"] = pose.numpy(); out[f"rays_{tag}_inc"] = np.asarray(inc, np.float32)
     np.savez_compressed(os.path.join(OUT, "ref_python.npz"), **out)
     print("ref_python.npz", {k: v.shape for k, v in out.items()})
+
+
+def lift_statements(path: str, func: str, first_target: str, last_target: str):
+    """The statements of `func`'s body from the first assignment to `first_target` through the assignment to `last_target`,
+    compiled as they stand (used to run the middle of raytracing() without its tracer calls)."""
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == func)
+    tgt = lambda n: [t.id for t in n.targets if isinstance(t, ast.Name)] if isinstance(n, ast.Assign) else []
+    i0 = next(i for i, n in enumerate(fn.body) if first_target in tgt(n))
+    i1 = max(i for i, n in enumerate(fn.body) if last_target in tgt(n))
+    return compile(ast.Module(fn.body[i0:i1 + 1], []), path, "exec"), (fn.body[i0].lineno, fn.body[i1].end_lineno)
+
+
+def gen_prepare_fixtures():
+    """what lrt_prepare / lrt_prepare_backward replace, produced by the reference's own statements."""
+    rng = np.random.default_rng(17)
+    gu = lift(f"{REF}/lib/utils/general_utils.py", ["build_rotation", "quaternion_raw_multiply"])
+    gm = lift(f"{REF}/lib/scene/gaussian_model.py",
+              ["GaussianModel.setup_functions", "GaussianModel.get_scaling", "GaussianModel.get_rotation", "GaussianModel.get_world_xyz",
+               "GaussianModel.get_features", "GaussianModel.get_opacity"],
+              dict(build_rotation=gu["build_rotation"], inverse_sigmoid=None), strip_decorators=True)
+    body, lines = lift_statements(f"{REF}/lib/gaussian_renderer/__init__.py", "raytracing", "all_means3D", "colors_precomp")
+
+    class Asset:                                   # the accessor surface raytracing() uses, bound to the lifted methods
+        def __init__(self, P, pose):
+            t = lambda a: torch.tensor(np.asarray(a, np.float32), requires_grad=True)
+            self._xyz = t(rng.uniform(-3, 3, (P, 3))); self._scaling = t(rng.normal(-2.0, 0.6, (P, 2)))
+            self._rotation = t(rng.standard_normal((P, 4)) * rng.uniform(0.3, 3.0, (P, 1)))
+            self._opacity = t(rng.normal(0, 2, (P, 1)))
+            self._features_dc = t(rng.standard_normal((P, 1, 3))); self._features_rest = t(0.1 * rng.standard_normal((P, 15, 3)))
+            self.active_sh_degree = 3; self.max_sh_degree = 3
+            self.bounding_box = None if pose is None else types.SimpleNamespace(frame={1: pose})
+            gm["setup_functions"](self)
+        get_scaling = property(gm["get_scaling"]); get_opacity = property(gm["get_opacity"]); get_features = property(gm["get_features"])
+        def get_rotation(self, ts=0.0): return gm["get_rotation"](self, ts)
+        def get_world_xyz(self, ts=0.0): return gm["get_world_xyz"](self, ts)
+        def leaves(self): return [self._xyz, self._scaling, self._rotation, self._opacity, self._features_dc, self._features_rest]
+
+    def pose():
+        return (torch.tensor(rng.uniform(-20, 20, 3).astype(np.float32)), torch.tensor((rng.standard_normal((1, 4)) * 1.4).astype(np.float32)))
+
+    with cuda_to_cpu():
+        assets = [Asset(300, None), Asset(100, pose()), Asset(120, pose())]
+    out = {"lines": np.array(lines, np.int32), "n_assets": np.int32(len(assets))}
+    names = ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest")
+    for k, a in enumerate(assets):
+        for nm, t in zip(names, a.leaves()):
+            out[f"asset{k}/{nm}"] = t.detach().numpy()
+        if a.bounding_box is not None:
+            out[f"asset{k}/pose_T"] = a.bounding_box.frame[1][0].numpy(); out[f"asset{k}/pose_quat"] = a.bounding_box.frame[1][1].numpy()
+    for tag, dynamic, decomp in (("static", False, False), ("dynamic", True, False), ("object", True, "object"), ("background", True, "background")):
+        use = assets[:1] if decomp == "background" else (assets[1:] if decomp == "object" else assets)
+        ns = dict(torch=torch, gaussian_assets=use, frame=1, decomp=decomp, override_color=None, scaling_modifier=1.0, sensor_center=None,
+                  args=types.SimpleNamespace(dynamic=dynamic, pipe=types.SimpleNamespace(compute_cov3D_python=False, convert_SHs_python=False)),
+                  quaternion_raw_multiply=gu["quaternion_raw_multiply"])
+        for a in assets:
+            for t in a.leaves():
+                t.grad = None
+        with cuda_to_cpu():
+            exec(body, ns)
+        res = [ns[n] for n in ("means3D", "opacity", "scales", "rotations", "shs")]
+        if not dynamic and len(use) > 1:
+            # the reference takes rot_in_local[0] only for a static scene (:117-118): fixtures use one asset there
+            use = use[:1]; ns["gaussian_assets"] = use
+            with cuda_to_cpu():
+                exec(body, ns)
+            res = [ns[n] for n in ("means3D", "opacity", "scales", "rotations", "shs")]
+        ws = [torch.tensor(rng.standard_normal(tuple(t.shape)).astype(np.float32)) for t in res]
+        sum((t * w).sum() for t, w in zip(res, ws)).backward()
+        out[f"{tag}/assets"] = np.array([assets.index(a) for a in use], np.int32)
+        for n, t, w in zip(("means3D", "opacity", "scales", "rotations", "shs"), res, ws):
+            out[f"{tag}/{n}"] = t.detach().numpy(); out[f"{tag}/w_{n}"] = w.numpy()
+        for a in use:
+            k = assets.index(a)
+            for nm, t in zip(names, a.leaves()):
+                out[f"{tag}/g_asset{k}/{nm}"] = t.grad.numpy().copy()
+    # pinhole rays of the Camera branch (lib/gaussian_renderer/__init__.py:31-41 -> graphics_utils.get_rays)
+    gr_ = lift(f"{REF}/lib/utils/graphics_utils.py", ["get_rays"])
+    W_, H_, fovx = 40, 24, 1.2
+    focal = 0.5 * W_ / np.tan(0.5 * fovx)
+    K = np.array([[focal, 0, 0.5 * W_], [0, focal, 0.5 * H_], [0, 0, 1]])
+    c2w = torch.tensor(syn.sensor_pose(4).astype(np.float32))[:3, :4]
+    with cuda_to_cpu():
+        ro, rd = gr_["get_rays"](K, c2w)
+    out["cam/K"] = K; out["cam/c2w"] = c2w.numpy(); out["cam/rays_o"] = ro.numpy(); out["cam/rays_d"] = rd.numpy()
+    out["cam/whf"] = np.array([W_, H_, fovx])
+    np.savez_compressed(os.path.join(OUT, "ref_prepare.npz"), **out)
+    print("ref_prepare.npz: raytracing() lines", lines, {k: v.shape for k, v in out.items() if k.startswith("dynamic/")})
 
 
 # ------------------------------------------------------------------ tracer fixtures from oracle/_ref
@@ -236,5 +330,10 @@ def gen_tracer_fixtures():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    gen_python_fixtures()
-    gen_tracer_fixtures()
+    which = sys.argv[1:] or ["python", "prepare", "tracer"]
+    if "python" in which:
+        gen_python_fixtures()
+    if "prepare" in which:
+        gen_prepare_fixtures()
+    if "tracer" in which:
+        gen_tracer_fixtures()
