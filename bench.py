@@ -404,8 +404,10 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item()), n_launch, ck, host_ms
 
     l0 = ctx.info().kernel_launches
-    step_kernels(Wm)
+    f_w = step_kernels(Wm)
     launches_per_step = ctx.info().kernel_launches - l0                            # kernels of ONE step (a graph replay launches the same kernels)
+    kc_acc[0] += f_w["hit_cnt"].sum(); f_w["out"][..., :4].contiguous()            # first use of these torch kernels loads their modules: not inside the timed region
+    del f_w
     ms_total, launches, clocks, host_ms = timed_region()
 
     # ---- 2. per-phase device times + hit statistics (separate instrumented pass)

@@ -172,6 +172,34 @@ typedef struct lrt_adam_tensor {
 } lrt_adam_tensor;
 int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, double beta1, double beta2, double eps, void* stream);
 
+/* ---- densify / prune as row compaction (second half) ----
+ * The reference restructures a GaussianModel one tensor at a time with torch indexing / torch.cat, re-allocating every parameter and
+ * both Adam moments at each of prune_points, densify_and_clone, densify_and_split (lib/scene/gaussian_model.py:235-352). Here every
+ * tensor that has one row per Gaussian — the six parameters, their exp_avg / exp_avg_sq, the densification statistics — is one
+ * lrt_row_tensor of a HOST table and ONE call moves them all. dst tensors are allocated by the caller (row counts below). */
+#define LRT_MAX_ROW_TENSORS 32
+enum lrt_row_kind {
+    LRT_ROW_COPY = 0,             /* new rows copy their parent's row (rotation, features, opacity) */
+    LRT_ROW_ZERO_NEW = 1,         /* new rows are zero (optimiser moments: cat(state, zeros_like(extension)), :281-282) */
+    LRT_ROW_XYZ = 2,              /* split children: build_rotation(rotation) . sample + xyz (:326-327); clones copy */
+    LRT_ROW_SCALING = 3           /* split children: log(exp(scaling) / (0.8 N)) (:328); clones copy */
+};
+typedef struct lrt_row_tensor {
+    const float* src;             /* (n_rows, row_floats) */
+    float* dst;                   /* (rows out, row_floats) */
+    int32_t row_floats;
+    int32_t kind;                 /* lrt_row_kind; ignored by lrt_compact_rows */
+} lrt_row_tensor;
+/* prune_points (:253-270): dst = src[keep] for every tensor, order kept. keep: device (n_rows) bytes, non-zero = keep. */
+int lrt_compact_rows(lrt_ctx* ctx, int n_rows, const uint8_t* keep, int n_tensors, const lrt_row_tensor* tensors, void* stream);
+/* densify_and_clone + densify_and_split including the removal of the split parents (:311-352), in one pass. Output rows
+ *   [ rows with split_mask == 0, in order | rows with clone_mask != 0, in order | N blocks of the split rows' children ]
+ * = P - n_split + n_clone + N n_split rows (n_clone / n_split = the masks' population counts, which the caller has: the reference
+ * calls .sum().item() on them too). samples: (N n_split, 3) normal samples in the reference's .repeat(N, 1) order (child b of the
+ * j-th split row at row b n_split + j; the caller draws them: torch.normal(0, cat(exp(scaling), 0))); rotation: (P, 4) raw. */
+int lrt_densify_rows(lrt_ctx* ctx, int P, const uint8_t* clone_mask, const uint8_t* split_mask, int n_clone, int n_split, int N,
+                     const float* samples, const float* rotation, int n_tensors, const lrt_row_tensor* tensors, void* stream);
+
 /* Tuning knobs; none of them changes results.
  *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill, 2 = 8 lanes per ray,
  *                           3 = breadth-first wavefront through the hierarchy + per-ray sort + compositing,

@@ -14,7 +14,7 @@ mkdir -p "$OBJ"
 # a change of flags invalidates every object
 STAMP="$OBJ/.flags"; FLAGS_NOW="$NVCC $HOSTCXX $EXTRA"
 if [ ! -f "$STAMP" ] || [ "$(cat "$STAMP")" != "$FLAGS_NOW" ]; then rm -f "$OBJ"/*.o; echo "$FLAGS_NOW" > "$STAMP"; fi
-SRCS=(lrt_api lrt_build lrt_forward lrt_backward lrt_prepare lrt_rays lrt_chamfer lrt_adam)
+SRCS=(lrt_api lrt_build lrt_forward lrt_backward lrt_prepare lrt_rays lrt_chamfer lrt_adam lrt_densify)
 pids=()
 for s in "${SRCS[@]}"; do
     o="$OBJ/$s.o"; fresh=1

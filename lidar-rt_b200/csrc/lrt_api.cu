@@ -41,7 +41,7 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
     DevBuf* bufs[] = {&ctx->leafq, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->rec_g, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
                       &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb,
                       &ctx->wf_ids, &ctx->wf_keys, &ctx->wf_sort_tmp, &ctx->bw_ids, &ctx->bw_keys, &ctx->bw_sort_tmp,
-                      &ctx->bw_off, &ctx->bw_rec_a, &ctx->bw_rec_b, &ctx->sp_cnt, &ctx->sp_rec, &ctx->sp_scan_tmp, &ctx->sp_hits, &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan,
+                      &ctx->bw_off, &ctx->bw_rec_a, &ctx->bw_rec_b, &ctx->dn_pos, &ctx->dn_tmp, &ctx->sp_cnt, &ctx->sp_rec, &ctx->sp_scan_tmp, &ctx->sp_hits, &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan,
                       &ctx->ch_tmp, &ctx->ch_bounds, &ctx->ch_keys_a, &ctx->ch_keys_b, &ctx->ch_idx_a, &ctx->ch_idx_b,
                       &ctx->ch[0].pts, &ctx->ch[0].boxes, &ctx->ch[1].pts, &ctx->ch[1].boxes};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -138,6 +138,19 @@ int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, d
 {
     if (!ctx) return LRT_ERR_INVALID;
     return lrt_adam_step_impl(ctx, n_tensors, tensors, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+int lrt_compact_rows(lrt_ctx* ctx, int n_rows, const uint8_t* keep, int n_tensors, const lrt_row_tensor* tensors, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_compact_rows_impl(ctx, n_rows, keep, n_tensors, tensors, (cudaStream_t)stream);
+}
+
+int lrt_densify_rows(lrt_ctx* ctx, int P, const uint8_t* clone_mask, const uint8_t* split_mask, int n_clone, int n_split, int N,
+                     const float* samples, const float* rotation, int n_tensors, const lrt_row_tensor* tensors, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    return lrt_densify_rows_impl(ctx, P, clone_mask, split_mask, n_clone, n_split, N, samples, rotation, n_tensors, tensors, (cudaStream_t)stream);
 }
 
 int lrt_set_option(lrt_ctx* ctx, int option, int value)

@@ -32,6 +32,7 @@ struct lrt_ctx {
     DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, rec_g, sort_tmp, bounds, counter;
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
     DevBuf bw_off, bw_rec_a, bw_rec_b;   // hit-parallel backward (lrt_backward.cu)
+    DevBuf dn_pos, dn_tmp;               // densify / prune row compaction (lrt_densify.cu)
     DevBuf sp_cnt, sp_rec, sp_scan_tmp, sp_hits;   // split forward passes (lrt_split.cuh): slice offsets, sorted record stream, internal hit lists
     DevBuf bg_ang, bg_cell_of, bg_cells, bg_sray, bg_wide, bg_plan;   // shared-origin beam grid (lrt_beamgrid.cuh)
     // chamfer distance (lrt_chamfer.cu): one Morton-sorted point hierarchy per cloud, rebuilt every call
@@ -107,7 +108,7 @@ struct lrt_ctx {
         return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
                bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
-               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + sp_cnt.cap + sp_rec.cap + sp_scan_tmp.cap + sp_hits.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap + ch_keys_a.cap + ch_keys_b.cap + ch_idx_a.cap + ch_idx_b.cap;
+               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + sp_cnt.cap + sp_rec.cap + sp_scan_tmp.cap + sp_hits.cap + dn_pos.cap + dn_tmp.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap + ch_keys_a.cap + ch_keys_b.cap + ch_idx_a.cap + ch_idx_b.cap;
     }
     BvhView view() const
     {
@@ -148,5 +149,8 @@ int lrt_chamfer_backward_impl(lrt_ctx* ctx, int b, int n, const float* xyz1, int
                               const float* grad_dist1, const float* grad_dist2, const int32_t* idx1, const int32_t* idx2,
                               float* grad_xyz1, float* grad_xyz2, cudaStream_t s);
 int lrt_adam_step_impl(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, double beta1, double beta2, double eps, cudaStream_t s);
+int lrt_compact_rows_impl(lrt_ctx* ctx, int n_rows, const unsigned char* keep, int n_tensors, const lrt_row_tensor* tensors, cudaStream_t s);
+int lrt_densify_rows_impl(lrt_ctx* ctx, int P, const unsigned char* clone_mask, const unsigned char* split_mask, int n_clone, int n_split,
+                          int N, const float* samples, const float* rotation, int n_tensors, const lrt_row_tensor* tensors, cudaStream_t s);
 int lrt_range_rays_impl(lrt_ctx* ctx, int H, int W, const float* inc_table, float inc_lo, float inc_hi, float pixel_offset,
                         float angle_offset, const float* sensor2world, const float* range_map, float* out, float* centre, cudaStream_t s);

@@ -48,6 +48,13 @@ class LrtAdamTensor(ctypes.Structure):
                 ("n", c_int64), ("lr", c_float), ("step", c_int32)]
 
 
+class LrtRowTensor(ctypes.Structure):
+    """lrt_row_tensor of include/lidar_rt_b200.h: one per-Gaussian tensor moved by lrt_compact_rows / lrt_densify_rows."""
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_floats", c_int32), ("kind", c_int32)]
+
+
+ROW_COPY, ROW_ZERO_NEW, ROW_XYZ, ROW_SCALING = 0, 1, 2, 3
+MAX_ROW_TENSORS = 32
 MAX_ASSETS = 128
 _lib = None
 
@@ -84,6 +91,9 @@ def load_library() -> ctypes.CDLL:
     lib.lrt_chamfer_forward.restype = c_int; lib.lrt_chamfer_backward.restype = c_int
     lib.lrt_adam_step.argtypes = [c_void_p, c_int, POINTER(LrtAdamTensor), c_double, c_double, c_double, c_void_p]
     lib.lrt_adam_step.restype = c_int
+    lib.lrt_compact_rows.argtypes = [c_void_p, c_int, c_void_p, c_int, POINTER(LrtRowTensor), c_void_p]
+    lib.lrt_densify_rows.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, fp, fp, c_int, POINTER(LrtRowTensor), c_void_p]
+    lib.lrt_compact_rows.restype = c_int; lib.lrt_densify_rows.restype = c_int
     lib.lrt_set_option.argtypes = [c_void_p, c_int, c_int]
     lib.lrt_get_kernel_times.argtypes = [c_void_p, c_char_p, POINTER(c_float), POINTER(c_int), c_int]
     lib.lrt_get_kernel_times.restype = c_int
@@ -337,6 +347,59 @@ class Context:
         with torch.cuda.device(self.device):
             self._check(self.lib.lrt_adam_step(self._h, int(table.shape[0]), ctypes.cast(table.ctypes.data, POINTER(LrtAdamTensor)),
                                                c_double(beta1), c_double(beta2), c_double(eps), _stream(self.device)))
+
+    # ---- densify / prune row compaction
+    def _row_table(self, rows, n_in):
+        rows = list(rows)
+        if not 1 <= len(rows) <= MAX_ROW_TENSORS:
+            raise LrtError(f"need 1..{MAX_ROW_TENSORS} row tensors, got {len(rows)}")
+        tab = (LrtRowTensor * len(rows))()
+        for k, (src, dst, kind) in enumerate(rows):
+            for t, nm in ((src, "src"), (dst, "dst")):
+                if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                    raise LrtError(f"row tensor {k}: {nm} must be a contiguous float32 CUDA tensor on {self.device}")
+            if src.shape[0] != n_in or tuple(src.shape[1:]) != tuple(dst.shape[1:]):
+                raise LrtError(f"row tensor {k}: src must have {n_in} rows and dst the same row shape")
+            rf = 1
+            for d in src.shape[1:]:
+                rf *= int(d)
+            tab[k].src, tab[k].dst, tab[k].row_floats, tab[k].kind = src.data_ptr(), dst.data_ptr(), max(rf, 1), int(kind)
+        return tab, len(rows), rows
+
+    @staticmethod
+    def _mask(m, n, name):
+        if not isinstance(m, torch.Tensor) or not m.is_cuda or m.numel() != n:
+            raise LrtError(f"{name} must be a CUDA tensor with {n} entries")
+        return (m.reshape(-1) != 0).to(torch.uint8).contiguous()
+
+    def compact_rows(self, keep, rows):
+        """lrt_compact_rows: dst = src[keep] for every (src, dst, kind) of `rows` (kind ignored). dst must have keep.sum() rows."""
+        rows = list(rows)
+        n = rows[0][0].shape[0]
+        k8 = self._mask(keep, n, "keep")
+        tab, nt, _ = self._row_table(rows, n)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.lrt_compact_rows(self._h, n, _ptr(k8), nt, tab, _stream(self.device)))
+
+    def densify_rows(self, clone_mask, split_mask, n_clone, n_split, N, samples, rotation, rows):
+        """lrt_densify_rows: clone + split + removal of the split parents in one pass (see include/lidar_rt_b200.h)."""
+        rows = list(rows)
+        P = rows[0][0].shape[0]
+        c8, s8 = self._mask(clone_mask, P, "clone_mask"), self._mask(split_mask, P, "split_mask")
+        n_out = P - n_split + n_clone + N * n_split
+        for k, (_, dst, _) in enumerate(rows):
+            if dst.shape[0] != n_out:
+                raise LrtError(f"row tensor {k}: dst must have {n_out} rows")
+        smp = rot = None
+        if n_split > 0:
+            smp = _f32(samples, "samples", (3,), self.device)
+            if smp.shape[0] != N * n_split:
+                raise LrtError("samples must be (N * n_split, 3)")
+            rot = _f32(rotation, "rotation", (4,), self.device)
+        tab, nt, _ = self._row_table(rows, P)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.lrt_densify_rows(self._h, P, _ptr(c8), _ptr(s8), int(n_clone), int(n_split), int(N), _ptr(smp), _ptr(rot), nt, tab,
+                                                  _stream(self.device)))
 
     # ---- Chamfer distance (SURVEY 8f N2)
     @staticmethod

@@ -18,6 +18,8 @@ Two sources, both the reference's OWN code:
           and the accessor loop + concatenations + rotation composition of lib/gaussian_renderer/__init__.py:68-134
           (statements cut out of raytracing() and executed as they are) -> ref_prepare.npz, values AND leaf gradients
       lib/utils/graphics_utils.py::get_rays                    (pinhole rays of the Camera branch of raytracing())
+      lib/scene/gaussian_model.py::GaussianModel.prune_points / densify_and_clone / densify_and_split / densify_and_prune (+ the
+          optimizer-state helpers they call), over a real torch.optim.Adam -> ref_densify.npz
 The fixtures are small; the GPU box has no /root/reference, so tests read only these files.
 """
 from __future__ import annotations
@@ -225,6 +227,84 @@ def gen_prepare_fixtures():
     print("ref_prepare.npz: raytracing() lines", lines, {k: v.shape for k, v in out.items() if k.startswith("dynamic/")})
 
 
+def gen_densify_fixtures():
+    """the reference's restructuring methods (gaussian_model.py:235-407), lifted and run unmodified on the CPU over a
+    seeded model with a real torch.optim.Adam(l, lr=0.0, eps=1e-15) that has taken two steps. The split's torch.normal samples are
+    recorded on the way so the native kernels can be fed the same numbers."""
+    torch.manual_seed(23)
+    rng = np.random.default_rng(23)
+    gu = lift(f"{REF}/lib/utils/general_utils.py", ["build_rotation"])
+    meths = ["setup_functions", "get_scaling", "get_opacity", "get_local_xyz", "_prune_optimizer", "prune_points", "cat_tensors_to_optimizer",
+             "densification_postfix", "densify_and_split", "densify_and_clone", "densify_and_prune"]
+    recorded = []
+    real_normal = torch.normal
+
+    def normal_rec(*a, **k):
+        r = real_normal(*a, **k); recorded.append(r.clone()); return r
+    class _TorchShim:                                  # `torch` as the lifted methods see it: normal() recorded, cuda.empty_cache() a no-op
+        normal = staticmethod(normal_rec)
+        cuda = types.SimpleNamespace(empty_cache=lambda: None)
+
+        def __getattr__(self, k):
+            return getattr(torch, k)
+    tshim = _TorchShim()
+    gm = lift(f"{REF}/lib/scene/gaussian_model.py", [f"GaussianModel.{m}" for m in meths],
+              dict(build_rotation=gu["build_rotation"], inverse_sigmoid=None, nn=torch.nn, torch=tshim, print=lambda *a, **k: None), strip_decorators=True)
+    P = 400
+
+    class M:
+        pass
+    for m in meths:
+        if m in ("get_scaling", "get_opacity", "get_local_xyz"):
+            setattr(M, m, property(gm[m]))
+        else:
+            setattr(M, m, gm[m])
+    me = M()
+    me.setup_functions()
+    t = lambda a: torch.nn.Parameter(torch.tensor(np.asarray(a, np.float32)))
+    me._xyz = t(rng.uniform(-5, 5, (P, 3))); me._features_dc = t(rng.standard_normal((P, 1, 3))); me._features_rest = t(0.1 * rng.standard_normal((P, 15, 3)))
+    me._opacity = t(rng.normal(0, 2.5, (P, 1))); me._scaling = t(rng.normal(-2.2, 0.7, (P, 2))); me._rotation = t(rng.standard_normal((P, 4)) * 1.5)
+    me.dimension = 2; me.extent = 10.0; me.densify_scale_threshold = 0.012; me.bounding_box = None
+    me.max_radii2D = torch.zeros(P)
+    me.xyz_gradient_accum = torch.tensor(rng.uniform(0, 2e-3, (P, 1)).astype(np.float32)); me.denom = torch.tensor(rng.integers(0, 4, (P, 1)).astype(np.float32))
+    names = [("xyz", "_xyz"), ("f_dc", "_features_dc"), ("f_rest", "_features_rest"), ("opacity", "_opacity"), ("scaling", "_scaling"), ("rotation", "_rotation")]
+    me.optimizer = torch.optim.Adam([{"params": [getattr(me, a)], "lr": 1e-3 * (k + 1), "name": n} for k, (n, a) in enumerate(names)], lr=0.0, eps=1e-15)
+    for _ in range(2):
+        for n, a in names:
+            getattr(me, a).grad = torch.tensor(rng.standard_normal(tuple(getattr(me, a).shape)).astype(np.float32))
+        me.optimizer.step()
+    out = {}
+
+    def snap(tag):
+        for n, a in names:
+            p = getattr(me, a); st = me.optimizer.state[p]
+            out[f"{tag}/{n}"] = p.detach().numpy().copy(); out[f"{tag}/{n}/exp_avg"] = st["exp_avg"].numpy().copy()
+            out[f"{tag}/{n}/exp_avg_sq"] = st["exp_avg_sq"].numpy().copy(); out[f"{tag}/{n}/step"] = np.float32(float(st["step"]))
+        out[f"{tag}/xyz_gradient_accum"] = me.xyz_gradient_accum.numpy().copy(); out[f"{tag}/denom"] = me.denom.numpy().copy()
+        out[f"{tag}/max_radii2D"] = me.max_radii2D.numpy().copy()
+    snap("in")
+    # 1. prune_points alone
+    mask = torch.tensor(rng.random(P) < 0.3)
+    out["prune/mask"] = mask.numpy()
+    import copy
+    keep_state = copy.deepcopy((me.__dict__))
+    with cuda_to_cpu():
+        me.prune_points(mask)
+    snap("prune")
+    # 2. the whole densify_and_prune on the ORIGINAL model
+    me.__dict__.update(keep_state)
+    opt = types.SimpleNamespace(densify_grad_threshold=3e-4, thresh_opa_prune=0.05, prune_size_threshold=0.5)
+    out["opt"] = np.array([opt.densify_grad_threshold, opt.thresh_opa_prune, opt.prune_size_threshold, me.densify_scale_threshold, me.extent], np.float64)
+    with cuda_to_cpu():
+        res = me.densify_and_prune(opt, 0.005, 20)
+    out["densify/counts"] = np.array(res, np.int64)
+    out["densify/samples"] = recorded[0].detach().numpy()
+    snap("densify")
+    np.savez_compressed(os.path.join(OUT, "ref_densify.npz"), **out)
+    print("ref_densify.npz: prune keeps", int((~mask).sum()), "of", P, "; densify_and_prune (clone, split, prune_scale, prune_opacity) =", res,
+          "->", out["densify/xyz"].shape[0], "rows; samples", out["densify/samples"].shape)
+
+
 # ------------------------------------------------------------------ tracer fixtures from oracle/_ref
 BG = np.array([0.0, 0.0, 1.0], np.float32)      # train.py:104-106
 
@@ -330,10 +410,12 @@ def gen_tracer_fixtures():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["python", "prepare", "tracer"]
+    which = sys.argv[1:] or ["python", "prepare", "densify", "tracer"]
     if "python" in which:
         gen_python_fixtures()
     if "prepare" in which:
         gen_prepare_fixtures()
+    if "densify" in which:
+        gen_densify_fixtures()
     if "tracer" in which:
         gen_tracer_fixtures()
