@@ -377,6 +377,8 @@ class Context:
         rows = list(rows)
         n = rows[0][0].shape[0]
         k8 = self._mask(keep, n, "keep")
+        if n == 0 or all(dst.shape[0] == 0 for _, dst, _ in rows):
+            return                                   # nothing survives: the (empty) outputs are already what src[keep] is
         tab, nt, _ = self._row_table(rows, n)
         with torch.cuda.device(self.device):
             self._check(self.lib.lrt_compact_rows(self._h, n, _ptr(k8), nt, tab, _stream(self.device)))
