@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) k_bg_angles(FwdArgs a, WfBufs w, BgBufs b
         ok = (az == az) && (el == el);
         b.ang[r] = ok ? make_float2(az, el) : make_float2(0.0f, 0.0f);     // NaN direction: hits nothing anyway
         w.hit_count[r] = 0;
+        w.emax[r] = 0;
         w.ray_ids[r] = r;
     }
     float hi = ok ? el : -4.0f, nlo = ok ? -el : -4.0f;
@@ -123,7 +124,19 @@ __device__ __forceinline__ bool bg_window(const SurfelRec* __restrict__ rec, int
     const float cx = r0.x - o[0], cy = r0.y - o[1], cz = r0.z - o[2];
     const float dist = sqrtf(cx * cx + cy * cy + cz * cz);
     if (!(dist < 1e30f) || !(su < 1e30f) || !(sv < 1e30f)) return false;
-    const float pad = 1e-4f + 2e-5f * dist;                                // world-space slack, >> fp32 rounding of the quad test
+    float pad = 1e-4f + 2e-5f * dist;                                      // world-space slack, >> fp32 rounding of the quad test
+    {   // + what quad_candidate() allows a hit to move in the surfel's plane: its depth-error bound for the least favourable ray
+        // that can hit the (relaxed) quad. Points x of the quad's plane have n.x = n.c, so n.d >= |n.c| / (dist + reach).
+        const float r3x = __ldg(&rec[i].r3.x), r3y = __ldg(&rec[i].r3.y), r3z = __ldg(&rec[i].r3.z);
+        const float reach = sqrtf(ax * ax + ay * ay + az_ * az_) + sqrtf(bx * bx + by * by + bz * bz);
+        const float tmax = dist + reach;
+        const float den_min = fabsf(r3x * cx + r3y * cy + r3z * cz) / tmax;
+        const float Sc = fabsf(r3x) * (fabsf(cx) + reach) + fabsf(r3y) * (fabsf(cy) + reach) + fabsf(r3z) * (fabsf(cz) + reach);
+        const float So = fabsf(r3x * o[0]) + fabsf(r3y * o[1]) + fabsf(r3z * o[2]);
+        float e = 1.2e-7f * ((8.0f * Sc + 12.0f * tmax + So) / den_min) + 3.6e-7f * tmax;
+        if (!(e < LRT_ERR_CAP)) e = LRT_ERR_CAP;
+        pad += e;
+    }
     const float ez = fabsf(az_) + fabsf(bz) + pad;
     const float exy = sqrtf(ax * ax + ay * ay) + sqrtf(bx * bx + by * by) + pad;
     const float rad = sqrtf(ax * ax + ay * ay + az_ * az_) + sqrtf(bx * bx + by * by + bz * bz) + pad;
@@ -165,12 +178,8 @@ __device__ __forceinline__ void bg_test_and_append(const SurfelRec* __restrict__
 {
     RaySetup rs;
     rs.ox = o[0]; rs.oy = o[1]; rs.oz = o[2]; rs.dx = sr.x; rs.dy = sr.y; rs.dz = sr.z;
-    float t; int g;
-    if (quad_candidate(rec, i, rs, t, g)) {
-        const int ray = __float_as_int(sr.w);
-        const int pos = atomicAdd(w.hit_count + ray, 1) & (WF_TAINT - 1);
-        if (pos < w.hcap) w.bins[(size_t)ray * w.hcap + pos] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
-    }
+    float t, e; int g;
+    if (quad_candidate(rec, i, rs, t, g, e)) wf_append(w, __float_as_int(sr.w), t, g, e);
 }
 
 // ---- 4. one pass over the surfel records. A warp takes 32 consecutive records (Morton order: neighbours in space,

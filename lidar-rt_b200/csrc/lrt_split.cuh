@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
         const int hc = w.hit_count[r];
         if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; a.hit_cnt[r] = 0; continue; }
         const int n = hc;
+        const float em = __int_as_float(w.emax[r]);
         const float4* __restrict__ rec = sp.srec + 4 * (size_t)sp.cbase[r];              // candidate i = rec[4 i .. 4 i + 3]
         FwdRay q;
         fwd_ray_init(q, r, a);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
         for (;;) {
             RaySetup rs;
             ray_setup(rs, q.o, q.d, q.base);
-            const float thr = q.base - 2.0f * (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
+            const float thr = q.base - 2.0f * wf_margin(q.base, em);
             {   // first candidate at or beyond thr (the stream is sorted by t). It lies a few entries in front of where the
                 // previous round stopped: walk back from there eight independent loads at a time (one wait per eight).
                 int hi = i_end;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
                     if (i0 + k >= n || done) continue;
                     if (cnt == LRT_KBUF) {
                         const float t16 = __uint_as_float((unsigned)(klast >> 32)) + q.base;
-                        if (t0v[k] - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) { done = true; i_end = i0 + k; continue; }
+                        if (t0v[k] - t16 > wf_margin(t16, em)) { done = true; i_end = i0 + k; continue; }
                     }
                     if (!hitv[k]) continue;
                     const unsigned long long key = keyv[k];

@@ -75,10 +75,22 @@ __device__ __forceinline__ bool quad_hit(const SurfelRec* __restrict__ rec, int 
     return t < LRT_TMAX;
 }
 
-// Candidate test for the wavefront's hit bins: the same plane hit, but with the quad bounds relaxed by a
-// margin far above fp32 rounding, so that the bin is a SUPERSET of what the exact test accepts from any
-// re-based origin on this ray. The exact quad_hit() decides, per round, which candidates are slots.
-__device__ __forceinline__ bool quad_candidate(const SurfelRec* __restrict__ rec, int prim, const RaySetup& r, float& t_out, int& g_out)
+// Candidate test for the wavefront's hit bins: the same plane hit, but with the quad bounds relaxed so that the bin is a
+// SUPERSET of what the exact test accepts from any re-based origin on this ray. The exact quad_hit() decides, per round, which
+// candidates are slots.
+//
+// How far apart can the two computations of a hit's depth be — t from the ray's origin o (the bin key) and t' + base from the
+// re-based origin o' = o + base d (what a round computes)? Both evaluate n.(mu - origin) / n.d in fp32; with u = 2^-24,
+//   S_c = sum |n_k| |mu_k - o_k|,  S_d = sum |n_k| |d_k|,  S_o = sum |n_k| |o_k|
+// a first-order bound of every rounding on both paths (differences, the three-term dot products, the division, o' itself and the
+// final t' + base) is   |t - (t' + base)| <= u (8 S_c + 12 |t| S_d + S_o) / |n.d| + 3 u |t|.
+// It grows like 1 / |n.d|: a ground surfel hit at a grazing angle of 2 degrees at 50 m, or a scene placed kilometres from the world
+// origin, exceeds the fixed millimetre margin the sorted-bin scan used to rely on. The bound (with a factor 2) is
+// returned in e_out: it widens this test's limits by the in-plane motion it allows, the beam-grid window (lrt_beamgrid.cuh), and —
+// as the per-ray maximum — the margin with which the compositing passes skip and stop in the sorted bin (wf_margin()).
+#define LRT_ERR_FLOOR 2.5e-4f      // below this the fixed margin covers the error: no per-ray bookkeeping
+#define LRT_ERR_CAP 5e-2f          // a candidate whose depth is uncertain by more than this sends its ray to the exact per-ray path
+__device__ __forceinline__ bool quad_candidate(const SurfelRec* __restrict__ rec, int prim, const RaySetup& r, float& t_out, int& g_out, float& e_out)
 {
     const float4 a0 = ld_f4(&rec[prim].r0), a3 = ld_f4(&rec[prim].r3);
     const float c0 = a0.x - r.ox, c1 = a0.y - r.oy, c2 = a0.z - r.oz;
@@ -87,15 +99,28 @@ __device__ __forceinline__ bool quad_candidate(const SurfelRec* __restrict__ rec
     const float t = num / den;
     if (!(t > -1e-3f)) return false;
     const float4 a1 = ld_f4(&rec[prim].r1), a2 = ld_f4(&rec[prim].r2);
+    const float anx = fabsf(a3.x), any_ = fabsf(a3.y), anz = fabsf(a3.z);
+    const float Sc = anx * fabsf(c0) + any_ * fabsf(c1) + anz * fabsf(c2);
+    const float Sd = anx * fabsf(r.dx) + any_ * fabsf(r.dy) + anz * fabsf(r.dz);
+    const float So = anx * fabsf(r.ox) + any_ * fabsf(r.oy) + anz * fabsf(r.oz);
+    const float at = fabsf(t);
+    float e = 1.2e-7f * ((8.0f * Sc + 12.0f * at * Sd + So) / fabsf(den)) + 3.6e-7f * at;          // 2 u (...) / |n.d| + 6 u |t|
+    if (!(e < LRT_ERR_CAP)) e = LRT_ERR_CAP;                                                      // also NaN / inf (n.d == 0)
     const float r0 = (r.ox + t * r.dx) - a0.x, r1 = (r.oy + t * r.dy) - a0.y, r2 = (r.oz + t * r.dz) - a0.z;
     const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
     const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
     const float lim = a0.w + 1e-3f * (1.0f + a0.w);
-    if (!(fabsf(u) <= lim && fabsf(v) <= lim)) return false;
+    // a depth error e moves the hit point by e d: |du| <= e sum |Lu_k d_k|
+    const float gu = fabsf(a1.x * r.dx) + fabsf(a1.y * r.dy) + fabsf(a1.z * r.dz), gv = fabsf(a2.x * r.dx) + fabsf(a2.y * r.dy) + fabsf(a2.z * r.dz);
+    if (!(fabsf(u) <= lim + e * gu && fabsf(v) <= lim + e * gv)) return false;
     t_out = fmaxf(t, 0.0f);
     g_out = __float_as_int(a2.w);
+    e_out = e;
     return t < LRT_TMAX;
 }
+
+// margin of the sorted-bin scan around depth t for a ray whose worst candidate error bound is em
+__device__ __forceinline__ float wf_margin(float t, float em) { return fmaxf(1e-3f + 1e-5f * fabsf(t), em); }
 
 // Sorted insertion into the register-resident k-buffer (ascending 64-bit keys = (t' bits, Gaussian id)).
 __device__ __forceinline__ void kbuf_insert(unsigned long long (&kb)[LRT_KBUF], unsigned long long key)

@@ -34,6 +34,7 @@ struct WfBufs {
     int* counts;                    // [0..7] items per level, [8] fallback count, [9] heavy beam-grid items, [10] bins beyond 512 candidates,
                                     // [12] rays whose hit list overflowed in the split passes, [13] candidate records in the sorted stream
     int* hit_count;                 // (R) hits in bin | WF_TAINT
+    int* emax;                      // (R) float bits: largest depth-error bound among the ray's candidates (0 below LRT_ERR_FLOOR)
     unsigned long long* bins;       // (R, hcap)
     int hcap;                       // bin capacity (<= WF_HCAP_MAX)
     int* fb_list;                   // (R) fallback ray ids
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) k_wf_setup(FwdArgs a, WfBufs w)
     ray_setup(rs, o, d, 0.0f);
     w.rs[r] = rs;
     w.hit_count[r] = 0;
+    w.emax[r] = 0;
     w.ray_ids[r] = r;
 }
 
@@ -124,6 +126,15 @@ __device__ __forceinline__ unsigned leafq_eval(const LeafQ* __restrict__ lq, con
     return m;
 }
 
+// a candidate joins its ray's bin; its depth-error bound joins the ray's maximum (or, beyond the cap, hands the ray to the exact path)
+__device__ __forceinline__ void wf_append(const WfBufs& w, int ray, float t, int g, float e)
+{
+    const int pos = atomicAdd(w.hit_count + ray, 1) & (WF_TAINT - 1);
+    if (pos < w.hcap) w.bins[(size_t)ray * w.hcap + pos] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+    if (e >= LRT_ERR_CAP) atomicOr(w.hit_count + ray, WF_TAINT);
+    else if (e > LRT_ERR_FLOOR) atomicMax(w.emax + ray, __float_as_int(e));
+}
+
 // One (ray, leaf) item per thread: the leaf's 8 surfel boxes, then the exact quad test (same arithmetic
 // as the per-ray kernels, bounds relaxed: the bin holds CANDIDATES), appended to the ray's bin.
 __global__ void __launch_bounds__(256) k_wf_leaf(BvhView bvh, FwdArgs a, WfBufs w, const uint2* __restrict__ in, const int* __restrict__ in_count)
@@ -159,11 +170,8 @@ __global__ void __launch_bounds__(256) k_wf_leaf(BvhView bvh, FwdArgs a, WfBufs 
         for (int j = lane; j < total; j += 32) {
             const uint2 pr = q[j];
             const RaySetup rs = w.rs[pr.x];
-            float t; int g;
-            if (quad_candidate(bvh.rec, (int)pr.y, rs, t, g)) {
-                const int pos = atomicAdd(w.hit_count + pr.x, 1) & (WF_TAINT - 1);
-                if (pos < w.hcap) w.bins[(size_t)pr.x * w.hcap + pos] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
-            }
+            float t, e; int g;
+            if (quad_candidate(bvh.rec, (int)pr.y, rs, t, g, e)) wf_append(w, (int)pr.x, t, g, e);
         }
         __syncwarp(FULL);
     }
@@ -227,6 +235,7 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
             continue;
         }
         const int n = hc;
+        const float em = __int_as_float(w.emax[r]);
         // ---- load + sort the bin (bitonic over the next power of two, in shared memory)
         int m = 32; while (m < n) m <<= 1;
         for (int i = lane; i < m; i += 32) keys[i] = i < n ? w.bins[(size_t)r * w.hcap + i] : LRT_KEY_EMPTY;
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
                 // the 16th best — so the round's slots are exactly the 16 nearest hits of the re-based ray.
                 RaySetup rs;
                 ray_setup(rs, q.o, q.d, q.base);
-                const float thr = q.base - 2.0f * (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
+                const float thr = q.base - 2.0f * wf_margin(q.base, em);
                 int below = 0;
                 for (int i = lane; i < n; i += 32) below += __uint_as_float((unsigned)(keys[i] >> 32)) < thr;
 #pragma unroll
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
                         const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
                         const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
                         const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
-                        if (t_next - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) break;
+                        if (t_next - t16 > wf_margin(t16, em)) break;
                     }
                 }
                 {
@@ -302,12 +311,12 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
                         const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
                         const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
                         const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
-                        if (!(have >= LRT_KBUF && t_next - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16))) sorted_ok = false;
+                        if (!(have >= LRT_KBUF && t_next - t16 > wf_margin(t16, em))) sorted_ok = false;
                     }
                     if (sorted_ok && have >= 32) {                                  // valid keys beyond the 32nd were dropped: they must
                         const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1), k32 = __shfl_sync(FULL, best, 31);   // lie safely behind the 16th
                         const float t16 = __uint_as_float((unsigned)(k16 >> 32)), t32 = __uint_as_float((unsigned)(k32 >> 32));
-                        if (!(t32 - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16 + q.base))) sorted_ok = false;
+                        if (!(t32 - t16 > wf_margin(t16 + q.base, em))) sorted_ok = false;
                     }
                 }
                 if (!sorted_ok) {                                                   // general path (near-ties re-ordered by re-basing)
@@ -329,7 +338,7 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
                     if (k16 != LRT_KEY_EMPTY) {
                         const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
                         const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
-                        if (t_next - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) break;   // nothing further can rank in the first 16
+                        if (t_next - t16 > wf_margin(t16, em)) break;   // nothing further can rank in the first 16
                     }
                 }
                 }
@@ -522,6 +531,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE_MIN_BLOCKS) k_wf_composite(
         const int hc = w.hit_count[r];
         if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }
         const int n = hc;
+        const float em = __int_as_float(w.emax[r]);
         const unsigned long long* __restrict__ bin = w.bins + (size_t)r * w.hcap;       // sorted by (t from o, id)
         FwdRay q;
         fwd_ray_init(q, r, a);
@@ -531,7 +541,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE_MIN_BLOCKS) k_wf_composite(
             // (at most) 16 smallest (t', id); stop once the next candidate lies safely behind the 16th
             RaySetup rs;
             ray_setup(rs, q.o, q.d, q.base);
-            const float thr = q.base - 2.0f * (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
+            const float thr = q.base - 2.0f * wf_margin(q.base, em);
             while (pos < n && __uint_as_float((unsigned)(bin[pos] >> 32)) < thr) pos++;
             unsigned long long kb[LRT_KBUF];
             int cnt = 0;
@@ -541,7 +551,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE_MIN_BLOCKS) k_wf_composite(
                 if (i + 1 < n) ck_next = bin[i + 1];                                       // one ahead: its latency hides behind this test
                 if (cnt == LRT_KBUF) {
                     const float t16 = __uint_as_float((unsigned)(kb[LRT_KBUF - 1] >> 32)) + q.base;
-                    if (__uint_as_float((unsigned)(ck >> 32)) - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) break;
+                    if (__uint_as_float((unsigned)(ck >> 32)) - t16 > wf_margin(t16, em)) break;
                 }
                 const int g = (int)(unsigned)(ck & 0xffffffffull);
                 float t; int g2;
@@ -593,6 +603,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite
         const int hc = w.hit_count[r];
         if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }
         const int n = hc;
+        const float em = __int_as_float(w.emax[r]);
         const unsigned long long* __restrict__ bin = w.bins + (size_t)r * w.hcap;       // sorted by (t from o, id)
         FwdRay q;
         fwd_ray_init(q, r, a);
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite
         for (;;) {
             RaySetup rs;
             ray_setup(rs, q.o, q.d, q.base);
-            const float thr = q.base - 2.0f * (WF_WINDOW_MARGIN + 1e-5f * fabsf(q.base));
+            const float thr = q.base - 2.0f * wf_margin(q.base, em);
             {   // first candidate at or beyond thr: lower bound in [pos, i_end] (the bin is sorted by t) — a few dependent loads instead of one per skipped candidate
                 int lo = pos, hi = i_end;
                 while (lo < hi) {
@@ -635,7 +646,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite
                     const float4 a0 = b0[k], a3 = b3[k];
                     if (cnt == LRT_KBUF) {
                         const float t16 = __uint_as_float((unsigned)(klast >> 32)) + q.base;
-                        if (__uint_as_float((unsigned)(ck >> 32)) - t16 > WF_WINDOW_MARGIN + 1e-5f * fabsf(t16)) { done = true; i_end = i0 + k; continue; }
+                        if (__uint_as_float((unsigned)(ck >> 32)) - t16 > wf_margin(t16, em)) { done = true; i_end = i0 + k; continue; }
                     }
                     const int g = (int)(unsigned)(ck & 0xffffffffull);
                     // quad_hit(), operation for operation

@@ -454,6 +454,37 @@ def _vs_oracle(ctx, oracle32, o, d, sc, D, mod=1.0, with_grad=True, seed=0):
     return res
 
 
+def test_far_from_world_origin_and_grazing_ground_rays(ctx, oracle32):
+    """the sorted-bin scan's fixed millimetre window is not a bound on |t from o - (t' + base)|, which grows like
+    ulp(|world coordinate|) / |n.d|. A ground strip seen at grazing angles of 0.3-6 degrees out to 150 m, with scene and sensor
+    translated 3 km from the world origin: the windowed paths (beam grid, wavefront) must still give the per-ray traversal's and the
+    brute-force oracle's hit lists bit for bit (per-candidate error bounds -> per-ray margins, lrt_trace.cuh)."""
+    from lidar_rt_b200 import native
+    rng = np.random.default_rng(41)
+    P = 9000
+    shift = np.array([3000.0, -2000.0, 150.0], np.float32)
+    means = np.stack([rng.uniform(4, 150, P), rng.uniform(-2.5, 2.5, P), -2.0 + 0.02 * rng.standard_normal(P)], 1).astype(np.float32)
+    nrm = np.tile([0.0, 0.0, 1.0], (P, 1)) + 0.05 * rng.standard_normal((P, 3))
+    sc = dict(means=means + shift, scales=np.exp(rng.normal(np.log(0.25), 0.4, (P, 2))).astype(np.float32),
+              rots=syn._quat_from_normal(nrm, rng.uniform(0, 2 * np.pi, P)).astype(np.float32),
+              opac=np.clip(rng.uniform(0.02, 0.5, (P, 1)), 0.01, 0.999).astype(np.float32), shs=(0.05 * rng.standard_normal((P, 16, 3))).astype(np.float32))
+    H, W = 24, 96
+    el = -np.radians(np.geomspace(0.3, 6.0, H))[:, None]; az = np.radians(np.linspace(-0.9, 0.9, W))[None, :]
+    d = np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el) * np.ones_like(az)], -1).astype(np.float32)
+    o = shift.reshape(1, 3).copy()
+    f = oracle32.forward(o, d, BG, sc["means"], sc["scales"], sc["rots"], sc["opac"], sc["shs"], 2, cap=128)      # brute force over all quads
+    assert f["slot_cnt"].max() > 32 and f["hit_cnt"].mean() > 4
+    try:
+        for kernel in (4, 3, 0):
+            ctx.set_option(native.OPT_FORWARD_KERNEL, kernel)
+            res = run_cuda(ctx, o, d, sc, 2, cap=128)
+            assert hit_lists(res) == oracle_lists(f), f"kernel {kernel}: hit indices must be bit-exact"
+            assert np.array_equal(res["slot_cnt"], f["slot_cnt"]), f"kernel {kernel}"
+            assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, f"kernel {kernel} forward")
+    finally:
+        ctx.set_option(native.OPT_FORWARD_KERNEL, 4)
+
+
 def test_per_ray_origins_and_unnormalised_directions(ctx, oracle32):
     """ray_o (R,3) with a different origin per ray (stride 3) and |d| != 1 (t is the ray parameter; SH uses d/|d|)."""
     sc = as_dict(syn.make_street_scene(40000, seed=21))
