@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_bg_angles(FwdArgs a, WfBufs w, BgBufs b
         ok = (az == az) && (el == el);
         b.ang[r] = ok ? make_float2(az, el) : make_float2(0.0f, 0.0f);     // NaN direction: hits nothing anyway
         w.hit_count[r] = 0;
-        w.emax[r] = 0;
+        w.emax[r] = 0; w.nwild[r] = 0;
         w.ray_ids[r] = r;
     }
     float hi = ok ? el : -4.0f, nlo = ok ? -el : -4.0f;

@@ -545,7 +545,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_a, sizeof(uint2) * (size_t)cap_items));
             LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_b, sizeof(uint2) * (size_t)cap_items));
         }
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_hit_count, sizeof(int) * 2 * (size_t)R));
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_hit_count, sizeof(int) * 3 * (size_t)R));
         // bin capacity: 8192 candidates per ray while that stays under ~6 GB (4096 at one Waymo frame), never below what the
         // shared-memory sort takes
         int hcap = WF_HCAP_MAX;
@@ -558,7 +558,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->counter, sizeof(int) * 16));
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 16, s));
         w.rs = (RaySetup*)ctx->wf_rs.p; w.list_a = (uint2*)ctx->wf_list_a.p; w.list_b = (uint2*)ctx->wf_list_b.p;
-        w.cap_items = (int)cap_items; w.counts = (int*)ctx->counter.p; w.hit_count = (int*)ctx->wf_hit_count.p; w.emax = w.hit_count + R;
+        w.cap_items = (int)cap_items; w.counts = (int*)ctx->counter.p; w.hit_count = (int*)ctx->wf_hit_count.p; w.emax = w.hit_count + R; w.nwild = w.hit_count + 2 * (size_t)R;
         w.bins = (unsigned long long*)ctx->wf_bins.p; w.fb_list = (int*)ctx->wf_fb.p; w.big_list = (int*)ctx->wf_fb.p + R;
         w.ov_list = (int*)ctx->wf_fb.p + 2 * (size_t)R;
         w.ray_ids = (int*)ctx->wf_ids.p; w.order = nullptr;

@@ -172,11 +172,12 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
         if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; a.hit_cnt[r] = 0; continue; }
         const int n = hc;
         const float em = __int_as_float(w.emax[r]);
+        const int nw = min(w.nwild[r], n);                         // wild candidates (key t = 0): the first nw of the sorted stream, tested in every round
         const float4* __restrict__ rec = sp.srec + 4 * (size_t)sp.cbase[r];              // candidate i = rec[4 i .. 4 i + 3]
         FwdRay q;
         fwd_ray_init(q, r, a);
-        int pos = 0;                                               // first candidate that can still matter
-        int i_end = 0;                                             // where the previous round's scan stopped: everything from there on lies beyond thr
+        int pos = nw;                                              // first candidate of the sorted part that can still matter
+        int i_end = nw;                                            // where the previous round's scan stopped: everything from there on lies beyond thr
         for (;;) {
             RaySetup rs;
             ray_setup(rs, q.o, q.d, q.base);
@@ -200,10 +201,12 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
             int cnt = 0;
             unsigned long long klast = 0ull;                       // s_kb[cnt - 1]
             bool done = false;
-            for (int i0 = pos; i0 < n && !done; i0 += SP_BATCH) {
+            for (int seg = nw > 0 ? 0 : 1; seg < 2; seg++) {       // segment 0: the wild candidates, no window; segment 1: the sorted rest
+            const int i_lo = seg ? pos : 0, i_hi = seg ? n : nw;
+            for (int i0 = i_lo; i0 < i_hi && !done; i0 += SP_BATCH) {
                 {
                     const float4* src = rec + 4 * (size_t)i0;
-                    const int nv = 4 * min(SP_BATCH, n - i0);
+                    const int nv = 4 * min(SP_BATCH, i_hi - i0);
 #pragma unroll
                     for (int v = 0; v < 4 * SP_BATCH; v++) if (v < nv) sp_cp_async16(&s_st[v][tx], src + v);
                     sp_cp_async_wait_all();
@@ -248,8 +251,8 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
                 // phase 2, in order: window stop, k-buffer
 #pragma unroll
                 for (int k = 0; k < SP_BATCH; k++) {
-                    if (i0 + k >= n || done) continue;
-                    if (cnt == LRT_KBUF) {
+                    if (i0 + k >= i_hi || done) continue;
+                    if (seg && cnt == LRT_KBUF) {
                         const float t16 = __uint_as_float((unsigned)(klast >> 32)) + q.base;
                         if (t0v[k] - t16 > wf_margin(t16, em)) { done = true; i_end = i0 + k; continue; }
                     }
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
                     cnt++;
                     klast = s_kb[cnt - 1][tx];
                 }
+            }
             }
             // the round's compositing (fwd_shade_round()) without the colour: weights, depth, transmittance, hit records
             bool terminated = false;

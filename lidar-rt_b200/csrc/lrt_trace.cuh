@@ -88,8 +88,8 @@ __device__ __forceinline__ bool quad_hit(const SurfelRec* __restrict__ rec, int 
 // origin, exceeds the fixed millimetre margin the sorted-bin scan used to rely on. The bound (with a factor 2) is
 // returned in e_out: it widens this test's limits by the in-plane motion it allows, the beam-grid window (lrt_beamgrid.cuh), and —
 // as the per-ray maximum — the margin with which the compositing passes skip and stop in the sorted bin (wf_margin()).
-#define LRT_ERR_FLOOR 2.5e-4f      // below this the fixed margin covers the error: no per-ray bookkeeping
-#define LRT_ERR_CAP 5e-2f          // a candidate whose depth is uncertain by more than this sends its ray to the exact per-ray path
+#define LRT_ERR_FLOOR 1e-3f        // at or below the fixed margin the bound changes nothing: no per-ray bookkeeping
+#define LRT_ERR_CAP 5e-2f          // the bound is clamped here (window padding, test limits); a candidate at the cap is tested in every round of its ray
 __device__ __forceinline__ bool quad_candidate(const SurfelRec* __restrict__ rec, int prim, const RaySetup& r, float& t_out, int& g_out, float& e_out)
 {
     const float4 a0 = ld_f4(&rec[prim].r0), a3 = ld_f4(&rec[prim].r3);
@@ -113,7 +113,7 @@ __device__ __forceinline__ bool quad_candidate(const SurfelRec* __restrict__ rec
     // a depth error e moves the hit point by e d: |du| <= e sum |Lu_k d_k|
     const float gu = fabsf(a1.x * r.dx) + fabsf(a1.y * r.dy) + fabsf(a1.z * r.dz), gv = fabsf(a2.x * r.dx) + fabsf(a2.y * r.dy) + fabsf(a2.z * r.dz);
     if (!(fabsf(u) <= lim + e * gu && fabsf(v) <= lim + e * gv)) return false;
-    t_out = fmaxf(t, 0.0f);
+    t_out = fmaxf(t, 1e-30f);                       // > 0: key t = 0 is reserved for wild candidates (wf_append)
     g_out = __float_as_int(a2.w);
     e_out = e;
     return t < LRT_TMAX;

@@ -35,6 +35,7 @@ struct WfBufs {
                                     // [12] rays whose hit list overflowed in the split passes, [13] candidate records in the sorted stream
     int* hit_count;                 // (R) hits in bin | WF_TAINT
     int* emax;                      // (R) float bits: largest depth-error bound among the ray's candidates (0 below LRT_ERR_FLOOR)
+    int* nwild;                     // (R) candidates whose bound hit the cap ("wild": depth numerically meaningless); their keys carry t = 0
     unsigned long long* bins;       // (R, hcap)
     int hcap;                       // bin capacity (<= WF_HCAP_MAX)
     int* fb_list;                   // (R) fallback ray ids
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) k_wf_setup(FwdArgs a, WfBufs w)
     ray_setup(rs, o, d, 0.0f);
     w.rs[r] = rs;
     w.hit_count[r] = 0;
-    w.emax[r] = 0;
+    w.emax[r] = 0; w.nwild[r] = 0;
     w.ray_ids[r] = r;
 }
 
@@ -126,12 +127,18 @@ __device__ __forceinline__ unsigned leafq_eval(const LeafQ* __restrict__ lq, con
     return m;
 }
 
-// a candidate joins its ray's bin; its depth-error bound joins the ray's maximum (or, beyond the cap, hands the ray to the exact path)
+// A candidate joins its ray's bin; its depth-error bound joins the ray's maximum. A bound at the cap (a surfel seen edge-on:
+// n.d ~ 0, the depth from the origin says nothing about the depth a re-based round will compute) makes the candidate WILD: its
+// key gets t = 0, so it sorts to the front of the bin, and every round of the ray tests the ray's wild candidates first, whatever
+// the window says, before it scans the sorted rest. (Giving such rays an infinite margin made a few hundred rays per frame re-scan
+// their whole bin every round — 0.14 ms of tail in pass A; handing them to the per-ray fallback cost 1.4 ms: rays sliding along
+// facades are common in a street scene.)
 __device__ __forceinline__ void wf_append(const WfBufs& w, int ray, float t, int g, float e)
 {
+    const bool wild = e >= LRT_ERR_CAP;
     const int pos = atomicAdd(w.hit_count + ray, 1) & (WF_TAINT - 1);
-    if (pos < w.hcap) w.bins[(size_t)ray * w.hcap + pos] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
-    if (e >= LRT_ERR_CAP) atomicOr(w.hit_count + ray, WF_TAINT);
+    if (pos < w.hcap) w.bins[(size_t)ray * w.hcap + pos] = ((unsigned long long)(wild ? 0u : __float_as_uint(t)) << 32) | (unsigned)g;
+    if (wild) atomicAdd(w.nwild + ray, 1);
     else if (e > LRT_ERR_FLOOR) atomicMax(w.emax + ray, __float_as_int(e));
 }
 
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
             continue;
         }
         const int n = hc;
-        const float em = __int_as_float(w.emax[r]);
+        const float em = w.nwild[r] > 0 ? __int_as_float(0x7f800000) : __int_as_float(w.emax[r]);      // wild candidates: these kernels scan the whole bin
         // ---- load + sort the bin (bitonic over the next power of two, in shared memory)
         int m = 32; while (m < n) m <<= 1;
         for (int i = lane; i < m; i += 32) keys[i] = i < n ? w.bins[(size_t)r * w.hcap + i] : LRT_KEY_EMPTY;
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE_MIN_BLOCKS) k_wf_composite(
         const int hc = w.hit_count[r];
         if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }
         const int n = hc;
-        const float em = __int_as_float(w.emax[r]);
+        const float em = w.nwild[r] > 0 ? __int_as_float(0x7f800000) : __int_as_float(w.emax[r]);      // wild candidates: these kernels scan the whole bin
         const unsigned long long* __restrict__ bin = w.bins + (size_t)r * w.hcap;       // sorted by (t from o, id)
         FwdRay q;
         fwd_ray_init(q, r, a);
@@ -603,7 +610,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite
         const int hc = w.hit_count[r];
         if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; continue; }
         const int n = hc;
-        const float em = __int_as_float(w.emax[r]);
+        const float em = w.nwild[r] > 0 ? __int_as_float(0x7f800000) : __int_as_float(w.emax[r]);      // wild candidates: these kernels scan the whole bin
         const unsigned long long* __restrict__ bin = w.bins + (size_t)r * w.hcap;       // sorted by (t from o, id)
         FwdRay q;
         fwd_ray_init(q, r, a);
