@@ -66,6 +66,7 @@ int lrt_refit(lrt_ctx* ctx, int P, const float* means, const float* scales, cons
  *   R rays; ray_o_stride = 3 (origins (R,3)) or 0 (one shared origin — the expanded stride-0 view
  *   LiDARSensor.get_range_rays returns, lidar_sensor.py:400); ray_d (R,3); bg (3) device.
  *   Gaussian arrays as given to lrt_build/lrt_refit (same values); shs (P,M,3); D = active degree.
+ *   shs may be NULL after lrt_set_sh_parts (rows read in place from the model's features_dc / features_rest).
  * Outputs (written entirely by the call):
  *   out (R,9)           channel map of config.h:19-24
  *   accum_w (P)         sum of blending weights per Gaussian (forward.cu:272)
@@ -171,6 +172,23 @@ typedef struct lrt_adam_tensor {
     int32_t step;
 } lrt_adam_tensor;
 int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, double beta1, double beta2, double eps, void* stream);
+
+/* ---- SH coefficients read, and differentiated, IN PLACE ----
+ * The reference concatenates cat(features_dc, features_rest) of every asset into one (P, M, 3) tensor per render call
+ * (gaussian_model.py:141-144, gaussian_renderer/__init__.py:105,131) and autograd splits the gradient back: 2 x 0.92 GB of copies per
+ * training step at 2.4 M Gaussians. After lrt_set_sh_parts, lrt_forward may be called with shs == NULL and lrt_backward with
+ * shs == NULL and dL_dshs == NULL: rows are then fetched from the parts (Gaussian g of the concatenation = row g - first_k of part k),
+ * and SH gradients are accumulated straight into d_features_dc / d_features_rest (zero-filled by lrt_backward; NULL = not wanted).
+ * parts: HOST array, copied by the call; the tensors must stay valid until the calls that use them have run. M as in lrt_forward.
+ * n_parts == 0 unbinds. 16-byte aligned features_rest / d_features_rest bases enable the vector paths. */
+typedef struct lrt_sh_part {
+    int32_t P; int32_t reserved;
+    const float* features_dc;     /* (P,1,3) */
+    const float* features_rest;   /* (P,M-1,3) */
+    float* d_features_dc;         /* lrt_backward: (P,1,3) or NULL */
+    float* d_features_rest;       /* lrt_backward: (P,M-1,3) or NULL */
+} lrt_sh_part;
+int lrt_set_sh_parts(lrt_ctx* ctx, int n_parts, const lrt_sh_part* parts, int M, void* stream);
 
 /* ---- densify / prune as row compaction (second half) ----
  * The reference restructures a GaussianModel one tensor at a time with torch indexing / torch.cat, re-allocating every parameter and

@@ -41,7 +41,7 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
     DevBuf* bufs[] = {&ctx->leafq, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->rec_g, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
                       &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb,
                       &ctx->wf_ids, &ctx->wf_keys, &ctx->wf_sort_tmp, &ctx->bw_ids, &ctx->bw_keys, &ctx->bw_sort_tmp,
-                      &ctx->bw_off, &ctx->bw_rec_a, &ctx->bw_rec_b, &ctx->dn_pos, &ctx->dn_tmp, &ctx->sp_cnt, &ctx->sp_rec, &ctx->sp_scan_tmp, &ctx->sp_hits, &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan,
+                      &ctx->bw_off, &ctx->bw_rec_a, &ctx->bw_rec_b, &ctx->dn_pos, &ctx->dn_tmp, &ctx->sh_tab, &ctx->sp_cnt, &ctx->sp_rec, &ctx->sp_scan_tmp, &ctx->sp_hits, &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan,
                       &ctx->ch_tmp, &ctx->ch_bounds, &ctx->ch_keys_a, &ctx->ch_keys_b, &ctx->ch_idx_a, &ctx->ch_idx_b,
                       &ctx->ch[0].pts, &ctx->ch[0].boxes, &ctx->ch[1].pts, &ctx->ch[1].boxes};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -138,6 +138,34 @@ int lrt_adam_step(lrt_ctx* ctx, int n_tensors, const lrt_adam_tensor* tensors, d
 {
     if (!ctx) return LRT_ERR_INVALID;
     return lrt_adam_step_impl(ctx, n_tensors, tensors, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+int lrt_set_sh_parts(lrt_ctx* ctx, int n_parts, const lrt_sh_part* parts, int M, void* stream)
+{
+    if (!ctx) return LRT_ERR_INVALID;
+    if (n_parts == 0) { ctx->sh_parts_n = 0; return LRT_OK; }
+    if (n_parts < 0 || n_parts > LRT_MAX_ASSETS || !parts || M < 1 || M > 16) { ctx->set_error("lrt_set_sh_parts: need 0..LRT_MAX_ASSETS parts and 1 <= M <= 16"); return LRT_ERR_INVALID; }
+    ShTab tab;
+    long long total = 0;
+    int vec = 1, gvec = 1;
+    for (int k = 0; k < n_parts; k++) {
+        const lrt_sh_part& p = parts[k];
+        if (p.P <= 0 || !p.features_dc || (M > 1 && !p.features_rest)) { ctx->set_error("lrt_set_sh_parts: part with P <= 0 or a null tensor"); return LRT_ERR_INVALID; }
+        tab.part[k].first = (int)total; tab.part[k].P = p.P; tab.part[k].dc = p.features_dc; tab.part[k].rest = p.features_rest;
+        tab.part[k].d_dc = p.d_features_dc; tab.part[k].d_rest = p.d_features_rest;
+        if (reinterpret_cast<uintptr_t>(p.features_rest) & 15) vec = 0;
+        if (p.d_features_rest && (reinterpret_cast<uintptr_t>(p.d_features_rest) & 15)) gvec = 0;
+        ctx->sh_parts[k] = p;
+        total += p.P;
+        if (total > 0x7fffffffLL / 64) { ctx->set_error("lrt_set_sh_parts: too many Gaussians"); return LRT_ERR_INVALID; }
+    }
+    tab.n = n_parts; tab.M = M;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LRT_ERR_CUDA;
+    cudaError_t e = ctx->reserve(ctx->sh_tab, sizeof(ShTab));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->sh_tab.p, &tab, sizeof(int) * 2 + sizeof(ShPartDev) * (size_t)n_parts, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) { ctx->set_error("lrt_set_sh_parts", e); return LRT_ERR_CUDA; }
+    ctx->sh_parts_n = n_parts; ctx->sh_parts_P = (int)total; ctx->sh_parts_M = M; ctx->sh_parts_vec = vec; ctx->sh_parts_grad_vec = gvec;
+    return LRT_OK;
 }
 
 int lrt_compact_rows(lrt_ctx* ctx, int n_rows, const uint8_t* keep, int n_tensors, const lrt_row_tensor* tensors, void* stream)

@@ -26,6 +26,8 @@ struct RayState {
 struct GradOut {
     float* d_means; float* d_shs; float* d_opac; float* d_scales; float* d_rots;
     int vec;                              // 128-bit / 64-bit vector reductions usable (alignment checked on the host)
+    const ShTab* sh_tab;                  // non-null: SH gradients go straight into the leaf gradients d_features_dc / d_features_rest
+    int sh_vec;                           // ... whose `rest` bases are 16-byte aligned (vector reductions on the aligned middle of a row)
 };
 
 // sm_90+ vector float reductions: one L2 operation for 4 (2) adjacent floats instead of 4 (2).
@@ -222,6 +224,22 @@ __device__ __forceinline__ void hit_scatter(int g, const float* o, const float* 
     atomicAdd(go.d_means + 3 * (size_t)g + 2, hv.dmu[2]);
     // computeColorFromSHBackward (:123-247): dL_dsh[j] = basis_j * dL_dcolour, channel 0 zero if clamped
     if (clamped0) dcol[0] = 0.0f;
+    if (go.sh_tab) {                                   // in-place leaf gradients (rare paths: scalar reductions)
+        int j;
+        const ShPartDev& p = sh_find(go.sh_tab, g, j);
+#pragma unroll
+        for (int jj = 0; jj < 16; jj++) {
+            if (jj < nb) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    float* dst = jj == 0 ? (p.d_dc ? p.d_dc + 3 * (size_t)j + ch : nullptr)
+                                         : (p.d_rest ? p.d_rest + 3 * (size_t)(go.sh_tab->M - 1) * j + 3 * (jj - 1) + ch : nullptr);
+                    if (dst) atomicAdd(dst, basis[jj] * dcol[ch]);
+                }
+            }
+        }
+        return;
+    }
     float* dsh = go.d_shs + (size_t)g * M * 3;
     if (go.vec && (M & 3) == 0) {
         // (j, ch) pairs are contiguous: 3 nb floats = groups of 4 (nb = 1 -> 3 floats: scalar tail)
@@ -267,7 +285,8 @@ __device__ __forceinline__ int hit_backward(int g, float dpt, const float* o, co
     if (FILTER && st.T * (1.0f - h.alpha) < LRT_T_MIN) return 2;
     const int nb = (D + 1) * (D + 1);
     float sh[48], c[3], basis[16]; bool clamped0;
-    load_sh_bw(shs, g, M, nb, sh);
+    if (go.sh_tab) load_sh_parts(go.sh_tab, g, nb, sh);
+    else load_sh_bw(shs, g, M, nb, sh);
     sh_colour<true>(D, dirn, sh, c, clamped0, basis);
     float w;
     const float dalpha = hit_state(st, h.alpha, c, h.s.n, dpt, bg, flags, w);
@@ -397,6 +416,7 @@ __device__ __forceinline__ float seg_sum(float v, unsigned same)
 
 __global__ void __launch_bounds__(256) k_bw_hits(BwArgs a, BwFlat f)
 {
+    extern __shared__ float s_row[];                     // in-place SH gradients only: 8 warps x 32 lanes x 48 floats
     const unsigned FULL = 0xffffffffu;
     const int n = f.goff[f.P];
     if (n > f.capacity) return;
@@ -453,8 +473,56 @@ __global__ void __launch_bounds__(256) k_bw_hits(BwArgs a, BwFlat f)
             }
         }
         // SH: dL_dsh[j][ch] = basis_j dL_dcolour[ch], four contiguous floats at a time
-        float* dsh = go.d_shs + (size_t)(g < 0 ? 0 : g) * a.M * 3;
         const int nf = 3 * nb;
+        if (go.sh_tab) {
+            // leaf gradients in place: a Gaussian's row is d_features_dc[j] (3 floats) + d_features_rest[j] (3 (M - 1) floats at a
+            // 4-byte aligned address). The segment heads park their reduced row in shared memory; then the WARP emits one head's row
+            // at a time: one lane per aligned 16-byte group of the rest part (red.v4), one lane per float in front of, behind it and
+            // of the dc part — at most 20 lane-reductions per row, against 12 for an aligned concatenated row.
+            float* srow = s_row + ((threadIdx.x >> 5) * 32 + lane) * 48;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                if (4 * i < nf) {                          // warp-uniform
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int idx = 4 * i + e;
+                        const float v = seg_sum(basis[idx / 3] * dcol[idx % 3], same);
+                        if (head) srow[idx] = v;
+                    }
+                }
+            }
+            __syncwarp(FULL);
+            unsigned hm = __ballot_sync(FULL, head);
+            const int rf = 3 * (go.sh_tab->M - 1), nrest = nf - 3;
+            while (hm) {
+                const int hl = __ffs(hm) - 1; hm &= hm - 1;
+                const int gh = __shfl_sync(FULL, g, hl);
+                int j;
+                const ShPartDev& p = sh_find(go.sh_tab, gh, j);
+                const float* sv = s_row + ((threadIdx.x >> 5) * 32 + hl) * 48;
+                const size_t f0 = (size_t)rf * j;
+                float* rest = p.d_rest ? p.d_rest + f0 : nullptr;
+                const int lead = go.sh_vec ? min((4 - (int)(f0 & 3)) & 3, nrest) : nrest;      // floats in front of the first aligned group
+                const int nv4 = go.sh_vec ? (nrest - lead) >> 2 : 0;
+                const int tail = nrest - lead - 4 * nv4;
+                if (lane < nv4) {
+                    if (rest) { const float* q = sv + 3 + lead + 4 * lane; red_add_v4(rest + lead + 4 * lane, q[0], q[1], q[2], q[3]); }
+                } else if (go.sh_vec) {
+                    int k = lane - nv4;                                                         // lead, then tail, then dc
+                    if (k < lead) { if (rest) atomicAdd(rest + k, sv[3 + k]); }
+                    else if ((k -= lead) < tail) { if (rest) atomicAdd(rest + lead + 4 * nv4 + k, sv[3 + lead + 4 * nv4 + k]); }
+                    else if ((k -= tail) < 3) { if (p.d_dc) atomicAdd(p.d_dc + 3 * (size_t)j + k, sv[k]); }
+                } else {
+                    for (int k = lane; k < nf; k += 32) {
+                        if (k < 3) { if (p.d_dc) atomicAdd(p.d_dc + 3 * (size_t)j + k, sv[k]); }
+                        else if (rest) atomicAdd(rest + (k - 3), sv[k]);
+                    }
+                }
+            }
+            __syncwarp(FULL);
+            continue;
+        }
+        float* dsh = go.d_shs + (size_t)(g < 0 ? 0 : g) * a.M * 3;
         const bool vec = go.vec && (a.M & 3) == 0;
 #pragma unroll
         for (int i = 0; i < 12; i++) {
@@ -514,11 +582,12 @@ __global__ void __launch_bounds__(128) k_backward_warp(BwArgs a)
                 const float u = s.Lu[0] * rr0 + s.Lu[1] * rr1 + s.Lu[2] * rr2;
                 const float v = s.Lv[0] * rr0 + s.Lv[1] * rr1 + s.Lv[2] * rr2;
                 alpha = fminf(LRT_ALPHA_MAX, s.op * expf(-0.5f * (u * u + v * v)));
-                if ((a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)) {
+                if (!a.go.sh_tab && (a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)) {
                     sh_colour_stream(a.D, dirn, a.shs + (size_t)g * a.M * 3, wc);
                 } else {
                     float sh[48]; bool cl;
-                    load_sh_bw(a.shs, g, a.M, (a.D + 1) * (a.D + 1), sh);
+                    if (a.go.sh_tab) load_sh_parts(a.go.sh_tab, g, (a.D + 1) * (a.D + 1), sh);
+                    else load_sh_bw(a.shs, g, a.M, (a.D + 1) * (a.D + 1), sh);
                     sh_colour<false>(a.D, dirn, sh, wc, cl, nullptr);
                 }
                 nrm[0] = s.n[0]; nrm[1] = s.n[1]; nrm[2] = s.n[2];
@@ -613,15 +682,29 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
                       float* dL_dmeans, float* dL_dshs, float* dL_dopac, float* dL_dscales,
                       float* dL_drots, int flags, cudaStream_t s)
 {
-    if (R < 0 || P <= 0 || !ray_o || !ray_d || !bg || !means || !scales || !rots || !opac || !shs || !fwd_out || !dL_dout ||
-        !dL_dmeans || !dL_dshs || !dL_dopac || !dL_dscales || !dL_drots) { ctx->set_error("lrt_backward: null argument"); return LRT_ERR_INVALID; }
+    const ShTab* sh_tab = nullptr;
+    if (!shs || !dL_dshs) {                              // SH rows and their gradients in place (lrt_set_sh_parts)
+        if (shs || dL_dshs) { ctx->set_error("lrt_backward: shs and dL_dshs must both be NULL to use the bound SH parts"); return LRT_ERR_INVALID; }
+        if (!ctx->sh_parts_n || ctx->sh_parts_P != P || ctx->sh_parts_M != M) { ctx->set_error("lrt_backward: shs is NULL and no matching SH parts are bound (lrt_set_sh_parts)"); return LRT_ERR_STATE; }
+        sh_tab = (const ShTab*)ctx->sh_tab.p;
+    }
+    if (R < 0 || P <= 0 || !ray_o || !ray_d || !bg || !means || !scales || !rots || !opac || !fwd_out || !dL_dout ||
+        !dL_dmeans || !dL_dopac || !dL_dscales || !dL_drots) { ctx->set_error("lrt_backward: null argument"); return LRT_ERR_INVALID; }
     if (ray_o_stride != 0 && ray_o_stride != 3) { ctx->set_error("lrt_backward: ray_o_stride must be 0 or 3"); return LRT_ERR_INVALID; }
     if (D < 0 || D > 3 || M < (D + 1) * (D + 1)) { ctx->set_error("lrt_backward: need 0 <= D <= 3 and M >= (D+1)^2"); return LRT_ERR_INVALID; }
     const bool have_lists = hit_gidx && hit_t && hit_cnt && cap > 0;
     if (!have_lists && (hit_gidx || hit_t)) { ctx->set_error("lrt_backward: hit_gidx, hit_t, hit_cnt and cap go together"); return LRT_ERR_INVALID; }
     LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dmeans, 0, sizeof(float) * (size_t)P * 3, s));
-    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dshs, 0, sizeof(float) * (size_t)P * M * 3, s));
+    if (sh_tab) {
+        for (int k = 0; k < ctx->sh_parts_n; k++) {
+            const lrt_sh_part& pt = ctx->sh_parts[k];
+            if (pt.d_features_dc) LRT_CUDA_TRY(ctx, cudaMemsetAsync(pt.d_features_dc, 0, sizeof(float) * 3 * (size_t)pt.P, s));
+            if (pt.d_features_rest && M > 1) LRT_CUDA_TRY(ctx, cudaMemsetAsync(pt.d_features_rest, 0, sizeof(float) * 3 * (size_t)(M - 1) * pt.P, s));
+        }
+    } else {
+        LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dshs, 0, sizeof(float) * (size_t)P * M * 3, s));
+    }
     LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dopac, 0, sizeof(float) * (size_t)P, s));
     LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dscales, 0, sizeof(float) * (size_t)P * 2, s));
     LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_drots, 0, sizeof(float) * (size_t)P * 4, s));
@@ -633,8 +716,9 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
     a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_aux = reinterpret_cast<const float4*>(hit_aux); a.hit_cnt = hit_cnt; a.cap = cap;
     a.order = nullptr; a.only_flag = nullptr;
     a.go.d_means = dL_dmeans; a.go.d_shs = dL_dshs; a.go.d_opac = dL_dopac; a.go.d_scales = dL_dscales; a.go.d_rots = dL_drots;
-    a.go.vec = ctx->opt_vector_atomics && (reinterpret_cast<uintptr_t>(dL_dshs) & 15) == 0 &&
+    a.go.vec = ctx->opt_vector_atomics && (sh_tab || (reinterpret_cast<uintptr_t>(dL_dshs) & 15) == 0) &&
                (reinterpret_cast<uintptr_t>(dL_drots) & 15) == 0 && (reinterpret_cast<uintptr_t>(dL_dscales) & 7) == 0;
+    a.go.sh_tab = sh_tab; a.go.sh_vec = sh_tab && ctx->opt_vector_atomics && ctx->sh_parts_grad_vec;
     const int TB = 128, GB = (R + TB - 1) / TB;
     const bool can_trace = ctx->built && ctx->P == P && ctx->scale_modifier == mod;
     if (have_lists) {
@@ -665,7 +749,9 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
             LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->bw_sort_tmp.p, tb, (const int*)gcnt, goff, P + 1, s));
             ctx->span_end(s);
             ctx->span_begin("k_bw_prefix", s); k_bw_prefix<<<GB, TB, 0, s>>>(a, f); ctx->span_end(s);
-            ctx->span_begin("k_bw_hits", s); k_bw_hits<<<ctx->num_sms * 8, 256, 0, s>>>(a, f); ctx->span_end(s);
+            ctx->span_begin("k_bw_hits", s);
+            k_bw_hits<<<ctx->num_sms * 8, 256, sh_tab ? sizeof(float) * 8 * 32 * 48 : 0, s>>>(a, f);
+            ctx->span_end(s);
             a.only_flag = legacy_flag;                // set on the device if the records did not fit (normally not)
             ctx->span_begin("k_backward_list", s); k_backward_list<<<GB, TB, 0, s>>>(a); ctx->span_end(s);
             ctx->launches += 6;

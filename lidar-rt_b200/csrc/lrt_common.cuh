@@ -136,6 +136,32 @@ __device__ __forceinline__ void sh_colour(int deg, const float* dirn, const floa
 
 __device__ __forceinline__ float ld_f(const float* p) { return __ldg(p); }
 
+// SH rows read (and differentiated) IN PLACE from the model's leaf tensors instead of a concatenated (P, M, 3) copy
+// (lrt_set_sh_parts): asset k owns the Gaussians [first, first + P) of the concatenation; row j of it is
+// cat(features_dc[j] (1,3), features_rest[j] (M-1,3)) — gaussian_model.py:141-144. Lives in device memory (ctx->sh_tab).
+struct ShPartDev { int first, P; const float* dc; const float* rest; float* d_dc; float* d_rest; };
+struct ShTab { int n, M; ShPartDev part[LRT_MAX_ASSETS]; };
+
+__device__ __forceinline__ const ShPartDev& sh_find(const ShTab* __restrict__ t, int g, int& j)
+{
+    int lo = 0, hi = t->n - 1;                           // last part whose first index is <= g
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (t->part[mid].first <= g) lo = mid; else hi = mid - 1; }
+    j = g - t->part[lo].first;
+    return t->part[lo];
+}
+
+// the first 3 nb floats of Gaussian g's concatenated row, gathered from the two leaf tensors (generic path: scalar loads)
+__device__ __forceinline__ void load_sh_parts(const ShTab* __restrict__ t, int g, int nb, float* sh)
+{
+    int j;
+    const ShPartDev& p = sh_find(t, g, j);
+    const float* dc = p.dc + 3 * (size_t)j;
+    const float* rest = p.rest + 3 * (size_t)(t->M - 1) * j;
+    sh[0] = ld_f(dc); sh[1] = ld_f(dc + 1); sh[2] = ld_f(dc + 2);
+#pragma unroll
+    for (int i = 3; i < 48; i++) if (i < nb * 3) sh[i] = ld_f(rest + (i - 3));
+}
+
 // SH basis only (same expressions as sh_colour); returns the number of active coefficients.
 __device__ __forceinline__ int sh_basis(int deg, const float* dirn, float* b)
 {

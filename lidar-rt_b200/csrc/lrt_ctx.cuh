@@ -33,6 +33,10 @@ struct lrt_ctx {
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
     DevBuf bw_off, bw_rec_a, bw_rec_b;   // hit-parallel backward (lrt_backward.cu)
     DevBuf dn_pos, dn_tmp;               // densify / prune row compaction (lrt_densify.cu)
+    // SH rows read / differentiated in place (lrt_set_sh_parts): host copy of the parts + the device table the kernels search
+    DevBuf sh_tab;
+    lrt_sh_part sh_parts[LRT_MAX_ASSETS];
+    int sh_parts_n = 0, sh_parts_P = 0, sh_parts_M = 0, sh_parts_vec = 0, sh_parts_grad_vec = 0;
     DevBuf sp_cnt, sp_rec, sp_scan_tmp, sp_hits;   // split forward passes (lrt_split.cuh): slice offsets, sorted record stream, internal hit lists
     DevBuf bg_ang, bg_cell_of, bg_cells, bg_sray, bg_wide, bg_plan;   // shared-origin beam grid (lrt_beamgrid.cuh)
     // chamfer distance (lrt_chamfer.cu): one Morton-sorted point hierarchy per cloud, rebuilt every call
@@ -108,7 +112,7 @@ struct lrt_ctx {
         return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
                bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
-               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + sp_cnt.cap + sp_rec.cap + sp_scan_tmp.cap + sp_hits.cap + dn_pos.cap + dn_tmp.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap + ch_keys_a.cap + ch_keys_b.cap + ch_idx_a.cap + ch_idx_b.cap;
+               bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + sp_cnt.cap + sp_rec.cap + sp_scan_tmp.cap + sp_hits.cap + dn_pos.cap + dn_tmp.cap + sh_tab.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap + ch_keys_a.cap + ch_keys_b.cap + ch_idx_a.cap + ch_idx_b.cap;
     }
     BvhView view() const
     {

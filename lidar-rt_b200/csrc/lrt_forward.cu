@@ -32,12 +32,23 @@ __device__ __forceinline__ void load_sh(const float* __restrict__ shs, int g, in
     }
 }
 
+struct FwdArgs;
+__device__ __forceinline__ void load_sh_any(const FwdArgs& a, int g, int nb, float* sh);
+
 struct FwdArgs {
     int R; const float* ray_o; int ray_o_stride; const float* ray_d; const float* bg; const float* shs; int D, M;
+    const ShTab* sh_tab;         // non-null: SH rows are read in place through the parts table (shs == nullptr)
     float* out; float* accum_w; int32_t* hit_gidx; float* hit_t; float4* hit_aux; int32_t* hit_cnt; int cap; int32_t* slot_cnt;
     int grid_w;                  // > 0: rays form a row-major (R / grid_w, grid_w) range image -> 4 x 8 warp tiles
     int* work_counter;           // persistent kernel: next work slot
 };
+
+__device__ __forceinline__ void load_sh_any(const FwdArgs& a, int g, int nb, float* sh)
+{
+    if (a.sh_tab) load_sh_parts(a.sh_tab, g, nb, sh);
+    else load_sh(a.shs, g, a.M, nb, sh);
+}
+__host__ __device__ __forceinline__ bool sh_rows_aligned(const FwdArgs& a) { return !a.sh_tab && (a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0); }
 
 // Per-ray compositing state (forward.cu:174-193).
 struct FwdRay {
@@ -91,11 +102,11 @@ __device__ __forceinline__ bool fwd_shade_round(FwdRay& q, const unsigned long l
         if (q.testT < LRT_T_MIN) { terminated = true; break; }                    // :253-257
         const float w = alpha * q.T;
         float c[3];
-        if ((a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)) {
+        if (sh_rows_aligned(a)) {
             sh_colour_stream(a.D, q.dirn, a.shs + (size_t)g * a.M * 3, c);        // same sums in the same order, no 48-float staging
         } else {
             float sh[48]; bool cl;
-            load_sh(a.shs, g, a.M, nb, sh);
+            load_sh_any(a, g, nb, sh);
             sh_colour<false>(a.D, q.dirn, sh, c, cl, nullptr);
         }
         q.C0 += w * c[0]; q.C1 += w * c[1]; q.C2 += w * c[2];
@@ -327,12 +338,12 @@ __device__ __forceinline__ void g8_shade_slot(unsigned long long key, bool valid
     if (o.alpha < 1.0f / 255.0f) return;
     o.flags |= G8_F_OK;
     float c[3];
-    if ((a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)) {
+    if (sh_rows_aligned(a)) {
         sh_colour_stream(a.D, q.dirn, a.shs + (size_t)g * a.M * 3, c);
     } else {
         const int nb = (a.D + 1) * (a.D + 1);
         float sh[48]; bool cl;
-        load_sh(a.shs, g, a.M, nb, sh);
+        load_sh_any(a, g, nb, sh);
         sh_colour<false>(a.D, q.dirn, sh, c, cl, nullptr);
     }
     o.c0 = c[0]; o.c1 = c[1]; o.c2 = c[2];
@@ -513,7 +524,12 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(accum_w, 0, sizeof(float) * (size_t)P, s));
         return LRT_OK;
     }
-    if (R < 0 || !ray_d || !ray_o || !bg || !shs || !out || !accum_w) { ctx->set_error("lrt_forward: null argument"); return LRT_ERR_INVALID; }
+    const ShTab* sh_tab = nullptr;
+    if (!shs) {                                                // SH rows in place (lrt_set_sh_parts)
+        if (!ctx->sh_parts_n || ctx->sh_parts_P != P || ctx->sh_parts_M != M) { ctx->set_error("lrt_forward: shs is NULL and no matching SH parts are bound (lrt_set_sh_parts)"); return LRT_ERR_STATE; }
+        sh_tab = (const ShTab*)ctx->sh_tab.p;
+    }
+    if (R < 0 || !ray_d || !ray_o || !bg || !out || !accum_w) { ctx->set_error("lrt_forward: null argument"); return LRT_ERR_INVALID; }
     if (ray_o_stride != 0 && ray_o_stride != 3) { ctx->set_error("lrt_forward: ray_o_stride must be 0 or 3"); return LRT_ERR_INVALID; }
     if (D < 0 || D > 3 || M < (D + 1) * (D + 1)) { ctx->set_error("lrt_forward: need 0 <= D <= 3 and M >= (D+1)^2"); return LRT_ERR_INVALID; }
     if ((hit_gidx == nullptr) != (hit_t == nullptr) || (hit_gidx && (cap <= 0 || !hit_cnt))) {
@@ -524,7 +540,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
     LRT_CUDA_TRY(ctx, cudaMemsetAsync(accum_w, 0, sizeof(float) * (size_t)P, s));
     if (R == 0) return LRT_OK;
     FwdArgs a;
-    a.R = R; a.ray_o = ray_o; a.ray_o_stride = ray_o_stride; a.ray_d = ray_d; a.bg = bg; a.shs = shs; a.D = D; a.M = M;
+    a.R = R; a.ray_o = ray_o; a.ray_o_stride = ray_o_stride; a.ray_d = ray_d; a.bg = bg; a.shs = shs; a.D = D; a.M = M; a.sh_tab = sh_tab;
     a.out = out; a.accum_w = accum_w; a.hit_gidx = hit_gidx; a.hit_t = hit_t; a.hit_aux = reinterpret_cast<float4*>(hit_aux); a.hit_cnt = hit_cnt; a.cap = cap; a.slot_cnt = slot_cnt;
     a.grid_w = (ctx->opt_ray_grid_w > 0 && R % ctx->opt_ray_grid_w == 0) ? ctx->opt_ray_grid_w : 0;
     a.work_counter = nullptr;
@@ -663,8 +679,9 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                 LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));
                 ctx->span_begin("k_sp_slots", s); k_sp_slots<<<(R + 127) / 128, 128, SP_SLOTS_SMEM, s>>>(a, w, sp); ctx->span_end(s);
                 ctx->span_begin("k_sp_colour", s);
-                if ((a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0)) k_sp_colour<true><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
-                else k_sp_colour<false><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
+                if (a.sh_tab && ctx->sh_parts_vec) k_sp_colour<2><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
+                else if (sh_rows_aligned(a)) k_sp_colour<1><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
+                else k_sp_colour<0><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
                 ctx->span_end(s);
                 ctx->span_begin("k_sp_fold", s); k_sp_fold<<<(R + 127) / 128, 128, 0, s>>>(a); ctx->span_end(s);
                 ctx->launches += 9;

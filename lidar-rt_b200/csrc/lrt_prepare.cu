@@ -247,7 +247,7 @@ int fill_table(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, PrepT
 int lrt_prepare_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, float* means, float* scales, float* rots,
                      float* opac, float* shs, cudaStream_t s)
 {
-    if (!means || !scales || !rots || !opac || !shs) { ctx->set_error("lrt_prepare: null output"); return LRT_ERR_INVALID; }
+    if (!means || !scales || !rots || !opac) { ctx->set_error("lrt_prepare: null output"); return LRT_ERR_INVALID; }      // shs == NULL: no concatenated copy (lrt_set_sh_parts)
     if ((reinterpret_cast<uintptr_t>(scales) & 7) || (reinterpret_cast<uintptr_t>(rots) & 15)) { ctx->set_error("lrt_prepare: scales must be 8-byte and rots 16-byte aligned"); return LRT_ERR_INVALID; }
     PrepTable t;
     const int rc = fill_table(ctx, n_assets, assets, M, t, "lrt_prepare");
@@ -255,7 +255,7 @@ int lrt_prepare_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M,
     LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->span_begin("k_prepare", s);
     k_prepare<<<(t.total + 255) / 256, 256, 0, s>>>(t, means, scales, rots, opac);
-    launch_prepare_sh<false>(t, shs, s);
+    if (shs) launch_prepare_sh<false>(t, shs, s);
     ctx->span_end(s);
     ctx->launches += 2;
     LRT_CUDA_TRY(ctx, cudaGetLastError());
@@ -265,7 +265,7 @@ int lrt_prepare_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M,
 int lrt_prepare_backward_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* assets, int M, const float* g_means, const float* g_scales,
                               const float* g_rots, const float* g_opac, const float* g_shs, cudaStream_t s)
 {
-    if (!g_means || !g_scales || !g_rots || !g_opac || !g_shs) { ctx->set_error("lrt_prepare_backward: null gradient input"); return LRT_ERR_INVALID; }
+    if (!g_means || !g_scales || !g_rots || !g_opac) { ctx->set_error("lrt_prepare_backward: null gradient input"); return LRT_ERR_INVALID; }      // g_shs == NULL: SH gradients were written in place
     if ((reinterpret_cast<uintptr_t>(g_scales) & 7) || (reinterpret_cast<uintptr_t>(g_rots) & 15)) { ctx->set_error("lrt_prepare_backward: dL_dscales must be 8-byte and dL_drots 16-byte aligned"); return LRT_ERR_INVALID; }
     PrepTable t;
     const int rc = fill_table(ctx, n_assets, assets, M, t, "lrt_prepare_backward");
@@ -278,7 +278,7 @@ int lrt_prepare_backward_impl(lrt_ctx* ctx, int n_assets, const lrt_asset* asset
     LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->span_begin("k_prepare_backward", s);
     k_prepare_backward<<<(t.total + 255) / 256, 256, 0, s>>>(t, g_means, g_scales, g_rots, g_opac);
-    launch_prepare_sh<true>(t, const_cast<float*>(g_shs), s);
+    if (g_shs) launch_prepare_sh<true>(t, const_cast<float*>(g_shs), s);
     ctx->span_end(s);
     ctx->launches += 2;
     LRT_CUDA_TRY(ctx, cudaGetLastError());

@@ -317,12 +317,30 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
     }
 }
 
+// colour from a row whose dc part sits in `dc` and whose rest part starts A floats into the 16-byte aligned window `wv`
+// (same sums, in the same order, as sh_colour_stream_b() over the concatenated row)
+template <int A>
+__device__ __forceinline__ void sp_colour_window(int nb, const float* b, const float* dc, const float* wv, float* c)
+{
+    const int nf = 3 * nb;
+    float r[3] = {b[0] * dc[0], b[0] * dc[1], b[0] * dc[2]};
+#pragma unroll
+    for (int idx = 3; idx < 48; idx++) {
+        if (idx < nf) { const int j = idx / 3, ch = idx % 3; r[ch] = r[ch] + b[j] * wv[A + idx - 3]; }
+    }
+    c[0] = r[0] + 0.5f; c[1] = r[1] + 0.5f; c[2] = r[2] + 0.5f;
+    if (c[0] < 0.0f) c[0] = -0.0f;     // see sh_colour
+}
+
 // Pass B: SH colour of every recorded hit (forward.cu:67-111, :261-266). Thread (x, y) owns ray x and its hits y, y + gridDim.y, ...
+// MODE 1: concatenated (P, M, 3) rows, 16-byte aligned: twelve 128-bit loads. MODE 2: rows read in place from features_dc /
+// features_rest (lrt_set_sh_parts): a `rest` row is 3 (M - 1) floats at a 4-byte aligned address, so the thread loads the twelve
+// 16-byte words that cover it and picks its coefficients at one of four compile-time offsets. MODE 0: anything else, scalar loads.
 #ifndef LRT_COLOUR_MIN_BLOCKS
 #define LRT_COLOUR_MIN_BLOCKS 4
 #endif
-template <bool SH_FAST>                                             // SH rows 16-byte aligned (M % 4 == 0): 128-bit loads
-__global__ void __launch_bounds__(256, LRT_COLOUR_MIN_BLOCKS) k_sp_colour(FwdArgs a)
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == 2 ? 2 : LRT_COLOUR_MIN_BLOCKS) k_sp_colour(FwdArgs a)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.R) return;
@@ -342,16 +360,44 @@ __global__ void __launch_bounds__(256, LRT_COLOUR_MIN_BLOCKS) k_sp_colour(FwdArg
         const int g = g_nx;
         if (k + (int)gridDim.y < cnt) {                            // the thread's next hit: its SH row starts moving towards L2 now
             g_nx = a.hit_gidx[at + (size_t)gridDim.y * a.R];
-            const char* row = reinterpret_cast<const char*>(a.shs + (size_t)g_nx * a.M * 3);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-            if (nb > 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+            if (MODE == 1) {
+                const char* row = reinterpret_cast<const char*>(a.shs + (size_t)g_nx * a.M * 3);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                if (nb > 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+            }
         }
         float c[3];
-        if (SH_FAST) {
+        bool done = false;
+        if (MODE == 1) {
             sh_colour_stream_b(nb, sb, a.shs + (size_t)g * a.M * 3, c);
-        } else {
+            done = true;
+        } else if (MODE == 2) {
+            int j;
+            const ShPartDev& p = sh_find(a.sh_tab, g, j);
+            if (j + 1 < p.P) {                                     // (the last row of a tensor: its window would read past the end)
+                const int rf = 3 * (a.sh_tab->M - 1);
+                const size_t f0 = (size_t)rf * j;
+                const int al = (int)(f0 & 3);
+                const float4* p4 = reinterpret_cast<const float4*>(p.rest + (f0 - al));
+                const float* dcp = p.dc + 3 * (size_t)j;
+                const float dc[3] = {ld_f(dcp), ld_f(dcp + 1), ld_f(dcp + 2)};
+                const int n4 = (al + 3 * nb - 3 + 3) >> 2;
+                float wv[48];
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    const float4 v = i < n4 ? ld_f4(p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    wv[4 * i] = v.x; wv[4 * i + 1] = v.y; wv[4 * i + 2] = v.z; wv[4 * i + 3] = v.w;
+                }
+                if (al == 0) sp_colour_window<0>(nb, sb, dc, wv, c);
+                else if (al == 1) sp_colour_window<1>(nb, sb, dc, wv, c);
+                else if (al == 2) sp_colour_window<2>(nb, sb, dc, wv, c);
+                else sp_colour_window<3>(nb, sb, dc, wv, c);
+                done = true;
+            }
+        }
+        if (!done) {
             float sh[48]; bool cl;
-            load_sh(a.shs, g, a.M, nb, sh);
+            load_sh_any(a, g, nb, sh);
             sh_colour<false>(a.D, dirn, sh, c, cl, nullptr);
         }
         float* ax = reinterpret_cast<float*>(a.hit_aux + at);

@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE_MIN_BLOCKS) k_wf_composite(
                 const int g = (int)(unsigned)(ck & 0xffffffffull);
                 float t; int g2;
                 if (!quad_hit(bvh.rec_g, g, rs, t, g2)) continue;
-                {   // a slot of this round: most slots composite, so start pulling its SH row (two 128 B lines at D = 3) into L2 now
+                if (a.shs) {   // a slot of this round: most slots composite, so start pulling its SH row (two 128 B lines at D = 3) into L2 now
                     const char* row = reinterpret_cast<const char*>(a.shs + (size_t)g * a.M * 3);
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
                     if (a.D >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite
     __shared__ float s_al[LRT_KBUF][128];                          // their blending opacities (0: cannot contribute)
     const int tx = threadIdx.x;
     const int S = w.order ? a.R : num_slots(a.R, a.grid_w);
-    const bool sh_fast = (a.M & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0);
+    const bool sh_fast = sh_rows_aligned(a);
     const SurfelRec* __restrict__ rec = bvh.rec_g;
     for (int s = blockIdx.x * blockDim.x + tx; s < S; s += gridDim.x * blockDim.x) {
         const int r = w.order ? w.order[s] : slot_to_ray(s, a.R, a.grid_w);
@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(128, LRT_COMPOSITE2_MIN_BLOCKS) k_wf_composite
                     sh_colour_stream_b(nb, sb, a.shs + (size_t)g * a.M * 3, c);
                 } else {
                     float sh[48]; bool cl;
-                    load_sh(a.shs, g, a.M, nb, sh);
+                    load_sh_any(a, g, nb, sh);
                     sh_colour<false>(a.D, q.dirn, sh, c, cl, nullptr);
                 }
                 q.C0 += wgt * c[0]; q.C1 += wgt * c[1]; q.C2 += wgt * c[2];

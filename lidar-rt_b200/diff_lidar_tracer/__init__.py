@@ -93,9 +93,19 @@ class _Tracer(torch.autograd.Function):
         s = tracer_settings
         means_d, scales_d, rots_d, opac_d, shs_d = (t.detach() for t in (means3D, scales, rotations, opacities, shs))
         gen = handle.ensure_built(means_d, scales_d, rots_d, opac_d, float(s.scale_modifier))
+        # SH handle of lidar_rt_b200.prepare.fused_prepare(sh_in_place=True): no concatenated coefficients exist; the library
+        # reads the model's features_dc / features_rest in place (lrt_set_sh_parts)
+        box = getattr(shs, "_lrt_sh", None)
+        ctx.sh_box = box
+        sh_M = 16
+        if box is not None:
+            if box.P != means3D.shape[0]:
+                raise ValueError("SH handle and means3D disagree on the number of Gaussians")
+            handle.ctx.set_sh_parts(box.parts)
+            shs_d, sh_M = None, box.M
         res = handle.ctx.forward(ray_o.detach(), ray_d.detach(), s.bg, means_d, scales_d, rots_d, opac_d, shs_d,
                                  int(s.sh_degree), float(s.scale_modifier), record_hits=handle.record_hits,
-                                 cap=handle.hit_cap)
+                                 cap=handle.hit_cap, sh_M=sh_M)
         out = res["out"]
         accum = res["accum_w"]
         ctx.handle = handle
@@ -125,9 +135,15 @@ class _Tracer(torch.autograd.Function):
             nctx.build(means3D.detach(), scales.detach(), rotations.detach(), opacities.detach(),
                        float(s.scale_modifier))
             handle.pending = "build"          # whatever was current is gone
+        box = ctx.sh_box
+        if box is not None:              # SH gradients straight into the leaf gradients; the handle's own gradient carries nothing
+            box.grads = box.gradient_buffers(means3D.device)
+            nctx.set_sh_parts(box.parts, box.grads)
         g = nctx.backward(ray_o, ray_d, s.bg, means3D.detach(), scales.detach(), rotations.detach(),
-                          opacities.detach(), shs.detach(), int(s.sh_degree), out, grad_out.contiguous(),
-                          hits=hits, scale_modifier=float(s.scale_modifier), flags=handle.bwd_flags)
+                          opacities.detach(), None if box is not None else shs.detach(), int(s.sh_degree), out, grad_out.contiguous(),
+                          hits=hits, scale_modifier=float(s.scale_modifier), flags=handle.bwd_flags, sh_M=box.M if box is not None else 16)
+        if box is not None:
+            g["shs"] = torch.zeros(1, dtype=torch.float32, device=means3D.device).expand(shs.shape)
         grad_opac = g["opac"].reshape(opacities.shape)
         zeros3 = torch.zeros_like(means3D)      # reference returns zero grads for the unused slots (:322-329)
         return (None, None, None, None, None,

@@ -125,7 +125,10 @@ def raytracing(frame, gaussian_assets, sensor, background, args, scaling_modifie
     if _arg(args, "pipe", "fused_prepare", True):
         # one native call instead of the accessor loop + torch.cat below (same values, same gradients); applies when
         # the assets expose the GaussianModel leaves
-        fused = fused_prepare(gaussian_assets, frame, dynamic, decomp, tracer_2dgs.optix_context.ctx)
+        # SH coefficients are not concatenated either: the tracer reads features_dc / features_rest in place and writes their
+        # gradients in place (2 x 0.92 GB of copies per training step at 2.4 M Gaussians otherwise); pipe.sh_in_place=False restores the copy
+        fused = fused_prepare(gaussian_assets, frame, dynamic, decomp, tracer_2dgs.optix_context.ctx,
+                              sh_in_place=bool(_arg(args, "pipe", "sh_in_place", True)))
     if fused is not None:
         means3D, opacity, scales, rotations, shs = fused
     else:

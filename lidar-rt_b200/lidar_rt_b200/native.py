@@ -48,6 +48,12 @@ class LrtAdamTensor(ctypes.Structure):
                 ("n", c_int64), ("lr", c_float), ("step", c_int32)]
 
 
+class LrtShPart(ctypes.Structure):
+    """lrt_sh_part of include/lidar_rt_b200.h: one asset's SH leaves (and, for the backward, their gradient buffers)."""
+    _fields_ = [("P", c_int32), ("reserved", c_int32), ("features_dc", c_void_p), ("features_rest", c_void_p),
+                ("d_features_dc", c_void_p), ("d_features_rest", c_void_p)]
+
+
 class LrtRowTensor(ctypes.Structure):
     """lrt_row_tensor of include/lidar_rt_b200.h: one per-Gaussian tensor moved by lrt_compact_rows / lrt_densify_rows."""
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_floats", c_int32), ("kind", c_int32)]
@@ -91,6 +97,8 @@ def load_library() -> ctypes.CDLL:
     lib.lrt_chamfer_forward.restype = c_int; lib.lrt_chamfer_backward.restype = c_int
     lib.lrt_adam_step.argtypes = [c_void_p, c_int, POINTER(LrtAdamTensor), c_double, c_double, c_double, c_void_p]
     lib.lrt_adam_step.restype = c_int
+    lib.lrt_set_sh_parts.argtypes = [c_void_p, c_int, POINTER(LrtShPart), c_int, c_void_p]
+    lib.lrt_set_sh_parts.restype = c_int
     lib.lrt_compact_rows.argtypes = [c_void_p, c_int, c_void_p, c_int, POINTER(LrtRowTensor), c_void_p]
     lib.lrt_densify_rows.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, fp, fp, c_int, POINTER(LrtRowTensor), c_void_p]
     lib.lrt_compact_rows.restype = c_int; lib.lrt_densify_rows.restype = c_int
@@ -250,21 +258,23 @@ class Context:
                         setattr(e, "d_" + name, t.data_ptr())
         return tab, n, M
 
-    def prepare(self, assets):
-        """lrt_prepare: -> (means (P,3), scales (P,2), rots (P,4), opac (P,1), shs (P,M,3)) for the concatenated assets."""
+    def prepare(self, assets, with_shs: bool = True):
+        """lrt_prepare: -> (means (P,3), scales (P,2), rots (P,4), opac (P,1), shs (P,M,3)) for the concatenated assets.
+        with_shs=False skips the concatenated SH copy (shs is None: the tracer reads the leaves in place, set_sh_parts)."""
         tab, n, M = self._asset_table(assets)
         P = sum(int(tab[k].P) for k in range(n))
         dev = self.device
         with torch.cuda.device(dev):
             means = torch.empty((P, 3), dtype=torch.float32, device=dev); scales = torch.empty((P, 2), dtype=torch.float32, device=dev)
             rots = torch.empty((P, 4), dtype=torch.float32, device=dev); opac = torch.empty((P, 1), dtype=torch.float32, device=dev)
-            shs = torch.empty((P, M, 3), dtype=torch.float32, device=dev)
+            shs = torch.empty((P, M, 3), dtype=torch.float32, device=dev) if with_shs else None
             self._check(self.lib.lrt_prepare(self._h, n, tab, M, _ptr(means), _ptr(scales), _ptr(rots), _ptr(opac), _ptr(shs), _stream(dev)))
         return means, scales, rots, opac, shs
 
     def prepare_backward(self, assets, g_means, g_scales, g_rots, g_opac, g_shs, want=None):
-        """lrt_prepare_backward: leaf gradients, one dict per asset (keys like the leaves)."""
-        names = ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest")
+        """lrt_prepare_backward: leaf gradients, one dict per asset (keys like the leaves). g_shs=None: the SH leaf gradients were
+        written in place by the tracer's backward (they are not produced here)."""
+        names = ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest") if g_shs is not None else ("xyz", "scaling", "rotation", "opacity")
         dev = self.device
         with torch.cuda.device(dev):
             # one allocation per leaf kind, carved into per-asset views (6 allocations instead of 6 per asset)
@@ -278,7 +288,7 @@ class Context:
                 for k, part in zip(ks, flat.split(sizes)):
                     grads[k][nm] = part.view(assets[k][nm].shape)
             tab, n, M = self._asset_table(assets, grads)
-            args = [_f32(g, nm) for g, nm in ((g_means, "dL_dmeans"), (g_scales, "dL_dscales"), (g_rots, "dL_drots"), (g_opac, "dL_dopac"), (g_shs, "dL_dshs"))]
+            args = [None if g is None else _f32(g, nm) for g, nm in ((g_means, "dL_dmeans"), (g_scales, "dL_dscales"), (g_rots, "dL_drots"), (g_opac, "dL_dopac"), (g_shs, "dL_dshs"))]
             self._check(self.lib.lrt_prepare_backward(self._h, n, tab, M, *(_ptr(t) for t in args), _stream(dev)))
         return grads
 
@@ -436,6 +446,39 @@ class Context:
                                                       _ptr(idx2.contiguous()), _ptr(ga), _ptr(gc), _stream(dev)))
         return ga, gc
 
+    # ---- SH rows in place
+    def set_sh_parts(self, parts, grads=None):
+        """lrt_set_sh_parts. parts: list of (features_dc (P,1,3), features_rest (P,M-1,3)) float32 CUDA contiguous tensors, in
+        concatenation order; grads: matching list of (d_features_dc, d_features_rest) tensors (or None entries) for lrt_backward.
+        Returns (P_total, M). An empty list unbinds."""
+        n = len(parts)
+        tab = (LrtShPart * max(n, 1))()
+        total, M = 0, None
+        for k, (dc, rest) in enumerate(parts):
+            for t, nm in ((dc, "features_dc"), (rest, "features_rest")):
+                if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                    raise LrtError(f"SH part {k}: {nm} must be a contiguous float32 CUDA tensor on {self.device}")
+            P = dc.shape[0]
+            if tuple(dc.shape) != (P, 1, 3) or rest.dim() != 3 or rest.shape[0] != P or rest.shape[2] != 3:
+                raise LrtError(f"SH part {k}: need features_dc (P,1,3) and features_rest (P,M-1,3)")
+            m_k = 1 + rest.shape[1]
+            if M is None:
+                M = m_k
+            elif M != m_k:
+                raise LrtError("SH parts disagree on the number of coefficients")
+            tab[k].P = P; tab[k].features_dc = dc.data_ptr(); tab[k].features_rest = rest.data_ptr()
+            if grads is not None:
+                gdc, grest = grads[k]
+                for t, ref in ((gdc, dc), (grest, rest)):
+                    if t is not None and (not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != ref.numel()):
+                        raise LrtError(f"SH part {k}: gradient buffers must be contiguous float32 CUDA tensors shaped like the leaves")
+                tab[k].d_features_dc = None if gdc is None else gdc.data_ptr()
+                tab[k].d_features_rest = None if grest is None else grest.data_ptr()
+            total += P
+        with torch.cuda.device(self.device):
+            self._check(self.lib.lrt_set_sh_parts(self._h, n, tab, int(M or 1), _stream(self.device)))
+        return total, M
+
     # ---- one frame of the hot path as a CUDA graph
     def graphed_step(self, ray_o, ray_d, dL_dout, bg, means, scales, rots, opac, shs, sh_degree: int, scale_modifier: float = 1.0,
                      refit: bool = False, backward: bool = True, cap: int = DEFAULT_HIT_CAP):
@@ -464,13 +507,16 @@ class Context:
         return R, lead, ray_o.contiguous(), 3, ray_d
 
     def forward(self, ray_o, ray_d, bg, means, scales, rots, opac, shs, sh_degree: int, scale_modifier: float = 1.0,
-                record_hits: bool = True, cap: int = DEFAULT_HIT_CAP, want_slots: bool = False, record_aux: bool = True):
+                record_hits: bool = True, cap: int = DEFAULT_HIT_CAP, want_slots: bool = False, record_aux: bool = True, sh_M: int = 16):
         P, means, scales, rots, opac = self._gauss(means, scales, rots, opac)
         R, lead, o, stride, d = self._rays(ray_o, ray_d)
-        shs = _f32(shs, "shs", (3,), self.device)
-        if shs.dim() != 3 or shs.shape[0] != P:
-            raise LrtError("shs must have dimensions (num_points, M, 3)")
-        M = shs.shape[1]
+        if shs is None:                  # rows read in place: set_sh_parts() was called for these Gaussians
+            M = int(sh_M)
+        else:
+            shs = _f32(shs, "shs", (3,), self.device)
+            if shs.dim() != 3 or shs.shape[0] != P:
+                raise LrtError("shs must have dimensions (num_points, M, 3)")
+            M = shs.shape[1]
         bg = _f32(bg, "bg", None, self.device).reshape(-1)
         dev = self.device
         self.set_option(OPT_RAY_GRID_WIDTH, lead[-1] if len(lead) >= 2 else 0)     # (H, W, 3) range image -> 4 x 8 warp tiles
@@ -493,10 +539,14 @@ class Context:
         return dict(out=out, accum_w=accum, hit_gidx=hit_g, hit_t=hit_t, hit_aux=hit_a, hit_cnt=hit_c, slot_cnt=slots, cap=cap)
 
     def backward(self, ray_o, ray_d, bg, means, scales, rots, opac, shs, sh_degree: int, fwd_out, dL_dout,
-                 hits: dict | None = None, scale_modifier: float = 1.0, flags: int = 0):
+                 hits: dict | None = None, scale_modifier: float = 1.0, flags: int = 0, sh_M: int = 16):
+        """shs=None: SH rows and their gradients in place (set_sh_parts with gradient buffers first); the returned dict then has no "shs"."""
         P, means, scales, rots, opac = self._gauss(means, scales, rots, opac)
         R, lead, o, stride, d = self._rays(ray_o, ray_d)
-        shs = _f32(shs, "shs", (3,), self.device); M = shs.shape[1]
+        if shs is None:
+            M = int(sh_M)
+        else:
+            shs = _f32(shs, "shs", (3,), self.device); M = shs.shape[1]
         bg = _f32(bg, "bg", None, self.device).reshape(-1)
         fwd_out = _f32(fwd_out, "out_attr_float32", (NUM_CHANNELS,), self.device); dL = _f32(dL_dout, "dL_dout", (NUM_CHANNELS,), self.device)
         if fwd_out.numel() != R * NUM_CHANNELS or dL.numel() != R * NUM_CHANNELS:
@@ -505,7 +555,7 @@ class Context:
         self.set_option(OPT_RAY_GRID_WIDTH, lead[-1] if len(lead) >= 2 else 0)
         with torch.cuda.device(dev):
             g_means = torch.empty((P, 3), dtype=torch.float32, device=dev)
-            g_shs = torch.empty((P, M, 3), dtype=torch.float32, device=dev)
+            g_shs = torch.empty((P, M, 3), dtype=torch.float32, device=dev) if shs is not None else None
             g_opac = torch.empty((P, 1), dtype=torch.float32, device=dev)
             g_scales = torch.empty((P, 2), dtype=torch.float32, device=dev)
             g_rots = torch.empty((P, 4), dtype=torch.float32, device=dev)
@@ -518,7 +568,10 @@ class Context:
                                               _ptr(fwd_out), _ptr(dL), _ptr(hg), _ptr(ht), _ptr(ha), _ptr(hc), cap,
                                               _ptr(g_means), _ptr(g_shs), _ptr(g_opac), _ptr(g_scales), _ptr(g_rots),
                                               int(flags), _stream(dev)))
-        return dict(means=g_means, shs=g_shs, opac=g_opac, scales=g_scales, rots=g_rots)
+        res = dict(means=g_means, opac=g_opac, scales=g_scales, rots=g_rots)
+        if g_shs is not None:
+            res["shs"] = g_shs
+        return res
 
 
 class GraphedStep:

@@ -29,34 +29,75 @@ def _pose(pc, frame):
     return None
 
 
+class ShInPlace:
+    """What travels with the SH handle tensor when the coefficients are NOT concatenated (fused_prepare(sh_in_place=True)): the
+    leaves the tracer reads in place (lrt_set_sh_parts) and, after the tracer's backward, the leaf gradients it wrote in place."""
+
+    def __init__(self, parts, want):
+        self.parts = parts            # [(features_dc, features_rest)] detached, concatenation order
+        self.want = want              # [(bool, bool)]: which leaf gradients are needed
+        self.grads = None             # [(d_features_dc | None, d_features_rest | None)], set by _Tracer.backward
+        self.M = 1 + parts[0][1].shape[1]
+        self.P = sum(dc.shape[0] for dc, _ in parts)
+
+    def gradient_buffers(self, device):
+        """One allocation per leaf kind; every asset's `rest` block starts on a 16-byte boundary (vector reductions)."""
+        n_dc = sum(dc.numel() for dc, _ in self.parts)
+        offs, n_rest = [], 0
+        for _, rest in self.parts:
+            offs.append(n_rest)
+            n_rest += (rest.numel() + 3) & ~3
+        f_dc = torch.empty(n_dc, dtype=torch.float32, device=device); f_rest = torch.empty(n_rest, dtype=torch.float32, device=device)
+        out, o = [], 0
+        for k, (dc, rest) in enumerate(self.parts):
+            gdc = f_dc[o:o + dc.numel()].view(dc.shape) if self.want[k][0] else None
+            grest = f_rest[offs[k]:offs[k] + rest.numel()].view(rest.shape) if self.want[k][1] else None
+            o += dc.numel()
+            out.append((gdc, grest))
+        return out
+
+
 class _FusedPrepare(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, nctx, specs, *leaves):
+    def forward(ctx, nctx, specs, box, *leaves):
         assets = []
         for k, sp in enumerate(specs):
             a = {nm: leaves[6 * k + i].detach() for i, nm in enumerate(_NAMES)}
             a.update(sp)
             assets.append(a)
-        out = nctx.prepare(assets)
-        ctx.nctx, ctx.assets = nctx, assets
-        ctx.want = [{nm: ctx.needs_input_grad[2 + 6 * k + i] for i, nm in enumerate(_NAMES)} for k in range(len(specs))]
-        return out
+        means, scales, rots, opac, shs = nctx.prepare(assets, with_shs=box is None)
+        ctx.nctx, ctx.assets, ctx.box = nctx, assets, box
+        ctx.want = [{nm: ctx.needs_input_grad[3 + 6 * k + i] for i, nm in enumerate(_NAMES)} for k in range(len(specs))]
+        if box is not None:
+            # the SH handle: shaped like the concatenated tensor, backed by ONE float (stride 0). It is only ever handed to the
+            # tracer, which reads the leaves through `box` instead.
+            box.want = [(w["features_dc"], w["features_rest"]) for w in ctx.want]
+            shs = torch.zeros(1, dtype=torch.float32, device=means.device).expand(means.shape[0], box.M, 3)
+        return means, scales, rots, opac, shs
 
     @staticmethod
     def backward(ctx, g_means, g_scales, g_rots, g_opac, g_shs):
         z = lambda g, ref_shape: torch.zeros(ref_shape, device=ctx.nctx.device) if g is None else g.contiguous()
         P = sum(a["xyz"].shape[0] for a in ctx.assets)
         M = 1 + ctx.assets[0]["features_rest"].shape[1]
+        box = ctx.box
         grads = ctx.nctx.prepare_backward(ctx.assets, z(g_means, (P, 3)), z(g_scales, (P, 2)), z(g_rots, (P, 4)), z(g_opac, (P, 1)),
-                                          z(g_shs, (P, M, 3)), want=ctx.want)
+                                          None if box is not None else z(g_shs, (P, M, 3)), want=ctx.want)
+        if box is not None:            # the tracer's backward wrote the SH leaf gradients in place (or never ran: no gradient)
+            for k, g in enumerate(grads):
+                gdc, grest = box.grads[k] if box.grads is not None else (None, None)
+                g["features_dc"], g["features_rest"] = gdc, grest
+            box.grads = None
         flat = []
         for g in grads:
             flat += [g[nm] for nm in _NAMES]
-        return (None, None, *flat)
+        return (None, None, None, *flat)
 
 
-def fused_prepare(gaussian_assets, frame, dynamic: bool, decomp, nctx: native.Context):
-    """-> (means3D, opacity, scales, rotations, shs) or None if the fused path does not apply."""
+def fused_prepare(gaussian_assets, frame, dynamic: bool, decomp, nctx: native.Context, sh_in_place: bool = False):
+    """-> (means3D, opacity, scales, rotations, shs) or None if the fused path does not apply.
+    sh_in_place=True: `shs` is only a HANDLE for diff_lidar_tracer.Tracer (attribute `_lrt_sh`): no concatenated copy of the SH
+    coefficients is made, the tracer reads features_dc / features_rest in place and its backward writes their gradients in place."""
     if not gaussian_assets or len(gaussian_assets) > native.MAX_ASSETS:
         return None
     specs, leaves = [], []
@@ -88,5 +129,10 @@ def fused_prepare(gaussian_assets, frame, dynamic: bool, decomp, nctx: native.Co
             return None           # an actor without a pose at this frame: the reference yields a zero quaternion; keep its path
         specs.append(sp)
         leaves += ts
-    means, scales, rots, opac, shs = _FusedPrepare.apply(nctx, specs, *leaves)
+    box = None
+    if sh_in_place:
+        box = ShInPlace([(leaves[6 * k + 4].detach(), leaves[6 * k + 5].detach()) for k in range(len(specs))], None)
+    means, scales, rots, opac, shs = _FusedPrepare.apply(nctx, specs, box, *leaves)
+    if box is not None:
+        shs._lrt_sh = box
     return means, opac, scales, rots, shs

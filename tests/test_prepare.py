@@ -90,6 +90,41 @@ def test_raytracing_with_and_without_fused_prepare():
             grad_close(x, y, 2e-3, f"asset {k}")
 
 
+@pytest.mark.parametrize("D", [3, 1, 0])
+def test_sh_in_place_equals_concatenated_copy(D):
+    """raytracing() with the SH coefficients read (and differentiated) in place from features_dc / features_rest
+    (lrt_set_sh_parts; pipe.sh_in_place, default) against the same call over the concatenated (P, M, 3) copy: the rendered
+    buffers must be bit-identical, the leaf gradients equal up to the order of the float reductions."""
+    import lib.gaussian_renderer as gr
+    assets = _assets(n_actors=3, per_actor=1500, P_bg=40001, seed=13)         # odd sizes: every alignment of the 180-byte rest rows occurs
+    for a in assets:
+        a.active_sh_degree = D
+    o, d = syn.ray_patch(24, 128)
+    H, W = d.shape[:2]
+    centre = torch.tensor(o[0], device="cuda")
+    rays = (centre[None, None].expand(H, W, 3), torch.as_tensor(d, device="cuda"), centre)
+    bg = torch.tensor([0.0, 0.0, 1.0], device="cuda")
+    w = torch.randn(H, W, 3, device="cuda")
+    res = {}
+    for inplace in (False, True):
+        for a in assets:
+            for p in a.parameters():
+                p.grad = None
+        args = types.SimpleNamespace(dynamic=True, pipe=types.SimpleNamespace(fused_prepare=True, sh_in_place=inplace, compute_cov3D_python=False, convert_SHs_python=False),
+                                     opt=types.SimpleNamespace(use_rayhit=True))
+        pkg = gr.raytracing(2, assets, rays, bg, args)
+        ((pkg["depth"] * w[..., 0:1]).sum() + (pkg["intensity"] * w[..., 1:2]).sum() + (pkg["raydrop"] * w[..., 2:3]).sum()).backward()
+        res[inplace] = ({k: pkg[k].detach().cpu().numpy() for k in ("depth", "intensity", "raydrop")}, _leaf_grads(assets))
+    for k in ("depth", "intensity", "raydrop"):
+        assert np.array_equal(res[True][0][k], res[False][0][k]), k
+    names = ("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest")
+    for k in range(len(assets)):
+        for nm, x, y in zip(names, res[True][1][k], res[False][1][k]):
+            assert x.shape == y.shape
+            grad_close(x, y, 1e-5, f"asset {k} d_{nm}")
+    assert np.abs(res[True][1][0][5]).max() > 0 or D == 0
+
+
 def test_prepare_rejects_bad_input():
     from lidar_rt_b200 import native
     ctx = native.Context()
