@@ -414,9 +414,10 @@ __device__ __forceinline__ float seg_sum(float v, unsigned same)
     return v;
 }
 
+#define BW_SROW 49
 __global__ void __launch_bounds__(256) k_bw_hits(BwArgs a, BwFlat f)
 {
-    extern __shared__ float s_row[];                     // in-place SH gradients only: 8 warps x 32 lanes x 48 floats
+    extern __shared__ float s_row[];                     // in-place SH gradients only: 8 warps x 32 lanes x BW_SROW floats
     const unsigned FULL = 0xffffffffu;
     const int n = f.goff[f.P];
     if (n > f.capacity) return;
@@ -476,10 +477,11 @@ __global__ void __launch_bounds__(256) k_bw_hits(BwArgs a, BwFlat f)
         const int nf = 3 * nb;
         if (go.sh_tab) {
             // leaf gradients in place: a Gaussian's row is d_features_dc[j] (3 floats) + d_features_rest[j] (3 (M - 1) floats at a
-            // 4-byte aligned address). The segment heads park their reduced row in shared memory; then the WARP emits one head's row
-            // at a time: one lane per aligned 16-byte group of the rest part (red.v4), one lane per float in front of, behind it and
-            // of the dc part — at most 20 lane-reductions per row, against 12 for an aligned concatenated row.
-            float* srow = s_row + ((threadIdx.x >> 5) * 32 + lane) * 48;
+            // 4-byte aligned address). The segment heads park their reduced row in shared memory (the 16-byte groups of the target
+            // do not line up with the groups the reduction produces), then emit it: red.v4 over the aligned middle of the rest
+            // part, scalar reductions for the up to three floats in front of and behind it and for the dc part — at most 20
+            // reductions per row against 12 for an aligned concatenated row.
+            float* srow = s_row + ((threadIdx.x >> 5) * 32 + lane) * BW_SROW;      // odd stride: the lanes' rows start in different banks
 #pragma unroll
             for (int i = 0; i < 12; i++) {
                 if (4 * i < nf) {                          // warp-uniform
@@ -492,31 +494,30 @@ __global__ void __launch_bounds__(256) k_bw_hits(BwArgs a, BwFlat f)
                 }
             }
             __syncwarp(FULL);
-            unsigned hm = __ballot_sync(FULL, head);
-            const int rf = 3 * (go.sh_tab->M - 1), nrest = nf - 3;
-            while (hm) {
-                const int hl = __ffs(hm) - 1; hm &= hm - 1;
-                const int gh = __shfl_sync(FULL, g, hl);
+            if (head) {                                    // every head emits its own row; the alignment only decides where the 16-byte groups start
+                const int rf = 3 * (go.sh_tab->M - 1), nrest = nf - 3;
                 int j;
-                const ShPartDev& p = sh_find(go.sh_tab, gh, j);
-                const float* sv = s_row + ((threadIdx.x >> 5) * 32 + hl) * 48;
+                const ShPartDev& p = sh_find(go.sh_tab, g, j);
                 const size_t f0 = (size_t)rf * j;
                 float* rest = p.d_rest ? p.d_rest + f0 : nullptr;
                 const int lead = go.sh_vec ? min((4 - (int)(f0 & 3)) & 3, nrest) : nrest;      // floats in front of the first aligned group
                 const int nv4 = go.sh_vec ? (nrest - lead) >> 2 : 0;
                 const int tail = nrest - lead - 4 * nv4;
-                if (lane < nv4) {
-                    if (rest) { const float* q = sv + 3 + lead + 4 * lane; red_add_v4(rest + lead + 4 * lane, q[0], q[1], q[2], q[3]); }
-                } else if (go.sh_vec) {
-                    int k = lane - nv4;                                                         // lead, then tail, then dc
-                    if (k < lead) { if (rest) atomicAdd(rest + k, sv[3 + k]); }
-                    else if ((k -= lead) < tail) { if (rest) atomicAdd(rest + lead + 4 * nv4 + k, sv[3 + lead + 4 * nv4 + k]); }
-                    else if ((k -= tail) < 3) { if (p.d_dc) atomicAdd(p.d_dc + 3 * (size_t)j + k, sv[k]); }
-                } else {
-                    for (int k = lane; k < nf; k += 32) {
-                        if (k < 3) { if (p.d_dc) atomicAdd(p.d_dc + 3 * (size_t)j + k, sv[k]); }
-                        else if (rest) atomicAdd(rest + (k - 3), sv[k]);
-                    }
+                // straight-line, predicated: heads of different alignment stay in step (loops with alignment-dependent trip counts
+                // made every alignment class run the emission on its own, 2-3 lanes at a time: ncu, profiles/r2_o_*)
+                if (p.d_dc) {
+                    float* dc = p.d_dc + 3 * (size_t)j;
+                    atomicAdd(dc, srow[0]); atomicAdd(dc + 1, srow[1]); atomicAdd(dc + 2, srow[2]);
+                }
+                if (rest) {
+                    const float* q = srow + 3 + lead;
+                    float* r4 = rest + lead;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) if (k < lead) atomicAdd(rest + k, srow[3 + k]);
+#pragma unroll
+                    for (int v = 0; v < 11; v++) if (v < nv4) red_add_v4(r4 + 4 * v, q[4 * v], q[4 * v + 1], q[4 * v + 2], q[4 * v + 3]);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) if (k < tail) atomicAdd(r4 + 4 * nv4 + k, q[4 * nv4 + k]);
                 }
             }
             __syncwarp(FULL);
@@ -750,7 +751,8 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
             ctx->span_end(s);
             ctx->span_begin("k_bw_prefix", s); k_bw_prefix<<<GB, TB, 0, s>>>(a, f); ctx->span_end(s);
             ctx->span_begin("k_bw_hits", s);
-            k_bw_hits<<<ctx->num_sms * 8, 256, sh_tab ? sizeof(float) * 8 * 32 * 48 : 0, s>>>(a, f);
+            if (sh_tab) LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bw_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * 32 * BW_SROW)));
+            k_bw_hits<<<ctx->num_sms * 8, 256, sh_tab ? sizeof(float) * 8 * 32 * BW_SROW : 0, s>>>(a, f);
             ctx->span_end(s);
             a.only_flag = legacy_flag;                // set on the device if the records did not fit (normally not)
             ctx->span_begin("k_backward_list", s); k_backward_list<<<GB, TB, 0, s>>>(a); ctx->span_end(s);

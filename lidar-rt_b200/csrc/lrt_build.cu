@@ -309,8 +309,11 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
         cub::DoubleBuffer<unsigned> dk32((unsigned*)ctx->keys_a.p, (unsigned*)ctx->keys_b.p);
         cub::DoubleBuffer<unsigned long long> dk64((unsigned long long*)ctx->keys_a.p, (unsigned long long*)ctx->keys_b.p);
         const int bits32 = ctx->opt_morton_bits == 32 ? 32 : 30;
+        // 32-bit keys are sorted on their top 24 bits only: 16.7 M cells for a few million surfels, the order inside a cell is
+        // irrelevant (the sort is stable), and the radix sort takes three 8-bit passes instead of four
+        const int lo_bit = bits32 == 32 ? 8 : 0;
         if (wide) { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk64, dv, P, 0, 63, s)); }
-        else { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk32, dv, P, 0, bits32, s)); }
+        else { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk32, dv, P, lo_bit, bits32, s)); }
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sort_tmp, tmp_bytes));
         k_bounds_init<<<1, 32, 0, s>>>((int*)ctx->bounds.p);
         const int gb = min((P + TB - 1) / TB, 148 * 8);
@@ -329,7 +332,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
                 k_morton<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,
                                                            (unsigned*)ctx->perm_b.p);
             ctx->span_begin("radix_sort", s);
-            LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk32, dv, P, 0, bits32, s));
+            LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, dk32, dv, P, lo_bit, bits32, s));
             ctx->span_end(s);
         }
         ctx->launches += 3 + 2 + (wide ? 8 : 4);     // bounds_init, bounds, morton + radix sort (histogram, scan, one onesweep launch per 8-bit digit)

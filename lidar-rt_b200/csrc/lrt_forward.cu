@@ -564,7 +564,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_hit_count, sizeof(int) * 3 * (size_t)R));
         // bin capacity: 8192 candidates per ray while that stays under ~6 GB (4096 at one Waymo frame), never below what the
         // shared-memory sort takes
-        int hcap = WF_HCAP_MAX;
+        int hcap = 2 * WF_HCAP_MAX;                                     // 16384 candidates per ray for patches of up to ~49 k rays
         while (hcap > WF_HCAP && (size_t)R * hcap * sizeof(unsigned long long) > ((size_t)6 << 30)) hcap >>= 1;
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_bins, sizeof(unsigned long long) * (size_t)R * hcap));
         w.hcap = hcap;
@@ -673,7 +673,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                     const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
                     LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
-                    k_sp_gather_big<<<ctx->num_sms, 256, 0, s>>>(bv, a, w, sp);
+                    k_sp_big<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
                 }
                 ctx->span_end(s);
                 LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_sp_counts(int R, WfBufs w, SpBufs sp)
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r > R) return;
     int c = 0;
-    if (r < R) { const int hc = w.hit_count[r]; c = ((hc & WF_TAINT) || hc > w.hcap) ? 0 : hc; }
+    if (r < R) { const int hc = w.hit_count[r]; c = ((hc & WF_TAINT) || hc > WF_HCAP) ? 0 : hc; }      // longer bins: fallback or k_sp_big, no stream slice
     sp.ccnt[r] = c;
 }
 
@@ -65,7 +65,11 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
     for (int s = blockIdx.x * 4 + wib; s < a.R; s += gridDim.x * 4) {
         const int r = w.order ? w.order[s] : s;
         const int n = sp.ccnt[r];
-        if (n <= 0) continue;
+        if (n <= 0) {                                              // empty, handed to the fallback, or longer than WF_HCAP:
+            const int hc = w.hit_count[r];                         // the latter are sorted by k_wf_sort_big and walked by k_sp_big
+            if (lane == 0 && !(hc & WF_TAINT) && hc > WF_HCAP && hc <= w.hcap) w.big_list[atomicAdd(w.counts + 10, 1)] = r;
+            continue;
+        }
         const long long base = sp.cbase[r];
         if (base + n > sp.capacity) {                              // the stream is full: this ray takes the per-ray fallback
             if (lane == 0) atomicOr(w.hit_count + r, WF_TAINT);
@@ -73,17 +77,30 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
         }
         const unsigned long long* bin = w.bins + (size_t)r * w.hcap;
         float4* dst = sp.srec + 4 * (size_t)base;
+        // Up to 64 candidates (nearly every ray): the network runs on 32-bit keys — the depth's bits with the low 5 (6) replaced by
+        // the candidate's slot — at half the shuffles, compares and selects of 64-bit (t, id) keys; the full key is then fetched
+        // from the lane that holds it. The stream comes out sorted up to 2^-17 t, which pass A's margin allows for (wf_margin()):
+        // its k-buffer orders the slots of a round by the exact (t', id) anyway.
         if (n <= 32) {
-            unsigned long long k = lane < n ? bin[lane] : LRT_KEY_EMPTY;
-            k = warp_sort32(k, lane);
-            if (lane < n) sp_emit(rec_g, dst + 4 * lane, k);
+            const unsigned long long k = lane < n ? bin[lane] : LRT_KEY_EMPTY;
+            unsigned k32 = lane < n ? (((unsigned)(k >> 32) & ~31u) | (unsigned)lane) : 0xffffffffu;
+            k32 = warp_sort32(k32, lane);
+            const unsigned long long ks = __shfl_sync(FULL, k, (int)(k32 & 31u));
+            if (lane < n) sp_emit(rec_g, dst + 4 * lane, ks);
             continue;
         }
         if (n <= 64) {
-            unsigned long long k0 = bin[lane], k1 = lane + 32 < n ? bin[lane + 32] : LRT_KEY_EMPTY;
-            warp_sort64(k0, k1, lane);
-            sp_emit(rec_g, dst + 4 * lane, k0);
-            if (lane + 32 < n) sp_emit(rec_g, dst + 4 * (lane + 32), k1);
+            const unsigned long long k0 = bin[lane], k1 = lane + 32 < n ? bin[lane + 32] : LRT_KEY_EMPTY;
+            unsigned a0 = ((unsigned)(k0 >> 32) & ~63u) | (unsigned)lane;
+            unsigned a1 = lane + 32 < n ? (((unsigned)(k1 >> 32) & ~63u) | (unsigned)(lane + 32)) : 0xffffffffu;
+            warp_sort64(a0, a1, lane);
+            {
+                const int s0 = (int)(a0 & 63u), s1 = (int)(a1 & 63u);
+                const unsigned long long x0 = __shfl_sync(FULL, k0, s0 & 31), y0 = __shfl_sync(FULL, k1, s0 & 31);
+                const unsigned long long x1 = __shfl_sync(FULL, k0, s1 & 31), y1 = __shfl_sync(FULL, k1, s1 & 31);
+                sp_emit(rec_g, dst + 4 * lane, (s0 >> 5) ? y0 : x0);
+                if (lane + 32 < n) sp_emit(rec_g, dst + 4 * (lane + 32), (s1 >> 5) ? y1 : x1);
+            }
             continue;
         }
         if (n <= 128) {
@@ -102,10 +119,6 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
             warp_sort_regs<8>(k, lane);
 #pragma unroll
             for (int j = 0; j < 8; j++) if (lane + 32 * j < n) sp_emit(rec_g, dst + 4 * (lane + 32 * j), k[j]);
-            continue;
-        }
-        if (n > WF_HCAP) {                                         // k_wf_sort_big sorts the bin in place, k_sp_gather_big emits it
-            if (lane == 0) w.big_list[atomicAdd(w.counts + 10, 1)] = r;
             continue;
         }
         const int m = WF_HCAP;                                     // 257..512 candidates: this warp's slice of shared memory
@@ -127,16 +140,20 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
     }
 }
 
-// the few bins beyond WF_HCAP candidates, sorted in place by k_wf_sort_big: one block each
-__global__ void __launch_bounds__(256) k_sp_gather_big(BvhView bvh, FwdArgs a, WfBufs w, SpBufs sp)
+// The rays with more than WF_HCAP candidates (a ray skimming a wall or the side of a vehicle: thousands), whose bins
+// k_wf_sort_big has sorted in place: one WARP per ray walks the sorted keys in global memory and does the whole job — slots,
+// colour, fold, hit lists (wf_shade_ray). Pass A skips these rays; passes B and C find complete hit records and reproduce the
+// same colours and sums. Replaces what used to be the "fallback cliff": such a ray cost a lone thread milliseconds.
+__global__ void __launch_bounds__(128) k_sp_big(BvhView bvh, FwdArgs a, WfBufs w)
 {
+    const int lane = threadIdx.x & 31;
     const int nbig = min(w.counts[10], a.R);
-    for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nbig; b += (gridDim.x * blockDim.x) >> 5) {
         const int r = w.big_list[b];
-        const int n = sp.ccnt[r];
-        const unsigned long long* bin = w.bins + (size_t)r * w.hcap;
-        float4* dst = sp.srec + 4 * (size_t)sp.cbase[r];
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sp_emit(bvh.rec_g, dst + 4 * i, bin[i]);
+        const int n = min(w.hit_count[r] & (WF_TAINT - 1), w.hcap);
+        const float em = w.nwild[r] > 0 ? __int_as_float(0x7f800000) : __int_as_float(w.emax[r]);
+        wf_shade_ray(w.bins + (size_t)r * w.hcap, n, r, em, bvh, a, lane);
+        __syncwarp(0xffffffffu);
     }
 }
 
@@ -170,6 +187,7 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
         const int r = w.order ? w.order[s] : s;
         const int hc = w.hit_count[r];
         if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; a.hit_cnt[r] = 0; continue; }
+        if (hc > WF_HCAP) continue;                                // done by k_sp_big, one warp per ray
         const int n = hc;
         const float em = __int_as_float(w.emax[r]);
         const int nw = min(w.nwild[r], n);                         // wild candidates (key t = 0): the first nw of the sorted stream, tested in every round
@@ -340,7 +358,7 @@ __device__ __forceinline__ void sp_colour_window(int nb, const float* b, const f
 #define LRT_COLOUR_MIN_BLOCKS 4
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(256, MODE == 2 ? 2 : LRT_COLOUR_MIN_BLOCKS) k_sp_colour(FwdArgs a)
+__global__ void __launch_bounds__(256, MODE == 2 ? 3 : LRT_COLOUR_MIN_BLOCKS) k_sp_colour(FwdArgs a)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.R) return;
@@ -367,35 +385,44 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : LRT_COLOUR_MIN_BLOCKS) k_
             }
         }
         float c[3];
-        bool done = false;
         if (MODE == 1) {
             sh_colour_stream_b(nb, sb, a.shs + (size_t)g * a.M * 3, c);
-            done = true;
         } else if (MODE == 2) {
             int j;
             const ShPartDev& p = sh_find(a.sh_tab, g, j);
-            if (j + 1 < p.P) {                                     // (the last row of a tensor: its window would read past the end)
+            {
                 const int rf = 3 * (a.sh_tab->M - 1);
                 const size_t f0 = (size_t)rf * j;
                 const int al = (int)(f0 & 3);
-                const float4* p4 = reinterpret_cast<const float4*>(p.rest + (f0 - al));
+                const float* w0 = p.rest + (f0 - al);
+                const float4* p4 = reinterpret_cast<const float4*>(w0);
                 const float* dcp = p.dc + 3 * (size_t)j;
                 const float dc[3] = {ld_f(dcp), ld_f(dcp + 1), ld_f(dcp + 2)};
                 const int n4 = (al + 3 * nb - 3 + 3) >> 2;
+                const int left = j + 1 == p.P ? al + rf : 64;      // floats of the window that exist (the tensor's last row: no read past its end)
                 float wv[48];
 #pragma unroll
                 for (int i = 0; i < 12; i++) {
-                    const float4 v = i < n4 ? ld_f4(p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < n4) {
+                        if (4 * i + 4 <= left) v = ld_f4(p4 + i);
+                        else {
+                            if (4 * i < left) v.x = ld_f(w0 + 4 * i);
+                            if (4 * i + 1 < left) v.y = ld_f(w0 + 4 * i + 1);
+                            if (4 * i + 2 < left) v.z = ld_f(w0 + 4 * i + 2);
+                        }
+                    }
                     wv[4 * i] = v.x; wv[4 * i + 1] = v.y; wv[4 * i + 2] = v.z; wv[4 * i + 3] = v.w;
                 }
-                if (al == 0) sp_colour_window<0>(nb, sb, dc, wv, c);
-                else if (al == 1) sp_colour_window<1>(nb, sb, dc, wv, c);
-                else if (al == 2) sp_colour_window<2>(nb, sb, dc, wv, c);
-                else sp_colour_window<3>(nb, sb, dc, wv, c);
-                done = true;
+                // bring the row to the front of the window: shift by 1 and by 2 floats as the bits of `al` say (predicated moves on
+                // registers; a 4-way branch on `al` would run the whole evaluation once per alignment present in the warp)
+#pragma unroll
+                for (int i = 0; i < 47; i++) wv[i] = (al & 1) ? wv[i + 1] : wv[i];
+#pragma unroll
+                for (int i = 0; i < 46; i++) wv[i] = (al & 2) ? wv[i + 2] : wv[i];
+                sp_colour_window<0>(nb, sb, dc, wv, c);
             }
-        }
-        if (!done) {
+        } else {
             float sh[48]; bool cl;
             load_sh_any(a, g, nb, sh);
             sh_colour<false>(a.D, dirn, sh, c, cl, nullptr);

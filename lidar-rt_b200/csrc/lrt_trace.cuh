@@ -119,8 +119,10 @@ __device__ __forceinline__ bool quad_candidate(const SurfelRec* __restrict__ rec
     return t < LRT_TMAX;
 }
 
-// margin of the sorted-bin scan around depth t for a ray whose worst candidate error bound is em
-__device__ __forceinline__ float wf_margin(float t, float em) { return fmaxf(1e-3f + 1e-5f * fabsf(t), em); }
+// margin of the sorted-bin scan around depth t for a ray whose worst candidate error bound is em. The last term covers the
+// ORDER of the split passes' candidate stream: bins of up to 64 candidates are sorted on 32-bit keys whose low 5-6 bits carry the
+// candidate's slot instead of the depth's last mantissa bits (lrt_split.cuh), so the stream is sorted only up to 7.6e-6 t.
+__device__ __forceinline__ float wf_margin(float t, float em) { return fmaxf(1e-3f + 1e-5f * fabsf(t), em) + 1e-5f * fabsf(t); }
 
 // Sorted insertion into the register-resident k-buffer (ascending 64-bit keys = (t' bits, Gaussian id)).
 __device__ __forceinline__ void kbuf_insert(unsigned long long (&kb)[LRT_KBUF], unsigned long long key)

@@ -184,14 +184,15 @@ __global__ void __launch_bounds__(256) k_wf_leaf(BvhView bvh, FwdArgs a, WfBufs 
     }
 }
 
-// warp-wide bitonic sort of one 64-bit key per lane (ascending)
-__device__ __forceinline__ unsigned long long warp_sort32(unsigned long long k, int lane)
+// warp-wide bitonic sort of one key per lane (ascending); T = 64-bit (t bits, id) keys or 32-bit truncated keys
+template <typename T>
+__device__ __forceinline__ T warp_sort32(T k, int lane)
 {
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, stride);
+            const T other = __shfl_xor_sync(0xffffffffu, k, stride);
             const bool up = ((lane & size) == 0);
             const bool lower = ((lane & stride) == 0);
             const bool take_min = (up == lower);
@@ -202,17 +203,18 @@ __device__ __forceinline__ unsigned long long warp_sort32(unsigned long long k, 
 }
 
 // warp-wide bitonic sort of 64 keys, two per lane: k0 = element `lane`, k1 = element `lane + 32` (ascending)
-__device__ __forceinline__ void warp_sort64(unsigned long long& k0, unsigned long long& k1, int lane)
+template <typename T>
+__device__ __forceinline__ void warp_sort64(T& k0, T& k1, int lane)
 {
 #pragma unroll
     for (int size = 2; size <= 64; size <<= 1) {
 #pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             if (stride == 32) {                            // partner is the lane's own second key; elements 0..63 all sort upwards here
-                const unsigned long long lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
+                const T lo = k0 < k1 ? k0 : k1, hi = k0 < k1 ? k1 : k0;
                 k0 = lo; k1 = hi;
             } else {
-                const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, stride), o1 = __shfl_xor_sync(0xffffffffu, k1, stride);
+                const T o0 = __shfl_xor_sync(0xffffffffu, k0, stride), o1 = __shfl_xor_sync(0xffffffffu, k1, stride);
                 const bool lower = ((lane & stride) == 0);
                 const bool up0 = ((lane & size) == 0), up1 = (((lane + 32) & size) == 0);
                 k0 = (lower == up0) ? (k0 < o0 ? k0 : o0) : (k0 < o0 ? o0 : k0);
@@ -220,6 +222,151 @@ __device__ __forceinline__ void warp_sort64(unsigned long long& k0, unsigned lon
             }
         }
     }
+}
+
+// One ray, walked by one WARP over its SORTED candidate keys (shared or global memory): the reference's rounds with 32 candidates
+// re-tested per step, the round's 16 slots shaded in parallel (16 lanes) and folded in order with shuffles. Used by k_wf_shade (every
+// ray) and by k_sp_big (split passes: the rays with more than WF_HCAP candidates — a thread walking thousands of candidates alone
+// takes milliseconds, the per-ray fallback of round 1 took 3-4 ms for such a ray).
+__device__ __forceinline__ void wf_shade_ray(const unsigned long long* keys, int n, int r, float em, const BvhView& bvh, const FwdArgs& a, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    // ---- the reference's round loop (forward.cu:195-292)
+    FwdRay q;
+    fwd_ray_init(q, r, a);
+    for (int round = 0;; round++) {
+        unsigned long long slot_key = LRT_KEY_EMPTY;           // lane i < 16 holds slot i of this round
+        int nvalid;
+        {
+            // Candidates are re-tested, exactly, from o' = o + base d, 32 at a time in bin order starting at
+            // the first one with t >= base - margin; the 32 best (t', id) keys are kept (bitonic merge). The
+            // scan stops when the bin is exhausted or when the next unexamined candidate lies safely beyond
+            // the 16th best — so the round's slots are exactly the 16 nearest hits of the re-based ray.
+            RaySetup rs;
+            ray_setup(rs, q.o, q.d, q.base);
+            const float thr = q.base - 2.0f * wf_margin(q.base, em);
+            int below = 0;                                      // candidates in front of thr: lower bound in the sorted keys (warp-uniform)
+            {
+                int lo = 0, hi = n;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__uint_as_float((unsigned)(keys[mid] >> 32)) < thr) lo = mid + 1; else hi = mid;
+                }
+                below = lo;
+            }
+            int pos = below;
+            unsigned long long best = LRT_KEY_EMPTY;
+            // Fast path: candidates are stored in ascending original depth, and re-testing from a point on
+            // the same ray preserves that order except between near-ties. So append the valid re-tested keys
+            // in bin order (ballot compaction) and only verify that they came out sorted; the general
+            // sort + bitonic-merge path below runs only if that check fails.
+            int have = 0;
+            bool sorted_ok = true;
+            const int pos0 = pos;
+            for (;;) {
+                unsigned long long nk = LRT_KEY_EMPTY;
+                const int idx = pos + lane;
+                if (idx < n) {
+                    const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
+                    float t; int g2;
+                    if (quad_hit(bvh.rec_g, g, rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                }
+                const unsigned vm = __ballot_sync(FULL, nk != LRT_KEY_EMPTY);
+                const int want = lane - have;                                   // lane takes the want-th valid key of this window
+                const int src = (want >= 0 && want < __popc(vm)) ? (int)__fns(vm, 0, want + 1) : -1;
+                const unsigned long long got = __shfl_sync(FULL, nk, src < 0 ? 0 : src);
+                if (src >= 0) best = got;
+                have = min(32, have + __popc(vm));
+                pos += 32;
+                if (pos >= n || have >= 32) break;
+                if (have >= LRT_KBUF) {
+                    const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
+                    const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
+                    const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
+                    if (t_next - t16 > wf_margin(t16, em)) break;
+                }
+            }
+            {
+                const unsigned long long prev = __shfl_up_sync(FULL, best, 1);
+                const bool bad = lane > 0 && lane < have && prev > best;
+                sorted_ok = __ballot_sync(FULL, bad) == 0;
+                // the scan may have stopped at 32 collected keys with candidates left: then the 16th must still be
+                // safely in front of the first unexamined candidate
+                if (sorted_ok && pos < n) {
+                    const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
+                    const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
+                    const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
+                    if (!(have >= LRT_KBUF && t_next - t16 > wf_margin(t16, em))) sorted_ok = false;
+                }
+                if (sorted_ok && have >= 32) {                                  // valid keys beyond the 32nd were dropped: they must
+                    const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1), k32 = __shfl_sync(FULL, best, 31);   // lie safely behind the 16th
+                    const float t16 = __uint_as_float((unsigned)(k16 >> 32)), t32 = __uint_as_float((unsigned)(k32 >> 32));
+                    if (!(t32 - t16 > wf_margin(t16 + q.base, em))) sorted_ok = false;
+                }
+            }
+            if (!sorted_ok) {                                                   // general path (near-ties re-ordered by re-basing)
+            pos = pos0; best = LRT_KEY_EMPTY;
+            for (;;) {
+                unsigned long long nk = LRT_KEY_EMPTY;
+                const int idx = pos + lane;
+                if (idx < n) {
+                    const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
+                    float t; int g2;
+                    if (quad_hit(bvh.rec_g, g, rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+                }
+                nk = warp_sort32(nk, lane);
+                const unsigned long long rev = __shfl_sync(FULL, nk, 31 - lane);      // bitonic merge: 32 smallest of best U nk
+                best = warp_sort32(best < rev ? best : rev, lane);
+                pos += 32;
+                if (pos >= n) break;                                                   // bin exhausted: exact
+                const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
+                if (k16 != LRT_KEY_EMPTY) {
+                    const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
+                    const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
+                    if (t_next - t16 > wf_margin(t16, em)) break;   // nothing further can rank in the first 16
+                }
+            }
+            }
+            slot_key = best;
+            nvalid = __popc(__ballot_sync(FULL, best != LRT_KEY_EMPTY));
+            // nvalid == 32 only says ">= 32": the round logic below only distinguishes < 16 from >= 16
+        }
+        const int nr = nvalid < LRT_KBUF ? nvalid : LRT_KBUF;   // slots of this round
+        G8Slot sl;
+        g8_shade_slot(slot_key, lane < nr, q, bvh, a, sl);
+        bool terminated = false;
+        for (int i = 0; i < nr; i++) {                          // in-order fold (forward.cu:201-280)
+            const float dpt_i = __shfl_sync(FULL, sl.dpt, i);
+            const unsigned fl_i = __shfl_sync(FULL, sl.flags, i);
+            q.nslots++;
+            q.dpt = dpt_i;
+            if (!(fl_i & G8_F_DPT_OK)) continue;
+            const int g_i = __shfl_sync(FULL, sl.g, i);
+            if (g_i == q.last) continue;
+            q.last = g_i;
+            if (!(fl_i & G8_F_OK)) continue;
+            const float alpha = __shfl_sync(FULL, sl.alpha, i);
+            q.testT = q.T * (1.0f - alpha);
+            if (q.testT < LRT_T_MIN) { terminated = true; break; }
+            const float wgt = alpha * q.T;
+            const float c0 = __shfl_sync(FULL, sl.c0, i), c1 = __shfl_sync(FULL, sl.c1, i), c2 = __shfl_sync(FULL, sl.c2, i);
+            q.C0 += wgt * c0; q.C1 += wgt * c1; q.C2 += wgt * c2;
+            q.Dp += wgt * dpt_i; q.W += wgt;
+            if (lane == i) {                                     // the owner of the slot commits it (forward.cu:272 + hit list);
+                atomicAdd(a.accum_w + g_i, wgt);                  // a ray is only handed to the fallback BEFORE its first round
+                if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
+                    a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g_i;
+                    a.hit_t[(size_t)q.ncontrib * a.R + q.r] = dpt_i;
+                    if (a.hit_aux) a.hit_aux[(size_t)q.ncontrib * a.R + q.r] = make_float4(alpha, c0, c1, c2);
+                }
+            }
+            q.ncontrib++;
+            q.T = q.testT;
+        }
+        if (terminated || q.testT < LRT_T_MIN || nvalid < LRT_KBUF) break;      // forward.cu:282-285
+        q.base = (float)((double)q.dpt + LRT_STEP_EPS);                          // :288
+    }
+    if (lane == 0) fwd_write(q, a, 0);
 }
 
 // One warp per ray. smem: 4 warps x WF_HCAP keys (16 KB).
@@ -258,137 +405,7 @@ __global__ void __launch_bounds__(128, LRT_SHADE_MIN_BLOCKS) k_wf_shade(BvhView 
                 __syncwarp(FULL);
             }
         }
-        // ---- the reference's round loop (forward.cu:195-292)
-        FwdRay q;
-        fwd_ray_init(q, r, a);
-        for (int round = 0;; round++) {
-            unsigned long long slot_key = LRT_KEY_EMPTY;           // lane i < 16 holds slot i of this round
-            int nvalid;
-            {
-                // Candidates are re-tested, exactly, from o' = o + base d, 32 at a time in bin order starting at
-                // the first one with t >= base - margin; the 32 best (t', id) keys are kept (bitonic merge). The
-                // scan stops when the bin is exhausted or when the next unexamined candidate lies safely beyond
-                // the 16th best — so the round's slots are exactly the 16 nearest hits of the re-based ray.
-                RaySetup rs;
-                ray_setup(rs, q.o, q.d, q.base);
-                const float thr = q.base - 2.0f * wf_margin(q.base, em);
-                int below = 0;
-                for (int i = lane; i < n; i += 32) below += __uint_as_float((unsigned)(keys[i] >> 32)) < thr;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) below += __shfl_xor_sync(FULL, below, o);
-                int pos = below;
-                unsigned long long best = LRT_KEY_EMPTY;
-                // Fast path: candidates are stored in ascending original depth, and re-testing from a point on
-                // the same ray preserves that order except between near-ties. So append the valid re-tested keys
-                // in bin order (ballot compaction) and only verify that they came out sorted; the general
-                // sort + bitonic-merge path below runs only if that check fails.
-                int have = 0;
-                bool sorted_ok = true;
-                const int pos0 = pos;
-                for (;;) {
-                    unsigned long long nk = LRT_KEY_EMPTY;
-                    const int idx = pos + lane;
-                    if (idx < n) {
-                        const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
-                        float t; int g2;
-                        if (quad_hit(bvh.rec_g, g, rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
-                    }
-                    const unsigned vm = __ballot_sync(FULL, nk != LRT_KEY_EMPTY);
-                    const int want = lane - have;                                   // lane takes the want-th valid key of this window
-                    const int src = (want >= 0 && want < __popc(vm)) ? (int)__fns(vm, 0, want + 1) : -1;
-                    const unsigned long long got = __shfl_sync(FULL, nk, src < 0 ? 0 : src);
-                    if (src >= 0) best = got;
-                    have = min(32, have + __popc(vm));
-                    pos += 32;
-                    if (pos >= n || have >= 32) break;
-                    if (have >= LRT_KBUF) {
-                        const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
-                        const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
-                        const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
-                        if (t_next - t16 > wf_margin(t16, em)) break;
-                    }
-                }
-                {
-                    const unsigned long long prev = __shfl_up_sync(FULL, best, 1);
-                    const bool bad = lane > 0 && lane < have && prev > best;
-                    sorted_ok = __ballot_sync(FULL, bad) == 0;
-                    // the scan may have stopped at 32 collected keys with candidates left: then the 16th must still be
-                    // safely in front of the first unexamined candidate
-                    if (sorted_ok && pos < n) {
-                        const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
-                        const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
-                        const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
-                        if (!(have >= LRT_KBUF && t_next - t16 > wf_margin(t16, em))) sorted_ok = false;
-                    }
-                    if (sorted_ok && have >= 32) {                                  // valid keys beyond the 32nd were dropped: they must
-                        const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1), k32 = __shfl_sync(FULL, best, 31);   // lie safely behind the 16th
-                        const float t16 = __uint_as_float((unsigned)(k16 >> 32)), t32 = __uint_as_float((unsigned)(k32 >> 32));
-                        if (!(t32 - t16 > wf_margin(t16 + q.base, em))) sorted_ok = false;
-                    }
-                }
-                if (!sorted_ok) {                                                   // general path (near-ties re-ordered by re-basing)
-                pos = pos0; best = LRT_KEY_EMPTY;
-                for (;;) {
-                    unsigned long long nk = LRT_KEY_EMPTY;
-                    const int idx = pos + lane;
-                    if (idx < n) {
-                        const int g = (int)(unsigned)(keys[idx] & 0xffffffffull);
-                        float t; int g2;
-                        if (quad_hit(bvh.rec_g, g, rs, t, g2)) nk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
-                    }
-                    nk = warp_sort32(nk, lane);
-                    const unsigned long long rev = __shfl_sync(FULL, nk, 31 - lane);      // bitonic merge: 32 smallest of best U nk
-                    best = warp_sort32(best < rev ? best : rev, lane);
-                    pos += 32;
-                    if (pos >= n) break;                                                   // bin exhausted: exact
-                    const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
-                    if (k16 != LRT_KEY_EMPTY) {
-                        const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
-                        const float t_next = __uint_as_float((unsigned)(keys[pos] >> 32));
-                        if (t_next - t16 > wf_margin(t16, em)) break;   // nothing further can rank in the first 16
-                    }
-                }
-                }
-                slot_key = best;
-                nvalid = __popc(__ballot_sync(FULL, best != LRT_KEY_EMPTY));
-                // nvalid == 32 only says ">= 32": the round logic below only distinguishes < 16 from >= 16
-            }
-            const int nr = nvalid < LRT_KBUF ? nvalid : LRT_KBUF;   // slots of this round
-            G8Slot sl;
-            g8_shade_slot(slot_key, lane < nr, q, bvh, a, sl);
-            bool terminated = false;
-            for (int i = 0; i < nr; i++) {                          // in-order fold (forward.cu:201-280)
-                const float dpt_i = __shfl_sync(FULL, sl.dpt, i);
-                const unsigned fl_i = __shfl_sync(FULL, sl.flags, i);
-                q.nslots++;
-                q.dpt = dpt_i;
-                if (!(fl_i & G8_F_DPT_OK)) continue;
-                const int g_i = __shfl_sync(FULL, sl.g, i);
-                if (g_i == q.last) continue;
-                q.last = g_i;
-                if (!(fl_i & G8_F_OK)) continue;
-                const float alpha = __shfl_sync(FULL, sl.alpha, i);
-                q.testT = q.T * (1.0f - alpha);
-                if (q.testT < LRT_T_MIN) { terminated = true; break; }
-                const float wgt = alpha * q.T;
-                const float c0 = __shfl_sync(FULL, sl.c0, i), c1 = __shfl_sync(FULL, sl.c1, i), c2 = __shfl_sync(FULL, sl.c2, i);
-                q.C0 += wgt * c0; q.C1 += wgt * c1; q.C2 += wgt * c2;
-                q.Dp += wgt * dpt_i; q.W += wgt;
-                if (lane == i) {                                     // the owner of the slot commits it (forward.cu:272 + hit list);
-                    atomicAdd(a.accum_w + g_i, wgt);                  // a ray is only handed to the fallback BEFORE its first round
-                    if (a.hit_gidx != nullptr && q.ncontrib < a.cap) {
-                        a.hit_gidx[(size_t)q.ncontrib * a.R + q.r] = g_i;
-                        a.hit_t[(size_t)q.ncontrib * a.R + q.r] = dpt_i;
-                        if (a.hit_aux) a.hit_aux[(size_t)q.ncontrib * a.R + q.r] = make_float4(alpha, c0, c1, c2);
-                    }
-                }
-                q.ncontrib++;
-                q.T = q.testT;
-            }
-            if (terminated || q.testT < LRT_T_MIN || nvalid < LRT_KBUF) break;      // forward.cu:282-285
-            q.base = (float)((double)q.dpt + LRT_STEP_EPS);                          // :288
-        }
-        if (lane == 0) fwd_write(q, a, 0);
+        wf_shade_ray(keys, n, r, em, bvh, a, lane);
         __syncwarp(FULL);
     }
 }

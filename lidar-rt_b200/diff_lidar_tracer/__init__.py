@@ -103,8 +103,11 @@ class _Tracer(torch.autograd.Function):
                 raise ValueError("SH handle and means3D disagree on the number of Gaussians")
             handle.ctx.set_sh_parts(box.parts)
             shs_d, sh_M = None, box.M
+        # hit lists are recorded for the backward's replay only: not under torch.no_grad() / when no input needs a gradient
+        # (the forward then keeps its lists in the context's own workspace instead of ~1 GB of fresh tensors per call)
+        record = handle.record_hits and any(ctx.needs_input_grad)
         res = handle.ctx.forward(ray_o.detach(), ray_d.detach(), s.bg, means_d, scales_d, rots_d, opac_d, shs_d,
-                                 int(s.sh_degree), float(s.scale_modifier), record_hits=handle.record_hits,
+                                 int(s.sh_degree), float(s.scale_modifier), record_hits=record,
                                  cap=handle.hit_cap, sh_M=sh_M)
         out = res["out"]
         accum = res["accum_w"]
