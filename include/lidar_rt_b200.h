@@ -218,7 +218,7 @@ int lrt_compact_rows(lrt_ctx* ctx, int n_rows, const uint8_t* keep, int n_tensor
 int lrt_densify_rows(lrt_ctx* ctx, int P, const uint8_t* clone_mask, const uint8_t* split_mask, int n_clone, int n_split, int N,
                      const float* samples, const float* rotation, int n_tensors, const lrt_row_tensor* tensors, void* stream);
 
-/* Tuning knobs; none of them changes results.
+/* Tuning knobs; none of them changes results — except LRT_OPT_TRIANGLE_DEPTH, which selects the reference's literal proxy geometry.
  *   LRT_OPT_FORWARD_KERNEL  0 = one thread per ray, 1 = persistent threads with per-lane refill, 2 = 8 lanes per ray,
  *                           3 = breadth-first wavefront through the hierarchy + per-ray sort + compositing,
  *                           4 = shared-origin beam grid (default): when ray_o_stride == 0 the frame's rays are binned by
@@ -235,15 +235,18 @@ int lrt_densify_rows(lrt_ctx* ctx, int P, const uint8_t* clone_mask, const uint8
  *   LRT_OPT_BEAM_CELL_PCT   beam grid: cell edge in percent of the size that gives one ray per cell (default 100)
  *   LRT_OPT_KERNEL_TIMING   1 = record CUDA events around every kernel launch (read with lrt_get_kernel_times)
  *   LRT_OPT_WAVEFRONT_SHADE wavefront compositing: 0 = one warp per ray, 1 = warp sort + one thread per ray,
- *                           2 = 1 with pipelined record loads and slot opacities computed on acceptance (default),
- *                           3 = EXPERIMENTAL and the one value that DOES change results (ulp-level, ~0.07 % of rays): depth of a hit
- *                               taken from the ray's own origin instead of the round's re-based origin; not yet
- *                               verified on a GPU
+ *                           2 = 1 with pipelined record loads and slot opacities computed on acceptance,
+ *                           3 = split passes (default): sort + gather into a sorted record stream, then slots / colour / fold
+ *   LRT_OPT_TRIANGLE_DEPTH  1 = the hits of a ray and their depths come from the reference's literal proxy, the two triangles
+ *                           (v0,v1,v2), (v2,v3,v1) over the corners build2DRectangle rounds to fp32 (primitive_utils.py:203-221),
+ *                           intersected in fp64 like the oracle's ORC_TRIANGLES mode, instead of the analytic quad |u|,|v| <= f:
+ *                           what forward.cu:319 reads with optixGetRayTmax. Default 0. Applies to the default forward path
+ *                           (kernel 4 / 3 with split passes); rays handed to the fallback paths keep the analytic quad.
  *   LRT_OPT_MORTON_BITS     32 = 32-bit keys, bits dealt to the axes so cells stay cubic (default); 63 = 21 bits/axis on
  *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build) */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,
                   LRT_OPT_BACKWARD_KERNEL = 5, LRT_OPT_WAVEFRONT_SHADE = 6, LRT_OPT_KERNEL_TIMING = 7,
-                  LRT_OPT_SORT_RAYS = 8, LRT_OPT_BEAM_CELL_PCT = 9 };
+                  LRT_OPT_SORT_RAYS = 8, LRT_OPT_BEAM_CELL_PCT = 9, LRT_OPT_TRIANGLE_DEPTH = 10 };
 int lrt_set_option(lrt_ctx* ctx, int option, int value);
 
 /* Introspection for tests / benchmarks (host pointers). */

@@ -415,7 +415,8 @@ __device__ __forceinline__ float seg_sum(float v, unsigned same)
 }
 
 #define BW_SROW 49
-__global__ void __launch_bounds__(256) k_bw_hits(BwArgs a, BwFlat f)
+template <bool INPLACE>                                  // SH gradients into the concatenated (P, M, 3) buffer, or in place into the leaf gradients
+__global__ void __launch_bounds__(256, 3) k_bw_hits(BwArgs a, BwFlat f)      // 3 blocks per SM (<= 85 registers) measured faster than 2 at 103
 {
     extern __shared__ float s_row[];                     // in-place SH gradients only: 8 warps x 32 lanes x BW_SROW floats
     const unsigned FULL = 0xffffffffu;
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(256) k_bw_hits(BwArgs a, BwFlat f)
         }
         // SH: dL_dsh[j][ch] = basis_j dL_dcolour[ch], four contiguous floats at a time
         const int nf = 3 * nb;
-        if (go.sh_tab) {
+        if (INPLACE) {
             // leaf gradients in place: a Gaussian's row is d_features_dc[j] (3 floats) + d_features_rest[j] (3 (M - 1) floats at a
             // 4-byte aligned address). The segment heads park their reduced row in shared memory (the 16-byte groups of the target
             // do not line up with the groups the reduction produces), then emit it: red.v4 over the aligned middle of the rest
@@ -751,8 +752,12 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
             ctx->span_end(s);
             ctx->span_begin("k_bw_prefix", s); k_bw_prefix<<<GB, TB, 0, s>>>(a, f); ctx->span_end(s);
             ctx->span_begin("k_bw_hits", s);
-            if (sh_tab) LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bw_hits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * 32 * BW_SROW)));
-            k_bw_hits<<<ctx->num_sms * 8, 256, sh_tab ? sizeof(float) * 8 * 32 * BW_SROW : 0, s>>>(a, f);
+            if (sh_tab) {
+                LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bw_hits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * 32 * BW_SROW)));
+                k_bw_hits<true><<<ctx->num_sms * 8, 256, sizeof(float) * 8 * 32 * BW_SROW, s>>>(a, f);
+            } else {
+                k_bw_hits<false><<<ctx->num_sms * 8, 256, 0, s>>>(a, f);
+            }
             ctx->span_end(s);
             a.only_flag = legacy_flag;                // set on the device if the records did not fit (normally not)
             ctx->span_begin("k_backward_list", s); k_backward_list<<<GB, TB, 0, s>>>(a); ctx->span_end(s);

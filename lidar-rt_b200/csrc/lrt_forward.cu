@@ -515,7 +515,6 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                      float* out, float* accum_w, int32_t* hit_gidx, float* hit_t, float* hit_aux, int32_t* hit_cnt,
                      int cap, int32_t* slot_cnt, cudaStream_t s)
 {
-    (void)means; (void)scales; (void)rots; (void)opac;
     if (!ctx->built) { ctx->set_error("lrt_forward: no acceleration structure (call lrt_build first)"); return LRT_ERR_STATE; }
     if (P != ctx->P) { ctx->set_error("lrt_forward: P differs from the built structure"); return LRT_ERR_STATE; }
     if (mod != ctx->scale_modifier) { ctx->set_error("lrt_forward: scale_modifier differs from the built structure"); return LRT_ERR_STATE; }
@@ -651,6 +650,8 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                 LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sp_cnt, sizeof(int) * 2 * ((size_t)R + 1)));
                 LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sp_rec, sizeof(float4) * 4 * (size_t)capacity));
                 sp.ccnt = (int*)ctx->sp_cnt.p; sp.cbase = sp.ccnt + (R + 1); sp.srec = (float4*)ctx->sp_rec.p;
+                sp.tri = ctx->opt_triangle_depth; sp.mod = mod; sp.means = means; sp.scales = scales; sp.rots = rots; sp.opac = opac;
+                if (sp.tri && (!means || !scales || !rots || !opac)) { ctx->set_error("lrt_forward: LRT_OPT_TRIANGLE_DEPTH needs the Gaussian parameters"); return LRT_ERR_INVALID; }
                 size_t tb = 0;
                 LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (const int*)sp.ccnt, sp.cbase, R + 1, s));
                 LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sp_scan_tmp, tb));
@@ -676,8 +677,15 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                     k_sp_big<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
                 }
                 ctx->span_end(s);
-                LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));
-                ctx->span_begin("k_sp_slots", s); k_sp_slots<<<(R + 127) / 128, 128, SP_SLOTS_SMEM, s>>>(a, w, sp); ctx->span_end(s);
+                ctx->span_begin("k_sp_slots", s);
+                if (sp.tri) {
+                    LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));
+                    k_sp_slots<true><<<(R + 127) / 128, 128, SP_SLOTS_SMEM, s>>>(a, w, sp);
+                } else {
+                    LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));
+                    k_sp_slots<false><<<(R + 127) / 128, 128, SP_SLOTS_SMEM, s>>>(a, w, sp);
+                }
+                ctx->span_end(s);
                 ctx->span_begin("k_sp_colour", s);
                 if (a.sh_tab && ctx->sh_parts_vec) k_sp_colour<2><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
                 else if (sh_rows_aligned(a)) k_sp_colour<1><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);

@@ -32,7 +32,11 @@ struct SpBufs {
     int* ccnt;                      // (R + 1) candidates per ray that go through the stream (0: ray handed to the fallback)
     int* cbase;                     // (R + 1) exclusive scan of ccnt = first record of each ray's slice
     float4* srec;                   // the stream: 4 x float4 per candidate = SurfelRec with r3.w = t from the ray's origin
-    long long capacity;             // records the stream can hold
+    long long capacity;             // 64-byte records the stream can hold
+    // LRT_OPT_TRIANGLE_DEPTH: 8 x float4 per candidate — the record, then the proxy quad's four corners as build2DRectangle
+    // rounds them to fp32 (derived again from the caller's raw parameters)
+    int tri; float mod;
+    const float* means; const float* scales; const float* rots; const float* opac;
 };
 
 __global__ void __launch_bounds__(256) k_sp_counts(int R, WfBufs w, SpBufs sp)
@@ -44,14 +48,52 @@ __global__ void __launch_bounds__(256) k_sp_counts(int R, WfBufs w, SpBufs sp)
     sp.ccnt[r] = c;
 }
 
-// gather the record of candidate `key` and drop it at its sorted position of the stream
-__device__ __forceinline__ void sp_emit(const SurfelRec* __restrict__ rec_g, float4* __restrict__ dst, unsigned long long key)
+// gather the record of candidate `key` and drop it at sorted position i of the ray's slice of the stream
+__device__ __forceinline__ void sp_emit(const SurfelRec* __restrict__ rec_g, const SpBufs& sp, float4* __restrict__ slice, int i, unsigned long long key)
 {
     const int g = (int)(unsigned)(key & 0xffffffffull);
     const float4 r0 = ld_f4(&rec_g[g].r0), r1 = ld_f4(&rec_g[g].r1), r2 = ld_f4(&rec_g[g].r2);
     float4 r3 = ld_f4(&rec_g[g].r3);
     r3.w = __uint_as_float((unsigned)(key >> 32));
+    float4* dst = slice + (sp.tri ? 8 : 4) * (size_t)i;
     dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
+    if (sp.tri) {
+        // the quad's corners exactly as build2DRectangle leaves them in fp32 (primitive_utils.py:203-209; oracle derive()):
+        // world = R diag(sx f, sy f, 1) local + mu with local = (-1,1) (-1,-1) (1,1) (1,-1); scale_modifier plays no part
+        const float mu[3] = {sp.means[3 * (size_t)g], sp.means[3 * (size_t)g + 1], sp.means[3 * (size_t)g + 2]};
+        const float sc[2] = {sp.scales[2 * (size_t)g], sp.scales[2 * (size_t)g + 1]};
+        const float q[4] = {sp.rots[4 * (size_t)g], sp.rots[4 * (size_t)g + 1], sp.rots[4 * (size_t)g + 2], sp.rots[4 * (size_t)g + 3]};
+        Derived d;
+        derive_surfel(mu, sc, q, sp.opac[g], sp.mod, d);
+        const float ax = sc[0] * d.f, ay = sc[1] * d.f;
+        const float lx[4] = {-1.f, -1.f, 1.f, 1.f}, ly[4] = {1.f, -1.f, 1.f, -1.f};
+        float v[12];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) v[3 * c + k] = (lx[c] * (d.tu[k] * ax) + ly[c] * (d.tv[k] * ay)) + mu[k];
+        dst[4] = make_float4(v[0], v[1], v[2], v[3]); dst[5] = make_float4(v[4], v[5], v[6], v[7]);
+        dst[6] = make_float4(v[8], v[9], v[10], v[11]); dst[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// fp64 Moeller-Trumbore on the fp32 corners, the oracle's stand-in for OptiX's ray / triangle test (oracle tri_hit(), operation
+// for operation): the ray parameter of the hit, or -1
+__device__ __forceinline__ double sp_tri_hit(const float* o, const float* d, const float* A, const float* B, const float* C)
+{
+    const double e1[3] = {(double)B[0] - A[0], (double)B[1] - A[1], (double)B[2] - A[2]};
+    const double e2[3] = {(double)C[0] - A[0], (double)C[1] - A[1], (double)C[2] - A[2]};
+    const double p[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+    const double det = e1[0] * p[0] + e1[1] * p[1] + e1[2] * p[2];
+    if (!(det != 0.0)) return -1.0;
+    const double inv = 1.0 / det;
+    const double s[3] = {(double)o[0] - A[0], (double)o[1] - A[1], (double)o[2] - A[2]};
+    const double u = (s[0] * p[0] + s[1] * p[1] + s[2] * p[2]) * inv;
+    if (!(u >= 0.0 && u <= 1.0)) return -1.0;
+    const double q[3] = {s[1] * e1[2] - s[2] * e1[1], s[2] * e1[0] - s[0] * e1[2], s[0] * e1[1] - s[1] * e1[0]};
+    const double v = (d[0] * q[0] + d[1] * q[1] + d[2] * q[2]) * inv;
+    if (!(v >= 0.0 && u + v <= 1.0)) return -1.0;
+    return (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]) * inv;
 }
 
 // One warp per ray.
@@ -71,12 +113,12 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
             continue;
         }
         const long long base = sp.cbase[r];
-        if (base + n > sp.capacity) {                              // the stream is full: this ray takes the per-ray fallback
+        if ((base + n) * (sp.tri ? 2 : 1) > sp.capacity) {                              // the stream is full: this ray takes the per-ray fallback
             if (lane == 0) atomicOr(w.hit_count + r, WF_TAINT);
             continue;
         }
         const unsigned long long* bin = w.bins + (size_t)r * w.hcap;
-        float4* dst = sp.srec + 4 * (size_t)base;
+        float4* dst = sp.srec + (sp.tri ? 8 : 4) * (size_t)base;
         // Up to 64 candidates (nearly every ray): the network runs on 32-bit keys — the depth's bits with the low 5 (6) replaced by
         // the candidate's slot — at half the shuffles, compares and selects of 64-bit (t, id) keys; the full key is then fetched
         // from the lane that holds it. The stream comes out sorted up to 2^-17 t, which pass A's margin allows for (wf_margin()):
@@ -86,7 +128,7 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
             unsigned k32 = lane < n ? (((unsigned)(k >> 32) & ~31u) | (unsigned)lane) : 0xffffffffu;
             k32 = warp_sort32(k32, lane);
             const unsigned long long ks = __shfl_sync(FULL, k, (int)(k32 & 31u));
-            if (lane < n) sp_emit(rec_g, dst + 4 * lane, ks);
+            if (lane < n) sp_emit(rec_g, sp, dst, lane, ks);
             continue;
         }
         if (n <= 64) {
@@ -98,8 +140,8 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
                 const int s0 = (int)(a0 & 63u), s1 = (int)(a1 & 63u);
                 const unsigned long long x0 = __shfl_sync(FULL, k0, s0 & 31), y0 = __shfl_sync(FULL, k1, s0 & 31);
                 const unsigned long long x1 = __shfl_sync(FULL, k0, s1 & 31), y1 = __shfl_sync(FULL, k1, s1 & 31);
-                sp_emit(rec_g, dst + 4 * lane, (s0 >> 5) ? y0 : x0);
-                if (lane + 32 < n) sp_emit(rec_g, dst + 4 * (lane + 32), (s1 >> 5) ? y1 : x1);
+                sp_emit(rec_g, sp, dst, lane, (s0 >> 5) ? y0 : x0);
+                if (lane + 32 < n) sp_emit(rec_g, sp, dst, lane + 32, (s1 >> 5) ? y1 : x1);
             }
             continue;
         }
@@ -109,7 +151,7 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
             for (int j = 0; j < 4; j++) k[j] = lane + 32 * j < n ? bin[lane + 32 * j] : LRT_KEY_EMPTY;
             warp_sort_regs<4>(k, lane);
 #pragma unroll
-            for (int j = 0; j < 4; j++) if (lane + 32 * j < n) sp_emit(rec_g, dst + 4 * (lane + 32 * j), k[j]);
+            for (int j = 0; j < 4; j++) if (lane + 32 * j < n) sp_emit(rec_g, sp, dst, lane + 32 * j, k[j]);
             continue;
         }
         if (n <= 256) {
@@ -118,7 +160,7 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
             for (int j = 0; j < 8; j++) k[j] = lane + 32 * j < n ? bin[lane + 32 * j] : LRT_KEY_EMPTY;
             warp_sort_regs<8>(k, lane);
 #pragma unroll
-            for (int j = 0; j < 8; j++) if (lane + 32 * j < n) sp_emit(rec_g, dst + 4 * (lane + 32 * j), k[j]);
+            for (int j = 0; j < 8; j++) if (lane + 32 * j < n) sp_emit(rec_g, sp, dst, lane + 32 * j, k[j]);
             continue;
         }
         const int m = WF_HCAP;                                     // 257..512 candidates: this warp's slice of shared memory
@@ -135,7 +177,7 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
                 __syncwarp(FULL);
             }
         }
-        for (int i = lane; i < n; i += 32) sp_emit(rec_g, dst + 4 * i, keys[i]);
+        for (int i = lane; i < n; i += 32) sp_emit(rec_g, sp, dst, i, keys[i]);
         __syncwarp(FULL);
     }
 }
@@ -176,8 +218,16 @@ __device__ __forceinline__ void sp_cp_async_wait_all() { asm volatile("cp.async.
 // registers, the inner parts on demand) waiting five times per four candidates, every wait a full L2 / DRAM round trip
 // (profiles/r2_b_split_first_ncu.txt). Columns are [slot][thread]: consecutive lanes touch consecutive 16-byte words (no bank
 // conflicts) and no thread ever reads another thread's column, so no block-level barrier is needed.
+// TRI (LRT_OPT_TRIANGLE_DEPTH): a candidate's hits come from the reference's literal proxy — the two triangles (v0,v1,v2), (v2,v3,v1)
+// over the fp32-rounded corners, fp64 Moeller-Trumbore like the oracle's ORC_TRIANGLES mode — instead of the analytic quad: keys are
+// (t', primitive id = 2 g + triangle), a candidate can give two slots (a ray through the shared diagonal), the depth of a hit is
+// the triangle's. Records are 128 bytes, staged two at a time.
+template <bool TRI>
 __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs a, WfBufs w, SpBufs sp)
 {
+    constexpr int RS = TRI ? 8 : 4;                                 // float4 per record
+    constexpr int NB = TRI ? SP_BATCH / 2 : SP_BATCH;               // records staged per wait (same bytes either way)
+    constexpr int NH = TRI ? 2 : 1;                                 // possible hits per candidate
     extern __shared__ __align__(16) unsigned char sp_smem[];
     float4 (*s_st)[128] = reinterpret_cast<float4 (*)[128]>(sp_smem);                                      // [SP_BATCH * 4][128] staging
     unsigned long long (*s_kb)[128] = reinterpret_cast<unsigned long long (*)[128]>(sp_smem + 128 * SP_BATCH * 64);   // the round's slots, ascending (t', id)
@@ -191,7 +241,7 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
         const int n = hc;
         const float em = __int_as_float(w.emax[r]);
         const int nw = min(w.nwild[r], n);                         // wild candidates (key t = 0): the first nw of the sorted stream, tested in every round
-        const float4* __restrict__ rec = sp.srec + 4 * (size_t)sp.cbase[r];              // candidate i = rec[4 i .. 4 i + 3]
+        const float4* __restrict__ rec = sp.srec + RS * (size_t)sp.cbase[r];             // candidate i = rec[RS i .. RS i + RS - 1]
         FwdRay q;
         fwd_ray_init(q, r, a);
         int pos = nw;                                              // first candidate of the sorted part that can still matter
@@ -206,7 +256,7 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
                 while (hi > pos) {
                     float tv[8];
 #pragma unroll
-                    for (int k = 0; k < 8; k++) tv[k] = hi - 1 - k >= pos ? __ldg(reinterpret_cast<const float*>(rec + 4 * (hi - 1 - k) + 3) + 3) : -1.0f;
+                    for (int k = 0; k < 8; k++) tv[k] = hi - 1 - k >= pos ? __ldg(reinterpret_cast<const float*>(rec + RS * (hi - 1 - k) + 3) + 3) : -1.0f;
                     int back = 0;
 #pragma unroll
                     for (int k = 0; k < 8; k++) if (back == k && hi - 1 - k >= pos && !(tv[k] < thr)) back = k + 1;
@@ -221,40 +271,53 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
             bool done = false;
             for (int seg = nw > 0 ? 0 : 1; seg < 2; seg++) {       // segment 0: the wild candidates, no window; segment 1: the sorted rest
             const int i_lo = seg ? pos : 0, i_hi = seg ? n : nw;
-            for (int i0 = i_lo; i0 < i_hi && !done; i0 += SP_BATCH) {
+            for (int i0 = i_lo; i0 < i_hi && !done; i0 += NB) {
                 {
-                    const float4* src = rec + 4 * (size_t)i0;
-                    const int nv = 4 * min(SP_BATCH, i_hi - i0);
+                    const float4* src = rec + RS * (size_t)i0;
+                    const int nv = RS * min(NB, i_hi - i0);
 #pragma unroll
-                    for (int v = 0; v < 4 * SP_BATCH; v++) if (v < nv) sp_cp_async16(&s_st[v][tx], src + v);
+                    for (int v = 0; v < RS * NB; v++) if (v < nv) sp_cp_async16(&s_st[v][tx], src + v);
                     sp_cp_async_wait_all();
                 }
                 // phase 1, branch-free: the exact test and the opacity of all SP_BATCH staged candidates, independent of each other
                 // (the instruction streams interleave: this kernel runs few warps per scheduler and every dependent chain of
                 // shared-memory loads, divisions and expf would otherwise be paid in full, one candidate after the other)
-                float t0v[SP_BATCH], alv[SP_BATCH];
-                unsigned long long keyv[SP_BATCH];
-                bool hitv[SP_BATCH];
+                float t0v[NB], alv[NB * NH];
+                unsigned long long keyv[NB * NH];
+                bool hitv[NB * NH];
 #pragma unroll
-                for (int k = 0; k < SP_BATCH; k++) {
-                    const float4 a0 = s_st[4 * k][tx], a1 = s_st[4 * k + 1][tx], a2 = s_st[4 * k + 2][tx], a3 = s_st[4 * k + 3][tx];
+                for (int k = 0; k < NB; k++) {
+                    const float4 a0 = s_st[RS * k][tx], a1 = s_st[RS * k + 1][tx], a2 = s_st[RS * k + 2][tx], a3 = s_st[RS * k + 3][tx];
                     t0v[k] = a3.w;
-                    // quad_hit(), operation for operation
-                    const float c0 = a0.x - rs.ox, c1 = a0.y - rs.oy, c2 = a0.z - rs.oz;
-                    const float den = a3.x * rs.dx + a3.y * rs.dy + a3.z * rs.dz;
-                    const float num = a3.x * c0 + a3.y * c1 + a3.z * c2;
-                    const float t = num / den;
-                    bool h = t > 0.0f;
-                    {
+                    float th[NH];
+                    if (TRI) {
+                        const float4 p4 = s_st[RS * k + 4][tx], p5 = s_st[RS * k + 5][tx], p6 = s_st[RS * k + 6][tx];
+                        const float v0[3] = {p4.x, p4.y, p4.z}, v1[3] = {p4.w, p5.x, p5.y}, v2[3] = {p5.z, p5.w, p6.x}, v3[3] = {p6.y, p6.z, p6.w};
+                        const float oo[3] = {rs.ox, rs.oy, rs.oz}, dd[3] = {rs.dx, rs.dy, rs.dz};
+                        // prim 2g = (v0,v1,v2), prim 2g+1 = (v2,v3,v1): primitive_utils.py:212-221; oracle test_gauss()
+                        const double ta = sp_tri_hit(oo, dd, v0, v1, v2), tb = sp_tri_hit(oo, dd, v2, v3, v1);
+                        th[0] = (float)ta; th[NH - 1] = (float)tb;
+                        hitv[NH * k] = ta > 0.0 && th[0] > 0.0f && th[0] < LRT_TMAX;
+                        hitv[NH * k + NH - 1] = tb > 0.0 && th[NH - 1] > 0.0f && th[NH - 1] < LRT_TMAX;
+                    } else {
+                        // quad_hit(), operation for operation
+                        const float c0 = a0.x - rs.ox, c1 = a0.y - rs.oy, c2 = a0.z - rs.oz;
+                        const float den = a3.x * rs.dx + a3.y * rs.dy + a3.z * rs.dz;
+                        const float num = a3.x * c0 + a3.y * c1 + a3.z * c2;
+                        const float t = num / den;
+                        bool h = t > 0.0f;
                         const float r0 = (rs.ox + t * rs.dx) - a0.x, r1 = (rs.oy + t * rs.dy) - a0.y, r2 = (rs.oz + t * rs.dz) - a0.z;
                         const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
                         const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
                         h = h && (fabsf(u) <= a0.w && fabsf(v) <= a0.w) && (t < LRT_TMAX);
+                        hitv[k] = h; th[0] = t;
                     }
-                    hitv[k] = h;
-                    keyv[k] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)__float_as_int(a2.w);
-                    // its opacity, as fwd_shade_round() computes it (forward.cu:212-251)
-                    {
+#pragma unroll
+                    for (int hh = 0; hh < NH; hh++) {
+                        const float t = th[hh];
+                        keyv[NH * k + hh] = ((unsigned long long)__float_as_uint(t) << 32) |
+                                            (TRI ? 2u * (unsigned)__float_as_int(a2.w) + (unsigned)hh : (unsigned)__float_as_int(a2.w));
+                        // its opacity, as fwd_shade_round() computes it (forward.cu:212-251)
                         const float dpt = t + q.base;
                         const float x0 = q.o[0] + dpt * q.d[0], x1 = q.o[1] + dpt * q.d[1], x2 = q.o[2] + dpt * q.d[2];
                         const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
@@ -263,20 +326,21 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
                         const float cosv = -((a0.x - q.o[0]) * a3.x + (a0.y - q.o[1]) * a3.y + (a0.z - q.o[2]) * a3.z);
                         const float rho = u * u + v * v;
                         const float power = -0.5f * rho;
-                        alv[k] = (cosv == 0.0f || power > 0.0f) ? 0.0f : fminf(LRT_ALPHA_MAX, a1.w * expf(power));
+                        alv[NH * k + hh] = (cosv == 0.0f || power > 0.0f) ? 0.0f : fminf(LRT_ALPHA_MAX, a1.w * expf(power));
                     }
                 }
                 // phase 2, in order: window stop, k-buffer
 #pragma unroll
-                for (int k = 0; k < SP_BATCH; k++) {
+                for (int kk = 0; kk < NB * NH; kk++) {
+                    const int k = kk / NH;
                     if (i0 + k >= i_hi || done) continue;
-                    if (seg && cnt == LRT_KBUF) {
+                    if (seg && cnt == LRT_KBUF && kk % NH == 0) {
                         const float t16 = __uint_as_float((unsigned)(klast >> 32)) + q.base;
                         if (t0v[k] - t16 > wf_margin(t16, em)) { done = true; i_end = i0 + k; continue; }
                     }
-                    if (!hitv[k]) continue;
-                    const unsigned long long key = keyv[k];
-                    const float alpha = alv[k];
+                    if (!hitv[kk]) continue;
+                    const unsigned long long key = keyv[kk];
+                    const float alpha = alv[kk];
                     if (cnt == LRT_KBUF && key >= klast) continue;                              // behind the current 16th
                     if (cnt < LRT_KBUF && (cnt == 0 || key > klast)) {                          // the usual case: append
                         s_kb[cnt][tx] = key; s_al[cnt][tx] = alpha; cnt++; klast = key;
@@ -301,7 +365,7 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
                 for (int j = 0; j < 4; j++) {
                     if (i4 + j >= cnt || terminated) continue;
                     const unsigned long long key = kq[j];
-                    const int g = (int)(unsigned)(key & 0xffffffffull);
+                    const int g = TRI ? (int)((unsigned)(key & 0xffffffffull) >> 1) : (int)(unsigned)(key & 0xffffffffull);     // gidx = pidx / 2
                     q.nslots++;
                     q.dpt = __uint_as_float((unsigned)(key >> 32)) + q.base;              // forward.cu:212
                     if (q.dpt < LRT_MIN_T) continue;                                      // :214

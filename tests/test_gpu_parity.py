@@ -324,6 +324,35 @@ def test_very_long_candidate_bins_and_bin_overflow(ctx, oracle32, n_stack):
     assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
 
 
+@pytest.mark.parametrize("P,H,W,seed", [(200_000, 16, 512, 5), (30_000, 32, 96, 7)])
+def test_triangle_depth_mode_vs_triangle_oracle(ctx, oracle32, P, H, W, seed):
+    """LRT_OPT_TRIANGLE_DEPTH: hits and depths from the reference's literal proxy (two fp32 triangles per Gaussian, fp64
+    Moeller-Trumbore) — the counterpart of the oracle's ORC_TRIANGLES mode, which stands in for what forward.cu:319 reads from OptiX
+    (optixGetRayTmax). Hit lists and slot counts bit-exact against that mode; gradients by value."""
+    from lidar_rt_b200 import native
+    from oracle.oracle import ORC_TRIANGLES
+    sc = syn.make_street_scene(P, seed=seed)
+    o, d = syn.ray_patch(H, W, frame=2)
+    rng = np.random.default_rng(seed)
+    dL = np.zeros((H * W, 9), np.float32); dL[:, :4] = rng.standard_normal((H * W, 4))
+    try:
+        ctx.set_option(native.OPT_TRIANGLE_DEPTH, 1)
+        res = run_cuda(ctx, o, d, as_dict(sc), 3, dL, cap=96)
+    finally:
+        ctx.set_option(native.OPT_TRIANGLE_DEPTH, 0)
+    args = (o, d, BG, sc.means, sc.scales, sc.rots, sc.opac, sc.shs, 3)
+    f = oracle32.forward(*args, flags=ORC_BVH | ORC_TRIANGLES, cap=96)
+    assert hit_lists(res) == oracle_lists(f), "hit indices must be bit-exact against the triangle-mode oracle"
+    assert np.array_equal(res["slot_cnt"], f["slot_cnt"])
+    assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
+    b = oracle32.backward(*args, f["out"], dL, flags=ORC_BVH | ORC_TRIANGLES)
+    for k in ("means", "shs", "opac", "scales", "rots"):
+        grad_close(res[f"g_{k}"], b[k], GRAD_REL, f"d_{k}")
+    # and it is a different answer from the analytic quad's on some rays (otherwise the option would be pointless to test)
+    res0 = run_cuda(ctx, o, d, as_dict(sc), 3, cap=96)
+    assert not np.array_equal(res0["out"][:, 3], res["out"][:, 3])
+
+
 def test_full_size_properties(ctx):
     """BASELINE config #2 shape (1M Gaussians, 64 x 2650 rays): size-independent invariants."""
     sc = syn.make_street_scene(1_000_000, seed=1)
