@@ -237,6 +237,8 @@ int lrt_densify_rows(lrt_ctx* ctx, int P, const uint8_t* clone_mask, const uint8
  *   LRT_OPT_WAVEFRONT_SHADE wavefront compositing: 0 = one warp per ray, 1 = warp sort + one thread per ray,
  *                           2 = 1 with pipelined record loads and slot opacities computed on acceptance,
  *                           3 = split passes (default): sort + gather into a sorted record stream, then slots / colour / fold
+ *   LRT_OPT_SPLIT_FUSED     split passes: 1 = the bin sort and the rounds' slot logic run in one kernel, one warp per ray, straight
+ *                           from the surfel records (default); 0 = two kernels with a sorted record stream in between
  *   LRT_OPT_TRIANGLE_DEPTH  1 = the hits of a ray and their depths come from the reference's literal proxy, the two triangles
  *                           (v0,v1,v2), (v2,v3,v1) over the corners build2DRectangle rounds to fp32 (primitive_utils.py:203-221),
  *                           intersected in fp64 like the oracle's ORC_TRIANGLES mode, instead of the analytic quad |u|,|v| <= f:
@@ -246,7 +248,7 @@ int lrt_densify_rows(lrt_ctx* ctx, int P, const uint8_t* clone_mask, const uint8
  *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build) */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,
                   LRT_OPT_BACKWARD_KERNEL = 5, LRT_OPT_WAVEFRONT_SHADE = 6, LRT_OPT_KERNEL_TIMING = 7,
-                  LRT_OPT_SORT_RAYS = 8, LRT_OPT_BEAM_CELL_PCT = 9, LRT_OPT_TRIANGLE_DEPTH = 10 };
+                  LRT_OPT_SORT_RAYS = 8, LRT_OPT_BEAM_CELL_PCT = 9, LRT_OPT_TRIANGLE_DEPTH = 10, LRT_OPT_SPLIT_FUSED = 11 };
 int lrt_set_option(lrt_ctx* ctx, int option, int value);
 
 /* Introspection for tests / benchmarks (host pointers). */

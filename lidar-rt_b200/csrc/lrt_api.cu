@@ -194,6 +194,7 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
     case LRT_OPT_BACKWARD_KERNEL: if (value < 0 || value > 2) break; ctx->opt_backward_kernel = value; return LRT_OK;
     case LRT_OPT_MORTON_BITS: if (value != 30 && value != 32 && value != 63) break; ctx->opt_morton_bits = value; return LRT_OK;
     case LRT_OPT_VECTOR_ATOMICS: if (value != 0 && value != 1) break; ctx->opt_vector_atomics = value; return LRT_OK;
+    case LRT_OPT_SPLIT_FUSED: if (value != 0 && value != 1) break; ctx->opt_split_fused = value; return LRT_OK;
     case LRT_OPT_TRIANGLE_DEPTH: if (value != 0 && value != 1) break; ctx->opt_triangle_depth = value; return LRT_OK;
     default: break;
     }

@@ -666,26 +666,40 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                     if (!a.hit_gidx) { a.hit_gidx = i_g; a.hit_t = i_t; a.hit_cnt = i_c; a.cap = icap; }
                     a.hit_aux = i_aux;
                 }
-                ctx->span_begin("k_sp_sort", s);
-                k_sp_counts<<<(R + 1 + 255) / 256, 256, 0, s>>>(R, w, sp);
-                LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->sp_scan_tmp.p, tb, (const int*)sp.ccnt, sp.cbase, R + 1, s));
-                k_sp_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(bv, a, w, sp);
-                {   // the few bins beyond 512 candidates: one block each (sort in place, then gather)
-                    const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
-                    LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
-                    k_sp_big<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
-                }
-                ctx->span_end(s);
-                ctx->span_begin("k_sp_slots", s);
-                if (sp.tri) {
-                    LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));
-                    k_sp_slots<true><<<(R + 127) / 128, 128, SP_SLOTS_SMEM, s>>>(a, w, sp);
+                const bool fused = ctx->opt_split_fused && !sp.tri;
+                if (fused) {
+                    // one warp per ray: sort + the rounds' slot logic, no record stream (lrt_split.cuh)
+                    ctx->span_begin("k_sp_warp", s);
+                    k_sp_warp<<<min((R + 3) / 4, ctx->num_sms * 24), 128, 0, s>>>(bv, a, w);
+                    {
+                        const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
+                        LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
+                        k_sp_big<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
+                    }
+                    ctx->span_end(s);
                 } else {
-                    LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));
-                    k_sp_slots<false><<<(R + 127) / 128, 128, SP_SLOTS_SMEM, s>>>(a, w, sp);
+                    ctx->span_begin("k_sp_sort", s);
+                    k_sp_counts<<<(R + 1 + 255) / 256, 256, 0, s>>>(R, w, sp);
+                    LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->sp_scan_tmp.p, tb, (const int*)sp.ccnt, sp.cbase, R + 1, s));
+                    k_sp_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(bv, a, w, sp);
+                    {   // the few bins beyond 512 candidates: one block each (sort in place, then gather)
+                        const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
+                        LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
+                        k_sp_big<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
+                    }
+                    ctx->span_end(s);
+                    ctx->span_begin("k_sp_slots", s);
+                    if (sp.tri) {
+                        LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));
+                        k_sp_slots<true><<<(R + 127) / 128, 128, SP_SLOTS_SMEM, s>>>(a, w, sp);
+                    } else {
+                        LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_sp_slots<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SLOTS_SMEM));
+                        k_sp_slots<false><<<(R + 127) / 128, 128, SP_SLOTS_SMEM, s>>>(a, w, sp);
+                    }
+                    ctx->span_end(s);
                 }
-                ctx->span_end(s);
                 ctx->span_begin("k_sp_colour", s);
                 if (a.sh_tab && ctx->sh_parts_vec) k_sp_colour<2><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
                 else if (sh_rows_aligned(a)) k_sp_colour<1><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);

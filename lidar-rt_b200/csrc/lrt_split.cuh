@@ -182,6 +182,283 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
     }
 }
 
+// ---- fused form (default, LRT_OPT_SPLIT_FUSED = 1): k_sp_sort and pass A as ONE kernel with one WARP per ray -------------------
+// The two-kernel form moves every candidate's 64-byte record three times (gather, stream write, stream read: 0.87 GB per frame
+// that SURVEY 8d does not know) so that a lone thread can walk them without dependent gathers — and that thread still waits on
+// memory most of the time (17 % of the warps resident, 27 % issue slots used: profiles/r2_r_top_kernels_ncu.txt). Here the warp
+// that sorted a ray's bin keeps the sorted keys in shared memory and runs the reference's rounds itself: per step the 32 lanes
+// gather and test 32 candidates (exact test from the re-based origin AND the blending opacity, arithmetic of k_sp_slots), the
+// accepted ones are compacted in bin order into the round's slot array, and the warp folds the 16 slots in order. No record is
+// written anywhere; 32 gathers are in flight per warp instead of 4 per thread. Near-tie reordering (re-based depths out of bin
+// order) falls back to a warp sort of the collected slots. Outputs are those of k_sp_slots, bit for bit.
+__device__ __forceinline__ void sp_test_candidate(const SurfelRec* __restrict__ rec, unsigned long long ck, const RaySetup& rs, const FwdRay& q,
+                                                  unsigned long long& key, float& alpha)
+{
+    key = LRT_KEY_EMPTY; alpha = 0.0f;
+    const int g = (int)(unsigned)(ck & 0xffffffffull);
+    const float4 a0 = ld_f4(&rec[g].r0), a1 = ld_f4(&rec[g].r1), a2 = ld_f4(&rec[g].r2), a3 = ld_f4(&rec[g].r3);
+    // quad_hit(), operation for operation
+    const float c0 = a0.x - rs.ox, c1 = a0.y - rs.oy, c2 = a0.z - rs.oz;
+    const float den = a3.x * rs.dx + a3.y * rs.dy + a3.z * rs.dz;
+    const float num = a3.x * c0 + a3.y * c1 + a3.z * c2;
+    const float t = num / den;
+    if (!(t > 0.0f)) return;
+    {
+        const float r0 = (rs.ox + t * rs.dx) - a0.x, r1 = (rs.oy + t * rs.dy) - a0.y, r2 = (rs.oz + t * rs.dz) - a0.z;
+        const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
+        const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+        if (!(fabsf(u) <= a0.w && fabsf(v) <= a0.w) || !(t < LRT_TMAX)) return;
+    }
+    key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)g;
+    // its opacity, as fwd_shade_round() computes it (forward.cu:212-251)
+    const float dpt = t + q.base;
+    const float x0 = q.o[0] + dpt * q.d[0], x1 = q.o[1] + dpt * q.d[1], x2 = q.o[2] + dpt * q.d[2];
+    const float r0 = x0 - a0.x, r1 = x1 - a0.y, r2 = x2 - a0.z;
+    const float u = a1.x * r0 + a1.y * r1 + a1.z * r2;
+    const float v = a2.x * r0 + a2.y * r1 + a2.z * r2;
+    const float cosv = -((a0.x - q.o[0]) * a3.x + (a0.y - q.o[1]) * a3.y + (a0.z - q.o[2]) * a3.z);
+    const float rho = u * u + v * v;
+    const float power = -0.5f * rho;
+    alpha = (cosv == 0.0f || power > 0.0f) ? 0.0f : fminf(LRT_ALPHA_MAX, a1.w * expf(power));
+}
+
+// warp-wide bitonic sort of one (64-bit key, float value) pair per lane, ascending by key
+__device__ __forceinline__ void warp_sort32_kv(unsigned long long& k, float& v, int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, stride);
+            const float ov = __shfl_xor_sync(0xffffffffu, v, stride);
+            const bool take_min = (((lane & size) == 0) == ((lane & stride) == 0));
+            const bool other = take_min ? (ok < k) : (k < ok);
+            k = other ? ok : k; v = other ? ov : v;
+        }
+    }
+}
+
+__device__ __forceinline__ void sp_slots_ray(const unsigned long long* keys, int n, int nw, int r, float em, const BvhView& bvh, const FwdArgs& a,
+                                             const WfBufs& w, unsigned long long* sk, float* sa, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    const SurfelRec* __restrict__ rec = bvh.rec_g;
+    FwdRay q;
+    fwd_ray_init(q, r, a);
+    for (;;) {
+        RaySetup rs;
+        ray_setup(rs, q.o, q.d, q.base);
+        const float thr = q.base - 2.0f * wf_margin(q.base, em);
+        int pos;                                                   // first candidate of the sorted part at or beyond thr (warp-uniform lower bound)
+        {
+            int lo = nw, hi = n;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__uint_as_float((unsigned)(keys[mid] >> 32)) < thr) lo = mid + 1; else hi = mid;
+            }
+            pos = lo;
+        }
+        // the round's slots: accepted candidates in bin order, compacted into sk / sa. Wild candidates (keys 0 .. nw) first.
+        int have = 0;                                              // accepted so far (may exceed 32: then only counted)
+        int have_wild = 0;                                         // ... of them from the wild segment (arbitrary depths, not in bin order)
+        for (int seg = nw > 0 ? 0 : 1; seg < 2; seg++) {
+            int i0 = seg ? pos : 0;
+            const int i_hi = seg ? n : nw;
+            if (seg) have_wild = have;
+            for (; i0 < i_hi; i0 += 32) {
+                if (seg && have - have_wild >= LRT_KBUF && have_wild + LRT_KBUF <= 32) {      // 16 accepted from the sorted part: does everything from here on lie safely behind the 16th of them?
+                    const float t16 = __uint_as_float((unsigned)(sk[have_wild + LRT_KBUF - 1] >> 32)) + q.base;
+                    if (__uint_as_float((unsigned)(keys[i0] >> 32)) - t16 > wf_margin(t16, em)) break;
+                }
+                unsigned long long key = LRT_KEY_EMPTY; float alpha = 0.0f;
+                if (i0 + lane < i_hi) sp_test_candidate(rec, keys[i0 + lane], rs, q, key, alpha);
+                const unsigned vm = __ballot_sync(FULL, key != LRT_KEY_EMPTY);
+                const int at = have + __popc(vm & ((1u << lane) - 1u));
+                if (key != LRT_KEY_EMPTY && at < 32) { sk[at] = key; sa[at] = alpha; }
+                have += __popc(vm);
+                __syncwarp(FULL);
+                if (have > 32) break;                              // more than 32 accepted: handled below
+            }
+            if (have > 32) break;
+        }
+        int nvalid = min(have, 32);
+        // accepted keys must ascend (re-basing can swap near-ties, wild candidates arrive out of order): otherwise sort the
+        // collected slots; more than 32 collected means a window of ties wider than the slot array: take the general path
+        {
+            const unsigned long long mine = lane < nvalid ? sk[lane] : LRT_KEY_EMPTY;
+            const unsigned long long prev = __shfl_up_sync(FULL, mine, 1);
+            const bool bad = lane > 0 && lane < nvalid && prev > mine;
+            if (__ballot_sync(FULL, bad) != 0 || have > 32) {
+                if (have > 32) {
+                    // general path: every candidate from the round's start, 32 at a time, keeping the 32 smallest (t', id) with their
+                    // opacities (bitonic merge); stops like the fast path, on the true 16th
+                    unsigned long long best = LRT_KEY_EMPTY; float bal = 0.0f;
+                    for (int seg = nw > 0 ? 0 : 1; seg < 2; seg++) {
+                        const int i_hi = seg ? n : nw;
+                        for (int i0 = seg ? pos : 0; i0 < i_hi; i0 += 32) {
+                            if (seg) {
+                                const unsigned long long k16 = __shfl_sync(FULL, best, LRT_KBUF - 1);
+                                if (k16 != LRT_KEY_EMPTY) {
+                                    const float t16 = __uint_as_float((unsigned)(k16 >> 32)) + q.base;
+                                    if (__uint_as_float((unsigned)(keys[i0] >> 32)) - t16 > wf_margin(t16, em)) break;
+                                }
+                            }
+                            unsigned long long key = LRT_KEY_EMPTY; float alpha = 0.0f;
+                            if (i0 + lane < i_hi) sp_test_candidate(rec, keys[i0 + lane], rs, q, key, alpha);
+                            warp_sort32_kv(key, alpha, lane);
+                            const unsigned long long rk = __shfl_sync(FULL, key, 31 - lane);
+                            const float ra = __shfl_sync(FULL, alpha, 31 - lane);
+                            if (rk < best) { best = rk; bal = ra; }                      // bitonic: element-wise minimum of (best, reversed new)
+                            warp_sort32_kv(best, bal, lane);
+                        }
+                    }
+                    sk[lane] = best; sa[lane] = bal;
+                    nvalid = __popc(__ballot_sync(FULL, best != LRT_KEY_EMPTY));
+                } else {
+                    unsigned long long k = mine; float v = lane < nvalid ? sa[lane] : 0.0f;
+                    warp_sort32_kv(k, v, lane);
+                    sk[lane] = k; sa[lane] = v;
+                }
+                __syncwarp(FULL);
+            }
+        }
+        // the round's compositing (fwd_shade_round()) without the colour. Lane i owns slot i: which slots contribute (:214, :220-224,
+        // alpha >= 1/255) is decided by all lanes at once; only the transmittance / depth chain over the contributing slots is
+        // walked in order (two shuffles and six float operations per hit instead of the whole per-slot body on every lane: that
+        // loop was 61 % of the kernel's instructions, profiles/r2_u_warp_ncu.txt); every owner then commits its own hit.
+        const int nr = nvalid < LRT_KBUF ? nvalid : LRT_KBUF;
+        bool terminated = false;
+        {
+            const unsigned long long key = lane < nr ? sk[lane] : 0ull;
+            const float alpha = lane < nr ? sa[lane] : 0.0f;
+            const int g = (int)(unsigned)(key & 0xffffffffull);
+            const float dpt = __uint_as_float((unsigned)(key >> 32)) + q.base;           // forward.cu:212
+            const bool okd = lane < nr && !(dpt < LRT_MIN_T);                            // :214
+            const unsigned okm = __ballot_sync(FULL, okd);
+            // :220-224: `last` is the id of the nearest slot in front that passed the depth test (a skipped duplicate leaves it unchanged)
+            const unsigned front = okm & ((1u << lane) - 1u);
+            const int gfront = __shfl_sync(FULL, g, front ? 31 - __clz(front) : 0);
+            const bool contrib = okd && g != (front ? gfront : q.last) && !(alpha < 1.0f / 255.0f);
+            const unsigned cm = __ballot_sync(FULL, contrib);
+            float myT = 0.0f;
+            int stop = nr;                                                               // slot whose testT fell below T_MIN (:253-257)
+            for (unsigned m = cm; m;) {
+                const int i = __ffs(m) - 1;
+                m &= m - 1;
+                const float al = __shfl_sync(FULL, alpha, i), dp = __shfl_sync(FULL, dpt, i);
+                q.testT = q.T * (1.0f - al);
+                if (q.testT < LRT_T_MIN) { terminated = true; stop = i; break; }
+                const float wgt = al * q.T;
+                q.Dp += wgt * dp; q.W += wgt;
+                myT = lane == i ? q.T : myT;
+                q.T = q.testT;
+            }
+            q.nslots += terminated ? stop + 1 : nr;
+            const unsigned done = cm & ((1u << stop) - 1u);                              // stop <= 16: the contributing slots in front of it
+            if (contrib && lane < stop) {
+                atomicAdd(a.accum_w + g, alpha * myT);                                   // :272
+                const int at_k = q.ncontrib + __popc(done & ((1u << lane) - 1u));
+                if (at_k < a.cap) {
+                    const size_t at = (size_t)at_k * a.R + q.r;
+                    a.hit_gidx[at] = g;
+                    a.hit_t[at] = dpt;
+                    reinterpret_cast<float*>(a.hit_aux + at)[0] = alpha;                  // colour: k_sp_colour
+                }
+            }
+            q.ncontrib += __popc(done);
+            if (!terminated && nr > 0) {
+                q.dpt = __shfl_sync(FULL, dpt, nr - 1);
+                if (okm) q.last = __shfl_sync(FULL, g, 31 - __clz(okm));
+            }
+        }
+        __syncwarp(FULL);
+        if (terminated || q.testT < LRT_T_MIN || nvalid < LRT_KBUF) break;                // :282-285
+        q.base = (float)((double)q.dpt + LRT_STEP_EPS);                                   // :288
+    }
+    if (lane == 0) {
+        float* op = a.out + (size_t)LRT_NCH * q.r;                                        // :296-305 minus the colour channels (k_sp_fold)
+        op[3] = q.Dp; op[4] = q.W; op[5] = 0.f; op[6] = 0.f; op[7] = 0.f; op[8] = q.T;
+        a.hit_cnt[q.r] = q.ncontrib;
+        if (a.slot_cnt) a.slot_cnt[q.r] = q.nslots;
+        if (q.ncontrib > a.cap) w.ov_list[atomicAdd(w.counts + 12, 1)] = q.r;             // list truncated: the ray is redone per ray
+    }
+}
+
+#ifndef LRT_WARP_MIN_BLOCKS
+#define LRT_WARP_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, LRT_WARP_MIN_BLOCKS) k_sp_warp(BvhView bvh, FwdArgs a, WfBufs w)
+{
+    __shared__ unsigned long long s_keys[4][WF_HCAP];
+    __shared__ unsigned long long s_sk[4][32];
+    __shared__ float s_sa[4][32];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned long long* keys = s_keys[wib];
+    for (int r = blockIdx.x * 4 + wib; r < a.R; r += gridDim.x * 4) {
+        const int hc = w.hit_count[r];
+        if ((hc & WF_TAINT) || hc > w.hcap) {                      // bin overflow: per-ray fallback
+            if (lane == 0) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; a.hit_cnt[r] = 0; }
+            continue;
+        }
+        if (hc > WF_HCAP) {                                        // sorted by k_wf_sort_big, walked by k_sp_big
+            if (lane == 0) w.big_list[atomicAdd(w.counts + 10, 1)] = r;
+            continue;
+        }
+        const int n = hc;
+        const unsigned long long* bin = w.bins + (size_t)r * w.hcap;
+        // ---- sort the bin into this warp's slice of shared memory (register networks as in k_sp_sort)
+        if (n <= 32) {
+            const unsigned long long k = lane < n ? bin[lane] : LRT_KEY_EMPTY;
+            unsigned k32 = lane < n ? (((unsigned)(k >> 32) & ~31u) | (unsigned)lane) : 0xffffffffu;
+            k32 = warp_sort32(k32, lane);
+            keys[lane] = __shfl_sync(FULL, k, (int)(k32 & 31u));
+        } else if (n <= 64) {
+            const unsigned long long k0 = bin[lane], k1 = lane + 32 < n ? bin[lane + 32] : LRT_KEY_EMPTY;
+            unsigned a0 = ((unsigned)(k0 >> 32) & ~63u) | (unsigned)lane;
+            unsigned a1 = lane + 32 < n ? (((unsigned)(k1 >> 32) & ~63u) | (unsigned)(lane + 32)) : 0xffffffffu;
+            warp_sort64(a0, a1, lane);
+            const int s0 = (int)(a0 & 63u), s1 = (int)(a1 & 63u);
+            const unsigned long long x0 = __shfl_sync(FULL, k0, s0 & 31), y0 = __shfl_sync(FULL, k1, s0 & 31);
+            const unsigned long long x1 = __shfl_sync(FULL, k0, s1 & 31), y1 = __shfl_sync(FULL, k1, s1 & 31);
+            keys[lane] = (s0 >> 5) ? y0 : x0;
+            keys[lane + 32] = a1 == 0xffffffffu ? LRT_KEY_EMPTY : ((s1 >> 5) ? y1 : x1);
+        } else if (n <= 128) {
+            unsigned long long k[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) k[j] = lane + 32 * j < n ? bin[lane + 32 * j] : LRT_KEY_EMPTY;
+            warp_sort_regs<4>(k, lane);
+#pragma unroll
+            for (int j = 0; j < 4; j++) keys[lane + 32 * j] = k[j];
+        } else if (n <= 256) {
+            unsigned long long k[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) k[j] = lane + 32 * j < n ? bin[lane + 32 * j] : LRT_KEY_EMPTY;
+            warp_sort_regs<8>(k, lane);
+#pragma unroll
+            for (int j = 0; j < 8; j++) keys[lane + 32 * j] = k[j];
+        } else {
+            const int m = WF_HCAP;
+            for (int i = lane; i < m; i += 32) keys[i] = i < n ? bin[i] : LRT_KEY_EMPTY;
+            __syncwarp(FULL);
+            for (int size = 2; size <= m; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int i = lane; i < (m >> 1); i += 32) {
+                        const int lo = ((i / stride) * stride * 2) + (i % stride), hi = lo + stride;
+                        const unsigned long long x = keys[lo], y = keys[hi];
+                        const bool up = ((lo & size) == 0);
+                        if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+                    }
+                    __syncwarp(FULL);
+                }
+            }
+        }
+        __syncwarp(FULL);
+        sp_slots_ray(keys, n, min(w.nwild[r], n), r, __int_as_float(w.emax[r]), bvh, a, w, s_sk[wib], s_sa[wib], lane);
+        __syncwarp(FULL);
+    }
+}
+
 // The rays with more than WF_HCAP candidates (a ray skimming a wall or the side of a vehicle: thousands), whose bins
 // k_wf_sort_big has sorted in place: one WARP per ray walks the sorted keys in global memory and does the whole job — slots,
 // colour, fold, hit lists (wf_shade_ray). Pass A skips these rays; passes B and C find complete hit records and reproduce the

@@ -10,6 +10,8 @@ for r in rows[1:]:
     name = r[ix["Kernel Name"]]
     name = re.sub(r"<unnamed>::|\(anonymous namespace\)::", "", name)
     name = re.sub(r"\(.*", "", name)
+    if "cub" not in name and "at::" not in name:
+        name = re.sub(r"<.*", "", re.sub(r"^void ", "", name)).strip()      # templates: k_bw_hits<(bool)0> -> k_bw_hits
     if "cub::" in name or name.startswith("void cub") or "DeviceRadixSort" in name or "DeviceScan" in name:
         name = "cub radix sort / scan kernels"
     elif name.startswith("void at::") or "at::native" in name:
@@ -33,5 +35,6 @@ lines.append(f"{'total':40s} {sum(v['n'] for v in per.values()) / frames:14.1f} 
 open(out + ".txt", "a").write("\n".join(lines) + "\n")
 print("\n".join(lines))
 tj = {"kernels": {k: (v["rd"] + v["wr"]) / frames for k, v in per.items()},
+      "step_total": sum(v["rd"] + v["wr"] for v in per.values()) / frames,
       "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per frame: {os.path.basename(out)}.csv"}
 json.dump(tj, open(os.path.join(os.path.dirname(out), "traffic.json"), "w"), indent=1)

@@ -150,10 +150,12 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
         for kernel in (0, 1, 2, 3, 4):
             for tiled in (True, False):
                 for morton in (32, 63, 30):
-                  for shade in ((0, 1, 2, 3, 4, 5) if kernel >= 3 else (3,)):
-                    # shade 3 = split passes (default); 4 / 5 = kernels 2 / 3 with the by-length ray ordering switched off
-                    ctx.set_option(native.OPT_SORT_RAYS, 0 if shade >= 4 else 1)
-                    shade = shade - 2 if shade >= 4 else shade
+                  for shade in ((0, 1, 2, 3, 4, 5, 6) if kernel >= 3 else (3,)):
+                    # shade 3 = split passes, sort + slots fused in one warp-per-ray kernel (default); 6 = the two-kernel form with the
+                    # sorted record stream; 4 / 5 = kernels 2 / 3 with the by-length ray ordering switched off
+                    ctx.set_option(native.OPT_SPLIT_FUSED, 0 if shade == 6 else 1)
+                    ctx.set_option(native.OPT_SORT_RAYS, 0 if shade in (4, 5) else 1)
+                    shade = 3 if shade == 6 else (shade - 2 if shade >= 4 else shade)
                     ctx.set_option(native.OPT_FORWARD_KERNEL, kernel)
                     ctx.set_option(native.OPT_MORTON_BITS, morton)
                     ctx.set_option(native.OPT_WAVEFRONT_SHADE, shade)
@@ -169,7 +171,7 @@ def test_all_forward_kernels_and_options_agree_bitwise(ctx):
                             assert np.array_equal(a_, b_), f"kernel={kernel} tiled={tiled} morton={morton} shade={shade} differs"
     finally:
         ctx.set_option(native.OPT_FORWARD_KERNEL, 4); ctx.set_option(native.OPT_MORTON_BITS, 32); ctx.set_option(native.OPT_WAVEFRONT_SHADE, 3)
-        ctx.set_option(native.OPT_SORT_RAYS, 1)
+        ctx.set_option(native.OPT_SORT_RAYS, 1); ctx.set_option(native.OPT_SPLIT_FUSED, 1)
     assert_close(res["accum_w"], run_cuda(ctx, o, d, as_dict(sc), 3)["accum_w"], 1e-5, 1e-5, "accum (atomic order)")
 
 
