@@ -467,9 +467,12 @@ def run_b200(args, rank, world, local_rank):
     kalg = {"k_bw_hits": B_bwd, "k_bg_bin": Ksum * 40, "k_wf_leaf": Ksum * 40,
             "k_wf_composite": R * (12 + 36) + Kcsum * (nsh + 8),
             "k_sp_slots": R * (12 + 36) + Kcsum * 8, "k_sp_colour": Kcsum * nsh,
+            # the fused sort + slot pass reads every evaluated hit's geometry once more (the rounds re-test it from the re-based
+            # origin, as the reference's any-hit program does every round) on top of the slot pass's own term
+            "k_sp_warp": R * (12 + 36) + Ksum * 40 + Kcsum * 8,
             "k_records": P * (40 + 48 + 32), "radix_sort": 2 * P * 8 * 4}
     # the compositing chain of the forward (sort + slots + colour + fold) against the compositing term of §8d
-    chain = [k for k in ("k_sp_sort", "k_sp_slots", "k_sp_colour", "k_sp_fold", "k_wf_sort", "k_wf_composite") if k in kernels]
+    chain = [k for k in ("k_sp_warp", "k_sp_sort", "k_sp_slots", "k_sp_colour", "k_sp_fold", "k_wf_sort", "k_wf_composite") if k in kernels]
     chain_ms = sum(kernels[k]["ms_per_step"] for k in chain)
     chain_bytes = R * (12 + 36) + Kcsum * (nsh + 8)
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else "forward"

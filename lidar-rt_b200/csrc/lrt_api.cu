@@ -38,7 +38,7 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
     cudaSetDevice(ctx->device);
     for (auto& t : ctx->spans) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    DevBuf* bufs[] = {&ctx->leafq, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->rec_g, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
+    DevBuf* bufs[] = {&ctx->leafq, &ctx->fit_ticket, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->rec_g, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
                       &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb,
                       &ctx->wf_ids, &ctx->wf_keys, &ctx->wf_sort_tmp, &ctx->bw_ids, &ctx->bw_keys, &ctx->bw_sort_tmp,
                       &ctx->bw_off, &ctx->bw_rec_a, &ctx->bw_rec_b, &ctx->dn_pos, &ctx->dn_tmp, &ctx->sh_tab, &ctx->sp_cnt, &ctx->sp_rec, &ctx->sp_scan_tmp, &ctx->sp_hits, &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan,

@@ -31,13 +31,29 @@ __global__ void k_bounds_init(int* b)
     else if (threadIdx.x < 6) b[threadIdx.x] = (int)0x80000000; // max
 }
 
+// Scene box. A thread takes FOUR means at a time as three 128-bit loads (the array is read once, fully coalesced); partial boxes
+// meet in the warp, then in the block, and one set of six atomics per BLOCK reaches memory (one per warp was 57 k atomics on six
+// addresses, which serialise in the L2: 0.045 ms for a 24 MB read).
 __global__ void __launch_bounds__(256) k_bounds(int P, const float* __restrict__ means, int* __restrict__ b)
 {
+    __shared__ float s_lo[8][3], s_hi[8][3];
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    const bool vec = (reinterpret_cast<uintptr_t>(means) & 15) == 0;
+    const int nquad = vec ? P >> 2 : 0;                         // groups of four means = three float4
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nquad; i += gridDim.x * blockDim.x) {
+        const float4* p4 = reinterpret_cast<const float4*>(means) + 3 * (size_t)i;
+        const float4 a = __ldg(p4), c = __ldg(p4 + 1), e = __ldg(p4 + 2);
+        const float v[12] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w, e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            const float x = v[j];
+            if (x == x && fabsf(x) < 1e30f) { lo[j % 3] = fminf(lo[j % 3], x); hi[j % 3] = fmaxf(hi[j % 3], x); }
+        }
+    }
+    for (int i = 4 * nquad + blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const float v = means[3 * i + k];
+            const float v = means[3 * (size_t)i + k];
             if (v == v && fabsf(v) < 1e30f) { lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v); }
         }
     }
@@ -49,9 +65,17 @@ __global__ void __launch_bounds__(256) k_bounds(int P, const float* __restrict__
             hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
         }
     }
-    if ((threadIdx.x & 31) == 0) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) { atomicMin(&b[k], f2ord(lo[k])); atomicMax(&b[3 + k], f2ord(hi[k])); }
+        for (int k = 0; k < 3; k++) { s_lo[wib][k] = lo[k]; s_hi[wib][k] = hi[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        float l = s_lo[0][k], h = s_hi[0][k];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) { l = fminf(l, s_lo[w][k]); h = fmaxf(h, s_hi[w][k]); }
+        atomicMin(&b[k], f2ord(l)); atomicMax(&b[3 + k], f2ord(h));
     }
 }
 
@@ -168,10 +192,13 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
                                                  const float* __restrict__ means, const float* __restrict__ scales,
                                                  const float* __restrict__ rots, const float* __restrict__ opac,
                                                  float mod, SurfelRec* __restrict__ rec, Node8* __restrict__ leaf,
-                                                 SurfelRec* __restrict__ rec_g, LeafQ* __restrict__ leafq)
+                                                 SurfelRec* __restrict__ rec_g, LeafQ* __restrict__ leafq,
+                                                 Node8* __restrict__ lvl1, int n1, Node8* __restrict__ lvl2, int n2)
 {
+    // No thread leaves early: the grid covers every child slot of levels 1 and 2 (slots beyond the last leaf are written as
+    // empty), the shuffles below run on full warps and the block meets at a barrier.
+    __shared__ float s_box[8][6];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P_pad) return;
     // empty slot marker: lo = hi = +FLT_MAX on every axis. A slab test maps it to an interval beyond
     // any tmax (or before 0), so it is never entered; k_fit skips it in unions.
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
@@ -207,19 +234,22 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
                 for (int k = 0; k < 3; k++) { lo[k] = FLT_MAX; hi[k] = FLT_MAX; }
             }
         }
-    } else {
+    } else if (i < P_pad) {
         SurfelRec r;
         r.r0 = make_float4(0.f, 0.f, 0.f, -1.0f); r.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
         r.r2 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); r.r3 = make_float4(0.f, 0.f, 1.f, 0.f);
         rec[i] = r;
     }
-    Node8& n = leaf[i >> 3];
     const int c = i & 7;
-    n.lox[c] = lo[0]; n.loy[c] = lo[1]; n.loz[c] = lo[2];
-    n.hix[c] = hi[0]; n.hiy[c] = hi[1]; n.hiz[c] = hi[2];
+    if (i < P_pad) {
+        Node8& n = leaf[i >> 3];
+        n.lox[c] = lo[0]; n.loy[c] = lo[1]; n.loz[c] = lo[2];
+        n.hix[c] = hi[0]; n.hiy[c] = hi[1]; n.hiz[c] = hi[2];
+    }
     // compact copy: bounds of the 8 surfels of this leaf (the 8 threads are consecutive lanes), then 8-bit boxes
     const bool empty = lo[0] == FLT_MAX;
-    LeafQ& lq = leafq[i >> 3];
+    LeafQ& lq = leafq[min(i, P_pad - 1) >> 3];                       // written only by threads i < P_pad
+    float ul[3], uh[3];                                              // union of the leaf's 8 boxes (l > h: all empty)
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         float l = empty ? FLT_MAX : lo[k], h = empty ? -FLT_MAX : hi[k];
@@ -228,6 +258,7 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
             l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
             h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
         }
+        ul[k] = l; uh[k] = h;
         const bool none = l > h;                                     // all 8 slots empty
         const float base = none ? FLT_MAX : l;
         const float sc = none ? 0.0f : fmaxf((h - l) * (1.0f / 255.0f), 1e-30f);
@@ -239,28 +270,68 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
             while (qh < 255 && fmaf((float)qh, sc, base) < hi[k]) qh++;
             if (fmaf((float)qh, sc, base) < hi[k]) { ql = 0; qh = 255; }   // cannot happen with sc >= (h-l)/255; belt and braces
         }
-        lq.qlo[k][c] = (unsigned char)ql; lq.qhi[k][c] = (unsigned char)qh;
-        if (c == 0) { lq.lo[k] = base; lq.sc[k] = sc; }
+        if (i < P_pad) {
+            lq.qlo[k][c] = (unsigned char)ql; lq.qhi[k][c] = (unsigned char)qh;
+            if (c == 0) { lq.lo[k] = base; lq.sc[k] = sc; }
+        }
+    }
+    // Levels 1 and 2 of the hierarchy, while the boxes are in registers (what k_fit would compute from the leaves it re-reads:
+    // unions skip empty slots, an all-empty child is lo = hi = +FLT_MAX). Level 1: child (i >> 3) & 7 of node i >> 6 is the
+    // union of leaf i >> 3, which its 8 lanes just formed. Level 2: child (i >> 6) & 7 of node i >> 9 is the union of 64
+    // consecutive threads = two warps, met through shared memory.
+    if (!lvl1) return;                                               // a single leaf: no upper level (block-uniform)
+    if (c == 0 && (i >> 6) < n1) {
+        const bool none = ul[0] > uh[0];
+        Node8& n = lvl1[i >> 6];
+        const int cc = (i >> 3) & 7;
+        n.lox[cc] = none ? FLT_MAX : ul[0]; n.loy[cc] = none ? FLT_MAX : ul[1]; n.loz[cc] = none ? FLT_MAX : ul[2];
+        n.hix[cc] = none ? FLT_MAX : uh[0]; n.hiy[cc] = none ? FLT_MAX : uh[1]; n.hiz[cc] = none ? FLT_MAX : uh[2];
+    }
+    if (!lvl2) return;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) {
+            ul[k] = fminf(ul[k], __shfl_xor_sync(0xffffffffu, ul[k], o));
+            uh[k] = fmaxf(uh[k], __shfl_xor_sync(0xffffffffu, uh[k], o));
+        }
+    }
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { s_box[wib][k] = ul[k]; s_box[wib][3 + k] = uh[k]; }
+    }
+    __syncthreads();
+    if (lane == 0 && (wib & 1) == 0 && (i >> 9) < n2) {
+        float l[3], h[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { l[k] = fminf(s_box[wib][k], s_box[wib + 1][k]); h[k] = fmaxf(s_box[wib][3 + k], s_box[wib + 1][3 + k]); }
+        const bool none = l[0] > h[0];
+        Node8& n = lvl2[i >> 9];
+        const int cc = (i >> 6) & 7;
+        n.lox[cc] = none ? FLT_MAX : l[0]; n.loy[cc] = none ? FLT_MAX : l[1]; n.loz[cc] = none ? FLT_MAX : l[2];
+        n.hix[cc] = none ? FLT_MAX : h[0]; n.hiy[cc] = none ? FLT_MAX : h[1]; n.hiz[cc] = none ? FLT_MAX : h[2];
     }
 }
 
-// level l >= 1: child c of node j is the union of the 8 boxes of node 8j+c one level below
-__global__ void __launch_bounds__(256) k_fit(int n_parent, int n_child, const Node8* __restrict__ child,
-                                             Node8* __restrict__ parent)
+// child c of node j of a level >= 1 is the union of the 8 boxes of node 8j+c one level below. The child level may have been
+// written earlier in the SAME launch (k_fit_top): its loads bypass L1.
+__device__ __forceinline__ void fit_child(int t, int n_child, const Node8* child, Node8* parent)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_parent * 8) return;
     const int j = t >> 3, c = t & 7, cj = 8 * j + c;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     bool any = false;
     if (cj < n_child) {
-        const Node8& ch = child[cj];
+        const float4* ch = reinterpret_cast<const float4*>(child + cj);          // lox[8] loy[8] loz[8] hix[8] hiy[8] hiz[8]
+        float v[48];
+#pragma unroll
+        for (int q = 0; q < 12; q++) { const float4 x = __ldcg(ch + q); v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w; }
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            if (ch.lox[k] != FLT_MAX) {                         // skip empty slots
+            if (v[k] != FLT_MAX) {                              // skip empty slots
                 any = true;
-                lo[0] = fminf(lo[0], ch.lox[k]); lo[1] = fminf(lo[1], ch.loy[k]); lo[2] = fminf(lo[2], ch.loz[k]);
-                hi[0] = fmaxf(hi[0], ch.hix[k]); hi[1] = fmaxf(hi[1], ch.hiy[k]); hi[2] = fmaxf(hi[2], ch.hiz[k]);
+                lo[0] = fminf(lo[0], v[k]); lo[1] = fminf(lo[1], v[8 + k]); lo[2] = fminf(lo[2], v[16 + k]);
+                hi[0] = fmaxf(hi[0], v[24 + k]); hi[1] = fmaxf(hi[1], v[32 + k]); hi[2] = fmaxf(hi[2], v[40 + k]);
             }
         }
     }
@@ -268,6 +339,35 @@ __global__ void __launch_bounds__(256) k_fit(int n_parent, int n_child, const No
     Node8& n = parent[j];
     n.lox[c] = lo[0]; n.loy[c] = lo[1]; n.loz[c] = lo[2];
     n.hix[c] = hi[0]; n.hiy[c] = hi[1]; n.hiz[c] = hi[2];
+}
+
+// Every level from `first` up in ONE launch (the six k_fit launches of a 2 M surfel build were 0.077 ms, nearly all of it launch
+// latency on levels of a few thousand nodes and fewer). All blocks fit level `first`; the block that finishes last (ticket
+// counter, reset for the next build) walks the remaining levels — a few hundred nodes in total — on its own.
+struct FitLevels { int first, levels; int off[LRT_MAX_LEVELS]; int cnt[LRT_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(256) k_fit_top(Node8* nodes, FitLevels fl, unsigned* ticket)
+{
+    __shared__ bool s_last;
+    {
+        const int l = fl.first, t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t < fl.cnt[l] * 8) fit_child(t, fl.cnt[l - 1], nodes + fl.off[l - 1], nodes + fl.off[l]);
+    }
+    if (fl.first + 1 >= fl.levels) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(ticket, 1u);
+        s_last = prev == gridDim.x - 1;
+        if (s_last) *ticket = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int l = fl.first + 1; l < fl.levels; l++) {
+        for (int t = threadIdx.x; t < fl.cnt[l] * 8; t += blockDim.x) fit_child(t, fl.cnt[l - 1], nodes + fl.off[l - 1], nodes + fl.off[l]);
+        __syncthreads();
+    }
 }
 
 } // namespace
@@ -316,7 +416,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
         else { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk32, dv, P, lo_bit, bits32, s)); }
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sort_tmp, tmp_bytes));
         k_bounds_init<<<1, 32, 0, s>>>((int*)ctx->bounds.p);
-        const int gb = min((P + TB - 1) / TB, 148 * 8);
+        const int gb = min((P / 4 + TB - 1) / TB + 1, 148 * 4);
         ctx->span_begin("k_bounds", s); k_bounds<<<gb, TB, 0, s>>>(P, means, (int*)ctx->bounds.p); ctx->span_end(s);
         if (wide) {
             k_morton64<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned long long*)ctx->keys_a.p,
@@ -342,14 +442,27 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
         }
     }
     Node8* nodes = (Node8*)ctx->nodes.p;
-    ctx->span_begin("k_records", s); k_records<<<(P_pad + TB - 1) / TB, TB, 0, s>>>(P, P_pad, (const unsigned*)ctx->perm_a.p, means, scales, rots, opac,
-                                                   mod, (SurfelRec*)ctx->rec.p, nodes + off[0], (SurfelRec*)ctx->rec_g.p, (LeafQ*)ctx->leafq.p); ctx->span_end(s);
-    for (int l = 1; l < L; l++) {
+    // k_records writes levels 0, 1 and 2; its grid covers every child slot of the highest of them
+    const int n_thr = L >= 3 ? cnt[2] * 512 : (L == 2 ? cnt[1] * 64 : P_pad);
+    ctx->span_begin("k_records", s);
+    k_records<<<(n_thr + TB - 1) / TB, TB, 0, s>>>(P, P_pad, (const unsigned*)ctx->perm_a.p, means, scales, rots, opac, mod, (SurfelRec*)ctx->rec.p,
+                                                  nodes + off[0], (SurfelRec*)ctx->rec_g.p, (LeafQ*)ctx->leafq.p,
+                                                  L >= 2 ? nodes + off[1] : nullptr, L >= 2 ? cnt[1] : 0, L >= 3 ? nodes + off[2] : nullptr, L >= 3 ? cnt[2] : 0);
+    ctx->span_end(s);
+    ctx->launches += 1;
+    if (L > 3) {
+        if (!ctx->fit_ticket.p) {
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->fit_ticket, 64));
+            LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->fit_ticket.p, 0, 64, s));
+        }
+        FitLevels fl;
+        fl.first = 3; fl.levels = L;
+        for (int l = 0; l < LRT_MAX_LEVELS; l++) { fl.off[l] = l < L ? off[l] : 0; fl.cnt[l] = l < L ? cnt[l] : 0; }
         ctx->span_begin("k_fit", s);
-        k_fit<<<(cnt[l] * 8 + TB - 1) / TB, TB, 0, s>>>(cnt[l], cnt[l - 1], nodes + off[l - 1], nodes + off[l]);
+        k_fit_top<<<(cnt[3] * 8 + TB - 1) / TB, TB, 0, s>>>(nodes, fl, (unsigned*)ctx->fit_ticket.p);
         ctx->span_end(s);
+        ctx->launches += 1;
     }
-    ctx->launches += L;
     LRT_CUDA_TRY(ctx, cudaGetLastError());
 
     ctx->P = P; ctx->P_pad = P_pad; ctx->levels = L; ctx->n_nodes = total; ctx->scale_modifier = mod;

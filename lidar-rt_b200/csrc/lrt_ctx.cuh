@@ -29,6 +29,7 @@ struct lrt_ctx {
     bool built = false;
     float scale_modifier = 1.0f;
     DevBuf leafq;
+    DevBuf fit_ticket;             // k_fit_top's last-block counter (zero between builds)
     DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, rec_g, sort_tmp, bounds, counter;
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
     DevBuf bw_off, bw_rec_a, bw_rec_b;   // hit-parallel backward (lrt_backward.cu)
@@ -111,7 +112,7 @@ struct lrt_ctx {
     }
     size_t total_bytes() const
     {
-        return leafq.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
+        return leafq.cap + fit_ticket.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
                bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
                bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + sp_cnt.cap + sp_rec.cap + sp_scan_tmp.cap + sp_hits.cap + dn_pos.cap + dn_tmp.cap + sh_tab.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap + ch_keys_a.cap + ch_keys_b.cap + ch_idx_a.cap + ch_idx_b.cap;
