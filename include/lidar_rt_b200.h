@@ -245,10 +245,12 @@ int lrt_densify_rows(lrt_ctx* ctx, int P, const uint8_t* clone_mask, const uint8
  *                           what forward.cu:319 reads with optixGetRayTmax. Default 0. Applies to the default forward path
  *                           (kernel 4 / 3 with split passes); rays handed to the fallback paths keep the analytic quad.
  *   LRT_OPT_MORTON_BITS     32 = 32-bit keys, bits dealt to the axes so cells stay cubic (default); 63 = 21 bits/axis on
- *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build) */
+ *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build)
+ *   LRT_OPT_SORT_KEY_BITS   how many of the top bits of a 32-bit key the build's radix sort orders (16 = default, 24, 32): one 8-bit
+ *                           pass each; surfels that agree on those bits keep the caller's order, results do not depend on it */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,
                   LRT_OPT_BACKWARD_KERNEL = 5, LRT_OPT_WAVEFRONT_SHADE = 6, LRT_OPT_KERNEL_TIMING = 7,
-                  LRT_OPT_SORT_RAYS = 8, LRT_OPT_BEAM_CELL_PCT = 9, LRT_OPT_TRIANGLE_DEPTH = 10, LRT_OPT_SPLIT_FUSED = 11 };
+                  LRT_OPT_SORT_RAYS = 8, LRT_OPT_BEAM_CELL_PCT = 9, LRT_OPT_TRIANGLE_DEPTH = 10, LRT_OPT_SPLIT_FUSED = 11, LRT_OPT_SORT_KEY_BITS = 12 };
 int lrt_set_option(lrt_ctx* ctx, int option, int value);
 
 /* Introspection for tests / benchmarks (host pointers). */

@@ -192,6 +192,7 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
     case LRT_OPT_KERNEL_TIMING: if (value != 0 && value != 1) break; ctx->opt_kernel_timing = value; return LRT_OK;
     case LRT_OPT_WAVEFRONT_SHADE: if (value < 0 || value > 3) break; ctx->opt_wavefront_shade = value; return LRT_OK;
     case LRT_OPT_BACKWARD_KERNEL: if (value < 0 || value > 2) break; ctx->opt_backward_kernel = value; return LRT_OK;
+    case LRT_OPT_SORT_KEY_BITS: if (value != 16 && value != 24 && value != 32) break; ctx->opt_sort_key_bits = value; return LRT_OK;
     case LRT_OPT_MORTON_BITS: if (value != 30 && value != 32 && value != 63) break; ctx->opt_morton_bits = value; return LRT_OK;
     case LRT_OPT_VECTOR_ATOMICS: if (value != 0 && value != 1) break; ctx->opt_vector_atomics = value; return LRT_OK;
     case LRT_OPT_SPLIT_FUSED: if (value != 0 && value != 1) break; ctx->opt_split_fused = value; return LRT_OK;

@@ -411,7 +411,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
         const int bits32 = ctx->opt_morton_bits == 32 ? 32 : 30;
         // 32-bit keys are sorted on their top 24 bits only: 16.7 M cells for a few million surfels, the order inside a cell is
         // irrelevant (the sort is stable), and the radix sort takes three 8-bit passes instead of four
-        const int lo_bit = bits32 == 32 ? 8 : 0;
+        const int lo_bit = bits32 == 32 ? 32 - ctx->opt_sort_key_bits : 0;
         if (wide) { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk64, dv, P, 0, 63, s)); }
         else { LRT_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk32, dv, P, lo_bit, bits32, s)); }
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->sort_tmp, tmp_bytes));

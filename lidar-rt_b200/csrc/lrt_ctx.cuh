@@ -63,6 +63,7 @@ struct lrt_ctx {
     int opt_vector_atomics = 1;   // backward: red.global.add.v4.f32 where alignment allows
     int opt_split_fused = 1;      // split passes: 1 = sort + slots in one warp-per-ray kernel (k_sp_warp), 0 = k_sp_sort + record stream + k_sp_slots
     int opt_triangle_depth = 0;   // split passes: hits and depths from the two fp32 proxy triangles (fp64 Moeller-Trumbore) instead of the analytic quad
+    int opt_sort_key_bits = 16;   // top bits of a 32-bit key the radix sort orders (8 per pass)
     int opt_morton_bits = 32;     // 32: 32-bit cubic-cell keys (default); 63: 21 bits/axis on cubic cells; 30: 10 bits/axis, per-axis extent
     int fwd_blocks_per_sm = 0, g8_blocks_per_sm = 0, num_sms = 0;
     long long builds = 0, refits = 0;
