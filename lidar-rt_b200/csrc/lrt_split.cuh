@@ -191,6 +191,18 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
 // accepted ones are compacted in bin order into the round's slot array, and the warp folds the 16 slots in order. No record is
 // written anywhere; 32 gathers are in flight per warp instead of 4 per thread. Near-tie reordering (re-based depths out of bin
 // order) falls back to a warp sort of the collected slots. Outputs are those of k_sp_slots, bit for bit.
+__device__ __forceinline__ void sp_cp_async8(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void sp_cp_async4(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void sp_cp_async_wait_all();
+
 __device__ __forceinline__ void sp_test_candidate(const SurfelRec* __restrict__ rec, unsigned long long ck, const RaySetup& rs, const FwdRay& q,
                                                   unsigned long long& key, float& alpha)
 {
@@ -249,8 +261,8 @@ __device__ __forceinline__ void sp_slots_ray(const unsigned long long* keys, int
         RaySetup rs;
         ray_setup(rs, q.o, q.d, q.base);
         const float thr = q.base - 2.0f * wf_margin(q.base, em);
-        int pos;                                                   // first candidate of the sorted part at or beyond thr (warp-uniform lower bound)
-        {
+        int pos = nw;                                              // first candidate of the sorted part at or beyond thr (warp-uniform lower bound)
+        if (q.base > 0.0f) {                                       // first round: thr < 0 and every sorted key is > 0
             int lo = nw, hi = n;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -324,8 +336,8 @@ __device__ __forceinline__ void sp_slots_ray(const unsigned long long* keys, int
         }
         // the round's compositing (fwd_shade_round()) without the colour. Lane i owns slot i: which slots contribute (:214, :220-224,
         // alpha >= 1/255) is decided by all lanes at once; only the transmittance / depth chain over the contributing slots is
-        // walked in order (two shuffles and six float operations per hit instead of the whole per-slot body on every lane: that
-        // loop was 61 % of the kernel's instructions, profiles/r2_u_warp_ncu.txt); every owner then commits its own hit.
+        // walked in order (one broadcast load and six float operations per hit instead of the whole per-slot body on every lane:
+        // that loop was 61 % of the kernel's instructions, profiles/r2_u_warp_ncu.txt); every owner then commits its own hit.
         const int nr = nvalid < LRT_KBUF ? nvalid : LRT_KBUF;
         bool terminated = false;
         {
@@ -340,19 +352,32 @@ __device__ __forceinline__ void sp_slots_ray(const unsigned long long* keys, int
             const int gfront = __shfl_sync(FULL, g, front ? 31 - __clz(front) : 0);
             const bool contrib = okd && g != (front ? gfront : q.last) && !(alpha < 1.0f / 255.0f);
             const unsigned cm = __ballot_sync(FULL, contrib);
-            float myT = 0.0f;
-            int stop = nr;                                                               // slot whose testT fell below T_MIN (:253-257)
-            for (unsigned m = cm; m;) {
-                const int i = __ffs(m) - 1;
-                m &= m - 1;
-                const float al = __shfl_sync(FULL, alpha, i), dp = __shfl_sync(FULL, dpt, i);
-                q.testT = q.T * (1.0f - al);
-                if (q.testT < LRT_T_MIN) { terminated = true; stop = i; break; }
-                const float wgt = al * q.T;
-                q.Dp += wgt * dp; q.W += wgt;
-                myT = lane == i ? q.T : myT;
+            // the contributing slots' (alpha, depth), compacted in order into this warp's slot array (every lane holds its own slot
+            // in registers by now); the chain below reads them as broadcasts and leaves the transmittance in front of each hit
+            const int mine = __popc(cm & ((1u << lane) - 1u));              // this lane's slot among the contributing ones
+            const int nc = __popc(cm);
+            float2* sc = reinterpret_cast<float2*>(sk);
+            __syncwarp(FULL);
+            if (contrib) sc[mine] = make_float2(alpha, dpt);
+            __syncwarp(FULL);
+            int stop = nr;                                                   // slot whose testT fell below T_MIN (:253-257)
+            int ndone = nc;                                                  // contributing slots in front of it
+            for (int i = 0; i < nc; i++) {
+                const float2 v = sc[i];
+                q.testT = q.T * (1.0f - v.x);
+                if (q.testT < LRT_T_MIN) { terminated = true; ndone = i; break; }
+                const float wgt = v.x * q.T;
+                q.Dp += wgt * v.y; q.W += wgt;
+                if (lane == 0) sa[i] = q.T;
                 q.T = q.testT;
             }
+            __syncwarp(FULL);
+            if (terminated) {                                                // the original slot index of the terminating hit
+                unsigned m = cm;
+                for (int i = 0; i < ndone; i++) m &= m - 1;
+                stop = __ffs(m) - 1;
+            }
+            const float myT = (contrib && mine < ndone) ? sa[mine] : 0.0f;
             q.nslots += terminated ? stop + 1 : nr;
             const unsigned done = cm & ((1u << stop) - 1u);                              // stop <= 16: the contributing slots in front of it
             if (contrib && lane < stop) {
@@ -395,8 +420,29 @@ __global__ void __launch_bounds__(128, LRT_WARP_MIN_BLOCKS) k_sp_warp(BvhView bv
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned long long* keys = s_keys[wib];
-    for (int r = blockIdx.x * 4 + wib; r < a.R; r += gridDim.x * 4) {
-        const int hc = w.hit_count[r];
+    // the next ray's candidate count and the first 32 keys of its bin travel to shared memory (cp.async: no destination register,
+    // nothing for the compiler to spill) while this ray is processed: the two dependent global loads in front of every sort were
+    // 4.6 % of the kernel's stall samples (profiles/r2_z_warp_ncu.txt)
+    __shared__ unsigned long long s_pf[4][32];
+    __shared__ int s_hc[4];
+    int r = blockIdx.x * 4 + wib;
+    if (r < a.R) {
+        sp_cp_async8(&s_pf[wib][lane], w.bins + (size_t)r * w.hcap + lane);
+        if (lane == 0) sp_cp_async4(&s_hc[wib], w.hit_count + r);
+    }
+    for (; r < a.R; r += gridDim.x * 4) {
+        sp_cp_async_wait_all();
+        __syncwarp(FULL);
+        const int hc = s_hc[wib];
+        const unsigned long long k_first = s_pf[wib][lane];
+        __syncwarp(FULL);
+        {
+            const int r2 = r + gridDim.x * 4;
+            if (r2 < a.R) {
+                sp_cp_async8(&s_pf[wib][lane], w.bins + (size_t)r2 * w.hcap + lane);
+                if (lane == 0) sp_cp_async4(&s_hc[wib], w.hit_count + r2);
+            }
+        }
         if ((hc & WF_TAINT) || hc > w.hcap) {                      // bin overflow: per-ray fallback
             if (lane == 0) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; a.hit_cnt[r] = 0; }
             continue;
@@ -409,12 +455,12 @@ __global__ void __launch_bounds__(128, LRT_WARP_MIN_BLOCKS) k_sp_warp(BvhView bv
         const unsigned long long* bin = w.bins + (size_t)r * w.hcap;
         // ---- sort the bin into this warp's slice of shared memory (register networks as in k_sp_sort)
         if (n <= 32) {
-            const unsigned long long k = lane < n ? bin[lane] : LRT_KEY_EMPTY;
+            const unsigned long long k = lane < n ? k_first : LRT_KEY_EMPTY;
             unsigned k32 = lane < n ? (((unsigned)(k >> 32) & ~31u) | (unsigned)lane) : 0xffffffffu;
             k32 = warp_sort32(k32, lane);
             keys[lane] = __shfl_sync(FULL, k, (int)(k32 & 31u));
         } else if (n <= 64) {
-            const unsigned long long k0 = bin[lane], k1 = lane + 32 < n ? bin[lane + 32] : LRT_KEY_EMPTY;
+            const unsigned long long k0 = k_first, k1 = lane + 32 < n ? bin[lane + 32] : LRT_KEY_EMPTY;
             unsigned a0 = ((unsigned)(k0 >> 32) & ~63u) | (unsigned)lane;
             unsigned a1 = lane + 32 < n ? (((unsigned)(k1 >> 32) & ~63u) | (unsigned)(lane + 32)) : 0xffffffffu;
             warp_sort64(a0, a1, lane);
