@@ -697,19 +697,36 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
     const bool have_lists = hit_gidx && hit_t && hit_cnt && cap > 0;
     if (!have_lists && (hit_gidx || hit_t)) { ctx->set_error("lrt_backward: hit_gidx, hit_t, hit_cnt and cap go together"); return LRT_ERR_INVALID; }
     LRT_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dmeans, 0, sizeof(float) * (size_t)P * 3, s));
+    // The gradient buffers are zero-filled (464 MB at 2 M Gaussians: pure bandwidth). In the grouped replay nothing touches them
+    // before k_bw_hits, so the fill runs on a side stream beside the count / scan / prefix passes, which wait on latency and
+    // leave the memory system idle; fork and join are events, so the same shape is recorded when the caller captures a graph.
+    const bool grouped = R > 0 && hit_gidx && hit_t && hit_cnt && cap > 0 && ctx->opt_backward_kernel == 2 && hit_aux &&
+                         (reinterpret_cast<uintptr_t>(hit_aux) & 15) == 0;
+    cudaStream_t zs = s;
+    if (grouped) {
+        if (!ctx->side_stream) {
+            LRT_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+            LRT_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            LRT_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        zs = ctx->side_stream;
+        LRT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, s));
+        LRT_CUDA_TRY(ctx, cudaStreamWaitEvent(zs, ctx->ev_fork, 0));
+    }
+    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dmeans, 0, sizeof(float) * (size_t)P * 3, zs));
     if (sh_tab) {
         for (int k = 0; k < ctx->sh_parts_n; k++) {
             const lrt_sh_part& pt = ctx->sh_parts[k];
-            if (pt.d_features_dc) LRT_CUDA_TRY(ctx, cudaMemsetAsync(pt.d_features_dc, 0, sizeof(float) * 3 * (size_t)pt.P, s));
-            if (pt.d_features_rest && M > 1) LRT_CUDA_TRY(ctx, cudaMemsetAsync(pt.d_features_rest, 0, sizeof(float) * 3 * (size_t)(M - 1) * pt.P, s));
+            if (pt.d_features_dc) LRT_CUDA_TRY(ctx, cudaMemsetAsync(pt.d_features_dc, 0, sizeof(float) * 3 * (size_t)pt.P, zs));
+            if (pt.d_features_rest && M > 1) LRT_CUDA_TRY(ctx, cudaMemsetAsync(pt.d_features_rest, 0, sizeof(float) * 3 * (size_t)(M - 1) * pt.P, zs));
         }
     } else {
-        LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dshs, 0, sizeof(float) * (size_t)P * M * 3, s));
+        LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dshs, 0, sizeof(float) * (size_t)P * M * 3, zs));
     }
-    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dopac, 0, sizeof(float) * (size_t)P, s));
-    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dscales, 0, sizeof(float) * (size_t)P * 2, s));
-    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_drots, 0, sizeof(float) * (size_t)P * 4, s));
+    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dopac, 0, sizeof(float) * (size_t)P, zs));
+    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_dscales, 0, sizeof(float) * (size_t)P * 2, zs));
+    LRT_CUDA_TRY(ctx, cudaMemsetAsync(dL_drots, 0, sizeof(float) * (size_t)P * 4, zs));
+    if (grouped) LRT_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, zs));
     if (R == 0) return LRT_OK;
     BwArgs a;
     a.R = R; a.ray_o = ray_o; a.ray_o_stride = ray_o_stride; a.ray_d = ray_d; a.bg = bg;
@@ -729,7 +746,7 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
             LRT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
             ctx->num_sms = sms > 0 ? sms : 148;
         }
-        if (ctx->opt_backward_kernel == 2 && hit_aux && (reinterpret_cast<uintptr_t>(hit_aux) & 15) == 0) {
+        if (grouped) {
             // grouped replay: hits regrouped by Gaussian, per-ray prefix pass, one thread per hit + segmented reduction
             long long want = (long long)R * 64; if (want < (1LL << 20)) want = 1LL << 20;
             const long long worst = (long long)R * cap;
@@ -751,6 +768,7 @@ int lrt_backward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride,
             LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->bw_sort_tmp.p, tb, (const int*)gcnt, goff, P + 1, s));
             ctx->span_end(s);
             ctx->span_begin("k_bw_prefix", s); k_bw_prefix<<<GB, TB, 0, s>>>(a, f); ctx->span_end(s);
+            LRT_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));      // the zero-filled gradient buffers
             ctx->span_begin("k_bw_hits", s);
             if (sh_tab) {
                 LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bw_hits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 8 * 32 * BW_SROW)));

@@ -159,7 +159,7 @@ __global__ void k_morton_plan(const int* __restrict__ b, int* __restrict__ plan)
 }
 
 __global__ void __launch_bounds__(256) k_morton32(int P, const float* __restrict__ means, const int* __restrict__ b,
-                                                  const int* __restrict__ plan, unsigned* __restrict__ keys, unsigned* __restrict__ idx)
+                                                  const int* __restrict__ plan, unsigned* __restrict__ keys, unsigned* __restrict__ idx, int nbits)
 {
     __shared__ int s_plan[35];
     if (threadIdx.x < 35) s_plan[threadIdx.x] = plan[threadIdx.x];
@@ -177,15 +177,21 @@ __global__ void __launch_bounds__(256) k_morton32(int P, const float* __restrict
         q[k] = (t == t) ? (unsigned)t : 0u;
         if (nbk > 24) q[k] <<= (nbk - 24);
     }
-    unsigned key = 0;
-#pragma unroll
-    for (int bit = 0; bit < 32; bit++) {
+    unsigned key = 0;                                // only the `nbits` top bits the radix sort looks at are assembled
+#pragma unroll 8
+    for (int bit = 0; bit < nbits; bit++) {
         const int pl = s_plan[bit], ax = pl >> 8, sh = pl & 0xff;
         const unsigned v = ax == 0 ? q[0] : (ax == 1 ? q[1] : q[2]);
         key = (key << 1) | ((v >> sh) & 1u);
     }
-    keys[i] = key;
+    keys[i] = nbits < 32 ? key << (32 - nbits) : key;
     idx[i] = (unsigned)i;
+}
+
+__device__ __forceinline__ void rec_store(SurfelRec* dst, const SurfelRec& r)
+{
+    float4* d = reinterpret_cast<float4*>(dst);
+    __stcs(d, r.r0); __stcs(d + 1, r.r1); __stcs(d + 2, r.r2); __stcs(d + 3, r.r3);
 }
 
 __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigned* __restrict__ perm,
@@ -217,8 +223,10 @@ __global__ void __launch_bounds__(256) k_records(int P, int P_pad, const unsigne
         r.r1 = make_float4(d.Lu[0], d.Lu[1], d.Lu[2], d.op);
         r.r2 = make_float4(d.Lv[0], d.Lv[1], d.Lv[2], __int_as_float(g));
         r.r3 = make_float4(d.n[0], d.n[1], d.n[2], 0.0f);
-        rec[i] = r;
-        rec_g[g] = r;
+        // streaming stores: 256 MB of records pass through the L2 once; the 80 MB of raw parameters, gathered through the
+        // permutation one 32-byte sector at a time (4-5 sectors per Gaussian), should be what stays resident
+        rec_store(rec + i, r);
+        rec_store(rec_g + g, r);
         const bool valid = (d.f == d.f) && d.f >= 0.0f && d.f < 1e30f;
         if (valid) {
             const float ax = mod * d.sx * d.f, ay = mod * d.sy * d.f;
@@ -426,7 +434,7 @@ int lrt_build_impl(lrt_ctx* ctx, int P, const float* means, const float* scales,
             if (bits32 == 32) {
                 k_morton_plan<<<1, 32, 0, s>>>((const int*)ctx->bounds.p, (int*)ctx->bounds.p + 8);
                 k_morton32<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (const int*)ctx->bounds.p + 8,
-                                                             (unsigned*)ctx->keys_a.p, (unsigned*)ctx->perm_b.p);
+                                                             (unsigned*)ctx->keys_a.p, (unsigned*)ctx->perm_b.p, ctx->opt_sort_key_bits);
             }
             else
                 k_morton<<<(P + TB - 1) / TB, TB, 0, s>>>(P, means, (const int*)ctx->bounds.p, (unsigned*)ctx->keys_a.p,

@@ -71,6 +71,8 @@ struct lrt_ctx {
 
     // optional live per-kernel timing (LRT_OPT_KERNEL_TIMING): CUDA events around every launch, on the launch stream
     int opt_kernel_timing = 0;
+    cudaStream_t side_stream = nullptr;     // backward: gradient zero-fill beside the count / scan / prefix passes
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     struct TimedSpan { const char* name; cudaEvent_t a, b; };
     std::vector<TimedSpan> spans;           // spans of the calls since the last lrt_get_kernel_times
     std::vector<cudaEvent_t> event_pool;
