@@ -486,6 +486,8 @@ def run_b200(args, rank, world, local_rank):
             tk = tj.get("kernels", {})
             traffic = tk.get(dom, tk.get(dom + "2"))       # ncu names (k_wf_composite2 ...) -> span names
             step_traffic = tj.get("step_total")
+            if step_traffic:       # ncu lists kernels only: the gradient zero-fill of the backward (memsets, 58 floats per Gaussian) is added
+                step_traffic += P * (3 + 2 + 4 + 1 + 3 * (D + 1) ** 2) * 4
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
