@@ -247,10 +247,12 @@ int lrt_densify_rows(lrt_ctx* ctx, int P, const uint8_t* clone_mask, const uint8
  *   LRT_OPT_MORTON_BITS     32 = 32-bit keys, bits dealt to the axes so cells stay cubic (default); 63 = 21 bits/axis on
  *                           cubic cells; 30 = 10 bits/axis on the per-axis extent (takes effect at the next lrt_build)
  *   LRT_OPT_SORT_KEY_BITS   how many of the top bits of a 32-bit key the build's radix sort orders (16 = default, 24, 32): one 8-bit
- *                           pass each; surfels that agree on those bits keep the caller's order, results do not depend on it */
+ *                           pass each; surfels that agree on those bits keep the caller's order, results do not depend on it
+ *   LRT_OPT_BIN_CAP         candidate-bin capacity per ray: 0 = automatic (default), or a power of two in [512, 16384]. Candidates
+ *                           beyond it travel through the overflow list of the split passes; results do not depend on it */
 enum lrt_option { LRT_OPT_FORWARD_KERNEL = 1, LRT_OPT_RAY_GRID_WIDTH = 2, LRT_OPT_VECTOR_ATOMICS = 3, LRT_OPT_MORTON_BITS = 4,
                   LRT_OPT_BACKWARD_KERNEL = 5, LRT_OPT_WAVEFRONT_SHADE = 6, LRT_OPT_KERNEL_TIMING = 7,
-                  LRT_OPT_SORT_RAYS = 8, LRT_OPT_BEAM_CELL_PCT = 9, LRT_OPT_TRIANGLE_DEPTH = 10, LRT_OPT_SPLIT_FUSED = 11, LRT_OPT_SORT_KEY_BITS = 12 };
+                  LRT_OPT_SORT_RAYS = 8, LRT_OPT_BEAM_CELL_PCT = 9, LRT_OPT_TRIANGLE_DEPTH = 10, LRT_OPT_SPLIT_FUSED = 11, LRT_OPT_SORT_KEY_BITS = 12, LRT_OPT_BIN_CAP = 13 };
 int lrt_set_option(lrt_ctx* ctx, int option, int value);
 
 /* Introspection for tests / benchmarks (host pointers). */

@@ -41,7 +41,7 @@ int lrt_ctx_destroy(lrt_ctx* ctx)
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
-    DevBuf* bufs[] = {&ctx->leafq, &ctx->fit_ticket, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->rec_g, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
+    DevBuf* bufs[] = {&ctx->leafq, &ctx->fit_ticket, &ctx->wf_ov_pairs, &ctx->wf_ov_area, &ctx->rec, &ctx->nodes, &ctx->keys_a, &ctx->keys_b, &ctx->perm_a, &ctx->perm_b, &ctx->rec_g, &ctx->sort_tmp, &ctx->bounds, &ctx->counter,
                       &ctx->wf_rs, &ctx->wf_list_a, &ctx->wf_list_b, &ctx->wf_hit_count, &ctx->wf_bins, &ctx->wf_fb,
                       &ctx->wf_ids, &ctx->wf_keys, &ctx->wf_sort_tmp, &ctx->bw_ids, &ctx->bw_keys, &ctx->bw_sort_tmp,
                       &ctx->bw_off, &ctx->bw_rec_a, &ctx->bw_rec_b, &ctx->dn_pos, &ctx->dn_tmp, &ctx->sh_tab, &ctx->sp_cnt, &ctx->sp_rec, &ctx->sp_scan_tmp, &ctx->sp_hits, &ctx->bg_ang, &ctx->bg_cell_of, &ctx->bg_cells, &ctx->bg_sray, &ctx->bg_wide, &ctx->bg_plan,
@@ -195,6 +195,7 @@ int lrt_set_option(lrt_ctx* ctx, int option, int value)
     case LRT_OPT_KERNEL_TIMING: if (value != 0 && value != 1) break; ctx->opt_kernel_timing = value; return LRT_OK;
     case LRT_OPT_WAVEFRONT_SHADE: if (value < 0 || value > 3) break; ctx->opt_wavefront_shade = value; return LRT_OK;
     case LRT_OPT_BACKWARD_KERNEL: if (value < 0 || value > 2) break; ctx->opt_backward_kernel = value; return LRT_OK;
+    case LRT_OPT_BIN_CAP: if (value != 0 && (value < 512 || value > 16384 || (value & (value - 1)))) break; ctx->opt_bin_cap = value; return LRT_OK;
     case LRT_OPT_SORT_KEY_BITS: if (value != 16 && value != 24 && value != 32) break; ctx->opt_sort_key_bits = value; return LRT_OK;
     case LRT_OPT_MORTON_BITS: if (value != 30 && value != 32 && value != 63) break; ctx->opt_morton_bits = value; return LRT_OK;
     case LRT_OPT_VECTOR_ATOMICS: if (value != 0 && value != 1) break; ctx->opt_vector_atomics = value; return LRT_OK;

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) k_bg_angles(FwdArgs a, WfBufs w, BgBufs b
         w.hit_count[r] = 0;
         w.emax[r] = 0; w.nwild[r] = 0;
         w.ray_ids[r] = r;
+        if (w.ov_fill) w.ov_fill[r] = 0;
     }
     float hi = ok ? el : -4.0f, nlo = ok ? -el : -4.0f;
 #pragma unroll

@@ -29,6 +29,7 @@ struct lrt_ctx {
     bool built = false;
     float scale_modifier = 1.0f;
     DevBuf leafq;
+    DevBuf wf_ov_pairs, wf_ov_area; // split passes: candidates beyond a bin (overflow list, arena of per-ray areas)
     DevBuf fit_ticket;             // k_fit_top's last-block counter (zero between builds)
     DevBuf rec, nodes, keys_a, keys_b, perm_a, perm_b, rec_g, sort_tmp, bounds, counter;
     DevBuf wf_rs, wf_list_a, wf_list_b, wf_hit_count, wf_bins, wf_fb, wf_ids, wf_keys, wf_sort_tmp, bw_ids, bw_keys, bw_sort_tmp;   // wavefront forward workspace
@@ -63,6 +64,7 @@ struct lrt_ctx {
     int opt_vector_atomics = 1;   // backward: red.global.add.v4.f32 where alignment allows
     int opt_split_fused = 1;      // split passes: 1 = sort + slots in one warp-per-ray kernel (k_sp_warp), 0 = k_sp_sort + record stream + k_sp_slots
     int opt_triangle_depth = 0;   // split passes: hits and depths from the two fp32 proxy triangles (fp64 Moeller-Trumbore) instead of the analytic quad
+    int opt_bin_cap = 0;          // > 0: candidate-bin capacity per ray forced to this power of two (tests)
     int opt_sort_key_bits = 16;   // top bits of a 32-bit key the radix sort orders (8 per pass)
     int opt_morton_bits = 32;     // 32: 32-bit cubic-cell keys (default); 63: 21 bits/axis on cubic cells; 30: 10 bits/axis, per-axis extent
     int fwd_blocks_per_sm = 0, g8_blocks_per_sm = 0, num_sms = 0;
@@ -115,7 +117,7 @@ struct lrt_ctx {
     }
     size_t total_bytes() const
     {
-        return leafq.cap + fit_ticket.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
+        return leafq.cap + fit_ticket.cap + wf_ov_pairs.cap + wf_ov_area.cap + rec.cap + nodes.cap + keys_a.cap + keys_b.cap + perm_a.cap + perm_b.cap + rec_g.cap + sort_tmp.cap + bounds.cap + counter.cap + wf_rs.cap + wf_list_a.cap + wf_list_b.cap +
                wf_hit_count.cap + wf_bins.cap + wf_fb.cap + wf_ids.cap + wf_keys.cap + wf_sort_tmp.cap + bw_ids.cap + bw_keys.cap + bw_sort_tmp.cap +
                bg_ang.cap + bg_cell_of.cap + bg_cells.cap + bg_sray.cap + bg_wide.cap + bg_plan.cap +
                bw_off.cap + bw_rec_a.cap + bw_rec_b.cap + sp_cnt.cap + sp_rec.cap + sp_scan_tmp.cap + sp_hits.cap + dn_pos.cap + dn_tmp.cap + sh_tab.cap + ch[0].bytes() + ch[1].bytes() + ch_tmp.cap + ch_bounds.cap + ch_keys_a.cap + ch_keys_b.cap + ch_idx_a.cap + ch_idx_b.cap;

@@ -560,13 +560,24 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
             LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_a, sizeof(uint2) * (size_t)cap_items));
             LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_list_b, sizeof(uint2) * (size_t)cap_items));
         }
-        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_hit_count, sizeof(int) * 3 * (size_t)R));
-        // bin capacity: 8192 candidates per ray while that stays under ~6 GB (4096 at one Waymo frame), never below what the
-        // shared-memory sort takes
-        int hcap = 2 * WF_HCAP_MAX;                                     // 16384 candidates per ray for patches of up to ~49 k rays
-        while (hcap > WF_HCAP && (size_t)R * hcap * sizeof(unsigned long long) > ((size_t)6 << 30)) hcap >>= 1;
+        LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_hit_count, sizeof(int) * 5 * (size_t)R));
+        // Bin capacity. The split passes take candidates beyond a bin through the overflow list (WfBufs::ov_pairs), so their bins
+        // only need to hold the usual ray: 16384 entries for small patches, halved while the array is above 1.5 GB (1024 at one
+        // Waymo frame: 1.4 GB; a full street-scene ray carries ~40 candidates, a grazing one several hundred). The other
+        // compositing forms drop a ray beyond its bin to the per-ray fallback and keep the 6 GB limit (4096 at one Waymo frame).
+        const bool ov_active = ctx->opt_wavefront_shade == 3;
+        int hcap = 2 * WF_HCAP_MAX;
+        while (hcap > WF_HCAP && (size_t)R * hcap * sizeof(unsigned long long) > (ov_active ? (size_t)3 << 29 : (size_t)6 << 30)) hcap >>= 1;
+        if (ctx->opt_bin_cap > 0) hcap = ctx->opt_bin_cap;             // LRT_OPT_BIN_CAP (tests: force the overflow route)
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_bins, sizeof(unsigned long long) * (size_t)R * hcap));
         w.hcap = hcap;
+        w.ov_pairs = nullptr; w.ov_pair_cap = 0; w.ov_area = nullptr; w.ov_area_cap = 0; w.ov_base = nullptr; w.ov_fill = nullptr;
+        if (ov_active) {
+            w.ov_pair_cap = 1 << 22; w.ov_area_cap = 1 << 23;         // 4 M pairs (64 MB), 8 M keys (64 MB)
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_ov_pairs, sizeof(uint4) * (size_t)w.ov_pair_cap));
+            LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_ov_area, sizeof(unsigned long long) * (size_t)w.ov_area_cap));
+            w.ov_pairs = (uint4*)ctx->wf_ov_pairs.p; w.ov_area = (unsigned long long*)ctx->wf_ov_area.p;
+        }
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_fb, sizeof(int) * (size_t)R * 3));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_ids, sizeof(int) * (size_t)R * 2));
         LRT_CUDA_TRY(ctx, ctx->reserve(ctx->wf_keys, sizeof(int) * (size_t)R));
@@ -574,6 +585,7 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
         LRT_CUDA_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(int) * 16, s));
         w.rs = (RaySetup*)ctx->wf_rs.p; w.list_a = (uint2*)ctx->wf_list_a.p; w.list_b = (uint2*)ctx->wf_list_b.p;
         w.cap_items = (int)cap_items; w.counts = (int*)ctx->counter.p; w.hit_count = (int*)ctx->wf_hit_count.p; w.emax = w.hit_count + R; w.nwild = w.hit_count + 2 * (size_t)R;
+        if (ov_active) { w.ov_base = w.hit_count + 3 * (size_t)R; w.ov_fill = w.hit_count + 4 * (size_t)R; }
         w.bins = (unsigned long long*)ctx->wf_bins.p; w.fb_list = (int*)ctx->wf_fb.p; w.big_list = (int*)ctx->wf_fb.p + R;
         w.ov_list = (int*)ctx->wf_fb.p + 2 * (size_t)R;
         w.ray_ids = (int*)ctx->wf_ids.p; w.order = nullptr;
@@ -671,10 +683,12 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                     // one warp per ray: sort + the rounds' slot logic, no record stream (lrt_split.cuh)
                     ctx->span_begin("k_sp_warp", s);
                     k_sp_warp<<<min((R + 3) / 4, ctx->num_sms * 24), 128, 0, s>>>(bv, a, w);
-                    {
-                        const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
+                    {   // bins beyond 512 candidates, and the rays with candidates on the overflow list: one block sorts, one warp walks
+                        const int smem_keys = 2 * WF_HCAP_MAX;
+                        const size_t smem = sizeof(unsigned long long) * (size_t)smem_keys;
                         LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
+                        k_ov_scatter<<<ctx->num_sms, 256, 0, s>>>(w);
+                        k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w, smem_keys);
                         k_sp_big<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
                     }
                     ctx->span_end(s);
@@ -683,10 +697,12 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                     k_sp_counts<<<(R + 1 + 255) / 256, 256, 0, s>>>(R, w, sp);
                     LRT_CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ctx->sp_scan_tmp.p, tb, (const int*)sp.ccnt, sp.cbase, R + 1, s));
                     k_sp_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(bv, a, w, sp);
-                    {   // the few bins beyond 512 candidates: one block each (sort in place, then gather)
-                        const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
+                    {   // the few bins beyond 512 candidates (and rays with an overflow list): one block each sorts, one warp walks
+                        const int smem_keys = 2 * WF_HCAP_MAX;
+                        const size_t smem = sizeof(unsigned long long) * (size_t)smem_keys;
                         LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
+                        k_ov_scatter<<<ctx->num_sms, 256, 0, s>>>(w);
+                        k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w, smem_keys);
                         k_sp_big<<<ctx->num_sms, 128, 0, s>>>(bv, a, w);
                     }
                     ctx->span_end(s);
@@ -706,14 +722,14 @@ int lrt_forward_impl(lrt_ctx* ctx, int R, const float* ray_o, int ray_o_stride, 
                 else k_sp_colour<0><<<dim3((R + 255) / 256, 16), 256, 0, s>>>(a);
                 ctx->span_end(s);
                 ctx->span_begin("k_sp_fold", s); k_sp_fold<<<(R + 127) / 128, 128, 0, s>>>(a); ctx->span_end(s);
-                ctx->launches += 9;
+                ctx->launches += 10;
             } else {
                 ctx->span_begin("k_wf_sort", s);
                 k_wf_sort<<<min((R + 3) / 4, ctx->num_sms * 16), 128, 0, s>>>(a, w);
                 {   // the few bins beyond 512 candidates: one block each, keys in dynamic shared memory (64 KB at hcap = 8192)
                     const size_t smem = sizeof(unsigned long long) * (size_t)w.hcap;
                     LRT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_wf_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w);
+                    k_wf_sort_big<<<ctx->num_sms, 256, smem, s>>>(a, w, w.hcap);
                 }
                 ctx->span_end(s);
                 ctx->launches += 1;

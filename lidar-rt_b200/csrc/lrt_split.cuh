@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(128) k_sp_sort(BvhView bvh, FwdArgs a, WfBufs 
         const int n = sp.ccnt[r];
         if (n <= 0) {                                              // empty, handed to the fallback, or longer than WF_HCAP:
             const int hc = w.hit_count[r];                         // the latter are sorted by k_wf_sort_big and walked by k_sp_big
-            if (lane == 0 && !(hc & WF_TAINT) && hc > WF_HCAP && hc <= w.hcap) w.big_list[atomicAdd(w.counts + 10, 1)] = r;
+            if (!(hc & WF_TAINT) && hc > w.hcap) wf_claim_area(w, r, hc, lane);        // k_sp_slots reads ov_base: -1 = fallback
+            else if (lane == 0 && !(hc & WF_TAINT) && hc > WF_HCAP) w.big_list[atomicAdd(w.counts + 10, 1)] = r;
             continue;
         }
         const long long base = sp.cbase[r];
@@ -443,10 +444,11 @@ __global__ void __launch_bounds__(128, LRT_WARP_MIN_BLOCKS) k_sp_warp(BvhView bv
                 if (lane == 0) sp_cp_async4(&s_hc[wib], w.hit_count + r2);
             }
         }
-        if ((hc & WF_TAINT) || hc > w.hcap) {                      // bin overflow: per-ray fallback
+        if ((hc & WF_TAINT) || (hc > w.hcap && !wf_claim_area(w, r, hc, lane))) {      // dropped candidates / no room for its overflow: per-ray fallback
             if (lane == 0) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; a.hit_cnt[r] = 0; }
             continue;
         }
+        if (hc > w.hcap) continue;                                 // listed by wf_claim_area: sorted by k_wf_sort_big, walked by k_sp_big
         if (hc > WF_HCAP) {                                        // sorted by k_wf_sort_big, walked by k_sp_big
             if (lane == 0) w.big_list[atomicAdd(w.counts + 10, 1)] = r;
             continue;
@@ -515,9 +517,9 @@ __global__ void __launch_bounds__(128) k_sp_big(BvhView bvh, FwdArgs a, WfBufs w
     const int nbig = min(w.counts[10], a.R);
     for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nbig; b += (gridDim.x * blockDim.x) >> 5) {
         const int r = w.big_list[b];
-        const int n = min(w.hit_count[r] & (WF_TAINT - 1), w.hcap);
+        const int n = w.hit_count[r] & (WF_TAINT - 1);             // beyond hcap: the ray's area of the overflow arena
         const float em = w.nwild[r] > 0 ? __int_as_float(0x7f800000) : __int_as_float(w.emax[r]);
-        wf_shade_ray(w.bins + (size_t)r * w.hcap, n, r, em, bvh, a, lane);
+        wf_shade_ray(wf_big_keys(w, r, n), n, r, em, bvh, a, lane);
         __syncwarp(0xffffffffu);
     }
 }
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(128, LRT_SLOTS_MIN_BLOCKS) k_sp_slots(FwdArgs 
     for (int s = blockIdx.x * blockDim.x + tx; s < a.R; s += gridDim.x * blockDim.x) {
         const int r = w.order ? w.order[s] : s;
         const int hc = w.hit_count[r];
-        if ((hc & WF_TAINT) || hc > w.hcap) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; a.hit_cnt[r] = 0; continue; }
+        if ((hc & WF_TAINT) || (hc > w.hcap && !(w.ov_pairs && w.ov_base[r] >= 0))) { w.fb_list[atomicAdd(w.counts + 8, 1)] = r; a.hit_cnt[r] = 0; continue; }
         if (hc > WF_HCAP) continue;                                // done by k_sp_big, one warp per ray
         const int n = hc;
         const float em = __int_as_float(w.emax[r]);

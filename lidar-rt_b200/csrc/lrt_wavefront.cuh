@@ -43,7 +43,20 @@ struct WfBufs {
     int* ov_list;                   // (R) split passes: rays whose contributing-hit list overflowed `cap`
     int* ray_ids;                   // (R) identity, input of the by-length sort
     const int* order;               // (R) rays sorted by descending candidate count, or nullptr (tile order)
+    // Candidates beyond a bin's capacity (split passes; nullptr elsewhere: such a ray then takes the per-ray fallback). They are
+    // appended as (ray, key) pairs to one list; a ray that has some gets an AREA of the arena (k_sp_warp / k_sp_sort: its bin is
+    // copied there, k_ov_scatter adds its pairs), which k_wf_sort_big sorts and k_sp_big walks like any long bin.
+    uint4* ov_pairs; int ov_pair_cap;          // counts[14] = pairs appended
+    unsigned long long* ov_area; int ov_area_cap;      // counts[15] = keys handed out (areas are padded to a power of two)
+    int* ov_base;                   // (R) first key of the ray's area, -1: none (the ray takes the fallback)
+    int* ov_fill;                   // (R) pairs of the ray already placed
 };
+
+// keys of a ray of the long-bin list: its bin, or its area of the overflow arena
+__device__ __forceinline__ unsigned long long* wf_big_keys(const WfBufs& w, int r, int hc)
+{
+    return hc > w.hcap ? w.ov_area + w.ov_base[r] : w.bins + (size_t)r * w.hcap;
+}
 
 __global__ void __launch_bounds__(256) k_wf_setup(FwdArgs a, WfBufs w)
 {
@@ -58,6 +71,7 @@ __global__ void __launch_bounds__(256) k_wf_setup(FwdArgs a, WfBufs w)
     w.hit_count[r] = 0;
     w.emax[r] = 0; w.nwild[r] = 0;
     w.ray_ids[r] = r;
+    if (w.ov_fill) w.ov_fill[r] = 0;
 }
 
 // One (ray, node) item per thread at `level` >= 1. in == nullptr: the implicit root list (every ray, node 0)
@@ -137,7 +151,13 @@ __device__ __forceinline__ void wf_append(const WfBufs& w, int ray, float t, int
 {
     const bool wild = e >= LRT_ERR_CAP;
     const int pos = atomicAdd(w.hit_count + ray, 1) & (WF_TAINT - 1);
-    if (pos < w.hcap) w.bins[(size_t)ray * w.hcap + pos] = ((unsigned long long)(wild ? 0u : __float_as_uint(t)) << 32) | (unsigned)g;
+    const unsigned long long key = ((unsigned long long)(wild ? 0u : __float_as_uint(t)) << 32) | (unsigned)g;
+    if (pos < w.hcap) w.bins[(size_t)ray * w.hcap + pos] = key;
+    else if (w.ov_pairs) {                               // beyond the bin: the overflow list; a dropped pair taints the ray (fallback)
+        const int j = atomicAdd(w.counts + 14, 1);
+        if (j < w.ov_pair_cap) w.ov_pairs[j] = make_uint4((unsigned)ray, 0u, (unsigned)(key & 0xffffffffull), (unsigned)(key >> 32));
+        else atomicOr(w.hit_count + ray, WF_TAINT);
+    }
     if (wild) atomicAdd(w.nwild + ray, 1);
     else if (e > LRT_ERR_FLOOR) atomicMax(w.emax + ray, __float_as_int(e));
 }
@@ -515,31 +535,73 @@ __global__ void __launch_bounds__(128) k_wf_sort(FwdArgs a, WfBufs w)
 
 // Bins beyond WF_HCAP candidates (a ray skimming a wall or a vehicle's side: hundreds to thousands), listed by k_wf_sort: one
 // 256-thread block per bin, bitonic sort of up to hcap (<= 8192) keys in dynamic shared memory (8 B x hcap).
-__global__ void __launch_bounds__(256) k_wf_sort_big(FwdArgs a, WfBufs w)
+__global__ void __launch_bounds__(256) k_wf_sort_big(FwdArgs a, WfBufs w, int smem_keys)
 {
     extern __shared__ unsigned long long s_big[];
     const int nbig = min(w.counts[10], a.R);
     for (int b = blockIdx.x; b < nbig; b += gridDim.x) {
         const int r = w.big_list[b];
-        const int n = min(w.hit_count[r] & (WF_TAINT - 1), w.hcap);
-        unsigned long long* bin = w.bins + (size_t)r * w.hcap;
-        int m = 2 * WF_HCAP; while (m < n) m <<= 1;                // <= hcap: hcap is a power of two
-        for (int i = threadIdx.x; i < m; i += blockDim.x) s_big[i] = i < n ? bin[i] : LRT_KEY_EMPTY;
+        const int hc = w.hit_count[r] & (WF_TAINT - 1);
+        const bool ov = hc > w.hcap;                                // keys in the overflow arena (area padded to a power of two)
+        const int n = ov ? hc : min(hc, w.hcap);
+        unsigned long long* bin = wf_big_keys(w, r, hc);
+        int m = 2 * WF_HCAP; while (m < n) m <<= 1;
+        // the block sorts in shared memory what fits there; a longer list (only ever an overflow area, which has its m slots)
+        // in place in global memory, one barrier per stage
+        unsigned long long* k = m <= smem_keys ? s_big : bin;
+        if (k == s_big) { for (int i = threadIdx.x; i < m; i += blockDim.x) s_big[i] = i < n ? bin[i] : LRT_KEY_EMPTY; }
+        else { for (int i = n + threadIdx.x; i < m; i += blockDim.x) bin[i] = LRT_KEY_EMPTY; }
         __syncthreads();
         for (int size = 2; size <= m; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int ls = 31 - __clz(size) - 1; ls >= 0; ls--) {
+                const int stride = 1 << ls;
                 for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
-                    const int lo = ((i / stride) * stride * 2) + (i % stride), hi = lo + stride;
-                    const unsigned long long x = s_big[lo], y = s_big[hi];
+                    const int lo = ((i >> ls) << (ls + 1)) + (i & (stride - 1)), hi = lo + stride;
+                    const unsigned long long x = k[lo], y = k[hi];
                     const bool up = ((lo & size) == 0);
-                    if ((x > y) == up) { s_big[lo] = y; s_big[hi] = x; }
+                    if ((x > y) == up) { k[lo] = y; k[hi] = x; }
                 }
                 __syncthreads();
             }
         }
-        for (int i = threadIdx.x; i < n; i += blockDim.x) bin[i] = s_big[i];
+        if (k == s_big) for (int i = threadIdx.x; i < n; i += blockDim.x) bin[i] = s_big[i];
         __syncthreads();
     }
+}
+
+// (ray, key) pairs of the overflow list -> behind the copy of the ray's bin in its area
+__global__ void __launch_bounds__(256) k_ov_scatter(WfBufs w)
+{
+    const int n = min(w.counts[14], w.ov_pair_cap);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint4 pr = w.ov_pairs[j];
+        const int r = (int)pr.x;
+        if (w.hit_count[r] & WF_TAINT) continue;
+        const int base = w.ov_base[r];
+        if (base < 0) continue;                                    // no room in the arena: the ray took the fallback
+        const int at = w.hcap + atomicAdd(w.ov_fill + r, 1);
+        w.ov_area[(size_t)base + at] = ((unsigned long long)pr.w << 32) | pr.z;
+    }
+}
+
+// A ray with more candidates than its bin holds (one warp, all lanes): claim an area of the arena, copy the bin there and put the
+// ray on the long-bin list. False: no overflow handling here, or the arena is full -> the caller hands the ray to the fallback.
+__device__ __forceinline__ bool wf_claim_area(const WfBufs& w, int r, int hc, int lane)
+{
+    if (!w.ov_pairs) return false;
+    int m = 2 * WF_HCAP; while (m < hc) m <<= 1;
+    int base = -1;
+    if (lane == 0) {
+        base = atomicAdd(w.counts + 15, m);
+        if (base < 0 || base > w.ov_area_cap - m) base = -1;
+        w.ov_base[r] = base;
+        if (base >= 0) w.big_list[atomicAdd(w.counts + 10, 1)] = r;
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base < 0) return false;
+    const unsigned long long* bin = w.bins + (size_t)r * w.hcap;
+    for (int i = lane; i < w.hcap; i += 32) w.ov_area[(size_t)base + i] = bin[i];
+    return true;
 }
 
 #ifndef LRT_COMPOSITE_MIN_BLOCKS

@@ -21,7 +21,7 @@ LRT_FLAG_FIX_BG_GRAD = 1
 NUM_CHANNELS = 9
 DEFAULT_HIT_CAP = 256          # contributing hits recorded per ray for the backward replay (rays beyond it are re-traced)
 OPT_FORWARD_KERNEL, OPT_RAY_GRID_WIDTH, OPT_VECTOR_ATOMICS, OPT_MORTON_BITS, OPT_BACKWARD_KERNEL, OPT_WAVEFRONT_SHADE, OPT_KERNEL_TIMING, OPT_SORT_RAYS, OPT_BEAM_CELL_PCT = 1, 2, 3, 4, 5, 6, 7, 8, 9
-OPT_TRIANGLE_DEPTH, OPT_SPLIT_FUSED, OPT_SORT_KEY_BITS = 10, 11, 12
+OPT_TRIANGLE_DEPTH, OPT_SPLIT_FUSED, OPT_SORT_KEY_BITS, OPT_BIN_CAP = 10, 11, 12, 13
 
 
 class LrtError(RuntimeError):

@@ -326,6 +326,57 @@ def test_very_long_candidate_bins_and_bin_overflow(ctx, oracle32, n_stack):
     assert_close(res["out"], f["out"], ORC_ATOL, ORC_RTOL, "forward")
 
 
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("n_stack,bin_cap", [(700, 512), (3000, 512), (3000, 2048), (9000, 1024), (20000, 512)])
+def test_candidates_beyond_the_bin_take_the_overflow_list(ctx, n_stack, bin_cap, fused):
+    """A ray with more candidates than its bin holds (LRT_OPT_BIN_CAP forces small bins) must not drop to the per-ray fallback:
+    the excess travels through the overflow list into the ray's area of the arena, is sorted by a block (in shared memory up to
+    16384 keys, in global memory beyond) and walked by a warp. Outputs, hit lists and slot counts must equal, bit for bit, what the
+    same frame gives with bins that hold everything (and, through test_very_long_candidate_bins_and_bin_overflow, the oracle)."""
+    import ctypes
+    from lidar_rt_b200 import native
+    rng = np.random.default_rng(n_stack)
+    P = n_stack + 500
+    means = np.zeros((P, 3), np.float32)
+    means[:n_stack, 0] = 5.0 + (0.002 if n_stack <= 9000 else 0.0009) * np.arange(n_stack); means[:n_stack, 1:] = 0.01 * rng.standard_normal((n_stack, 2))
+    means[n_stack:] = rng.uniform(-20, 20, (P - n_stack, 3)) + np.array([30, 0, 0], np.float32)
+    scales = np.full((P, 2), 0.4, np.float32)
+    rots = np.tile(np.array([np.cos(np.pi / 4), 0, np.sin(np.pi / 4), 0], np.float32), (P, 1))      # normal along +x
+    rots[n_stack:] = rng.standard_normal((P - n_stack, 4))
+    opac = np.full((P, 1), 0.012 if n_stack <= 9000 else 0.006, np.float32)
+    shs = (0.05 * rng.standard_normal((P, 16, 3))).astype(np.float32); shs[:, 0, :] = 0.5
+    sc = dict(means=means, scales=scales, rots=rots, opac=opac, shs=shs)
+    yy, zz = np.meshgrid(np.linspace(-0.03, 0.03, 8), np.linspace(-0.03, 0.03, 8), indexing="ij")
+    d = np.stack([np.ones_like(yy), yy, zz], -1).astype(np.float32); d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    o = np.zeros((1, 3), np.float32)
+    counters = lambda: (lambda c: (ctx.lib.lrt_debug_counters(ctx._h, c), list(c))[1])((ctypes.c_int * 16)())
+    try:
+        ctx.set_option(native.OPT_SPLIT_FUSED, fused)
+        ctx.set_option(native.OPT_BIN_CAP, 16384)
+        ref = run_cuda(ctx, o, d, sc, 3, cap=256)
+        c_ref = counters()
+        ctx.set_option(native.OPT_BIN_CAP, bin_cap)
+        res = run_cuda(ctx, o, d, sc, 3, cap=256)
+        c = counters()
+    finally:
+        ctx.set_option(native.OPT_BIN_CAP, 0); ctx.set_option(native.OPT_SPLIT_FUSED, 1)
+    assert res["slot_cnt"].max() >= 256
+    assert c[14] > 0 and c[15] > 0, f"the overflow list must have been used (counters {c})"
+    if n_stack <= 16384:
+        assert c_ref[14] == 0
+    assert c[8] == c_ref[8], f"rays handed to the per-ray fallback: {c[8]} with small bins, {c_ref[8]} with large ones"
+    if n_stack <= 16384:
+        assert c[8] == 0
+    _same_forward(res, ref, f"stack of {n_stack}, bins of {bin_cap}")
+    if n_stack > 16384:                                   # beyond any bin: the large-bin run used the overflow list too; check against per-ray traversal
+        try:
+            ctx.set_option(native.OPT_FORWARD_KERNEL, 0)
+            ref0 = run_cuda(ctx, o, d, sc, 3, cap=256)
+        finally:
+            ctx.set_option(native.OPT_FORWARD_KERNEL, 4)
+        _same_forward(res, ref0, f"stack of {n_stack} vs per-ray traversal")
+
+
 @pytest.mark.parametrize("P,H,W,seed", [(200_000, 16, 512, 5), (30_000, 32, 96, 7)])
 def test_triangle_depth_mode_vs_triangle_oracle(ctx, oracle32, P, H, W, seed):
     """LRT_OPT_TRIANGLE_DEPTH: hits and depths from the reference's literal proxy (two fp32 triangles per Gaussian, fp64
